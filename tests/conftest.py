@@ -1,0 +1,31 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
+    meta = json.loads(str(z['meta']))
+    return meta, {k: z[k] for k in z.files if k != 'meta'}
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _oracle_built():
+    # the oracle's C part is test infrastructure; build it on demand
+    so = os.path.join(ROOT, 'oracle', '_build', 'liboracle.so')
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
