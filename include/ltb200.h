@@ -1,0 +1,128 @@
+/* ltb200.h -- C ABI of the B200-native masked-reduction engine (libltb200.so).
+ *
+ * Drop-in boundary for LiberTEM's ApplyMasksUDF / CoMUDF / SumUDF / SumSigUDF hot path.
+ * Every entry point replaces one seam of the reference (paths relative to the LiberTEM
+ * source tree, src/libertem/...):
+ *
+ *   ltb200_masks_dense      <- ApplyMasksEngine.process_flat / _process_flat_{torch,standard}
+ *                              (udf/masks.py:31-83) + the `+=` of ApplyMasksUDF.process_tile
+ *                              (udf/masks.py:383-392); CoMUDF.process_tile (udf/com.py:577-582)
+ *                              is the same call with the 3 CoM mask rows appended; SumSigUDF
+ *                              (udf/sumsigudf.py:28-38) is an all-ones mask row.
+ *   ltb200_masks_dense_f64  <- the same seam when np.result_type(input, mask) is float64
+ *                              (udf/masks.py:360-368 dtype rule).
+ *   ltb200_masks_csr        <- ApplyMasksEngine._process_flat_spsp -> rmatmul
+ *                              (udf/masks.py:68-69, common/numba/__init__.py:90-184).
+ *   ltb200_frame_pass       <- one fused pass for [SumUDF, SumSigUDF, ApplyMasksUDF(sparse)]:
+ *                              udf/sum.py:44-49, udf/sumsigudf.py:28-38, udf/masks.py:383-392.
+ *   ltb200_radial_fourier   <- ApplyMasksUDF with radial_mask_factory masks
+ *                              (analysis/radialfourier.py:106-146,184-194).
+ *   ltb200_synth_fill       <- test/bench data source standing in for MemoryDataSet contents
+ *                              (io/dataset/memory.py:202-452); twin of oracle/synth.py.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller (torch tensors on the host
+ *     side); the library allocates nothing persistent.  `workspace` is caller-provided
+ *     device scratch of at least ltb200_*_workspace(...) bytes (may be NULL when that is 0).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous w.r.t. the host.
+ *   - Return value: 0 on success, negative LTB_ERR_* otherwise; ltb200_last_error() gives a
+ *     thread-local message.  Nothing throws, nothing falls back to the CPU.
+ *   - Matrices are row-major; `ld_*` are leading dimensions in ELEMENTS.
+ */
+#ifndef LTB200_H
+#define LTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LTB_API __attribute__((visibility("default")))
+#else
+#define LTB_API
+#endif
+
+/* element types of input tiles (numpy dtype of the dataset / tile) */
+enum ltb200_dtype {
+    LTB_F32 = 0,
+    LTB_U16 = 1,
+    LTB_U8 = 2,
+    LTB_I16 = 3,
+    LTB_F64 = 4,
+    LTB_I32 = 5,
+    LTB_U32 = 6,
+    LTB_I64 = 7,
+    LTB_U64 = 8,
+    LTB_I8 = 9
+};
+
+enum ltb200_error {
+    LTB_OK = 0,
+    LTB_ERR_ARG = -1,         /* invalid argument (shape, alignment, NULL pointer) */
+    LTB_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+    LTB_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+    LTB_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+LTB_API int ltb200_abi_version(void);
+LTB_API const char* ltb200_last_error(void);
+
+/* sm count / compute capability / opt-in shared memory of `device` */
+LTB_API int ltb200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
+                       int64_t* smem_optin_bytes);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense masked reduction (K1):  out[f, m] (+)= sum_k tile[f, k] * masks[m, k]
+ *   tile   : (n_frames, sig_size) of `tile_dtype`, leading dimension ld_tile
+ *   masks  : (n_masks, sig_size) float32 -- the physical layout of the reference's
+ *            F-ordered (sig_size, n_masks) mask matrix (common/container.py:86-91)
+ *   out    : (n_frames, n_masks) float32, leading dimension ld_out
+ *   accumulate: 0 -> out = result, 1 -> out += result (partial sig tiles)
+ *   sig_sum: optional (sig_size,) float32, sig_sum[k] += sum_f tile[f, k] (SumUDF), or NULL
+ * float32 arithmetic (FFMA), blocked accumulation (chains <= 512 terms).
+ * ------------------------------------------------------------------------------------- */
+LTB_API size_t ltb200_masks_dense_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
+                                    int with_sig_sum);
+LTB_API int ltb200_masks_dense(const void* tile, int tile_dtype, int64_t n_frames, int64_t sig_size,
+                       int64_t ld_tile, const float* masks, int n_masks, int64_t ld_masks,
+                       float* out, int64_t ld_out, int accumulate, float* sig_sum,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same contraction in float64 (int32/int64/float64 inputs or float64 masks). */
+LTB_API int ltb200_masks_dense_f64(const void* tile, int tile_dtype, int64_t n_frames,
+                           int64_t sig_size, int64_t ld_tile, const double* masks, int n_masks,
+                           int64_t ld_masks, double* out, int64_t ld_out, int accumulate,
+                           void* stream);
+
+/* which kernel the last ltb200_masks_dense call on this thread selected:
+ * 1 = TMA-staged FFMA kernel, 2 = generic kernel (diagnostics / tests) */
+LTB_API int ltb200_last_kernel(void);
+/* number of kernel launches issued by this library on this thread since the last reset */
+LTB_API int64_t ltb200_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------
+ * Sparse masked reduction (K2): masks given as CSC over (sig_size, n_masks), i.e. for each
+ * mask m the entries [indptr[m], indptr[m+1]) of (indices = pixel k ascending, values).
+ * out[f, m] (+)= sum_i tile[f, indices[i]] * values[i]
+ * ------------------------------------------------------------------------------------- */
+LTB_API int ltb200_masks_csc(const void* tile, int tile_dtype, int64_t n_frames, int64_t sig_size,
+                     int64_t ld_tile, const int32_t* indptr, const int32_t* indices,
+                     const float* values, int n_masks, float* out, int64_t ld_out,
+                     int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Synthetic data (twin of oracle/synth.py): fills dst[0..count) with value(start + i).
+ *   LTB_F32: uniform [0,1) (24-bit);  LTB_U16: Poisson(3) counts.
+ * ------------------------------------------------------------------------------------- */
+LTB_API int ltb200_synth_fill(void* dst, int dtype, int64_t start, int64_t count, uint32_t seed,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTB200_H */

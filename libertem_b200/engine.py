@@ -1,0 +1,133 @@
+"""Tensor-level wrappers over the C ABI (device pointers come from torch CUDA tensors).
+
+This is the seam of the reference's ``ApplyMasksEngine.process_flat``
+(src/libertem/udf/masks.py:31-83): two arrays in, ``(frames, masks)`` array out.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import get_lib, check
+
+_TORCH_DTYPES = {
+    torch.float32: _lib.LTB_F32, torch.uint16: _lib.LTB_U16, torch.uint8: _lib.LTB_U8,
+    torch.int16: _lib.LTB_I16, torch.float64: _lib.LTB_F64, torch.int32: _lib.LTB_I32,
+    torch.uint32: _lib.LTB_U32, torch.int64: _lib.LTB_I64, torch.uint64: _lib.LTB_U64,
+    torch.int8: _lib.LTB_I8,
+}
+
+_workspaces = {}
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device, nbytes):
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.LTB200Error(f'{name} must be a CUDA tensor (no CPU fallback)')
+
+
+def masks_dense(tile, masks, out=None, accumulate=False, sig_sum=None):
+    """``out[f, m] (+)= sum_k tile[f, k] * masks[m, k]`` on the GPU.
+
+    tile: (F, K) CUDA tensor (row stride arbitrary, unit inner stride); masks: (M, K) float32
+    (or float64 -> float64 path).  Returns ``out`` (F, M).
+    """
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    _require_cuda(masks, 'masks')
+    if tile.dim() != 2 or masks.dim() != 2 or tile.shape[1] != masks.shape[1]:
+        raise ValueError(f'shape mismatch: tile {tuple(tile.shape)} masks {tuple(masks.shape)}')
+    if tile.dtype not in _TORCH_DTYPES:
+        raise TypeError(f'unsupported tile dtype {tile.dtype}')
+    if tile.shape[1] > 0 and tile.stride(1) != 1:
+        tile = tile.contiguous()
+    if masks.shape[1] > 0 and masks.stride(1) != 1:
+        masks = masks.contiguous()
+    F, K = tile.shape
+    M = masks.shape[0]
+    f64 = masks.dtype == torch.float64
+    res_dtype = torch.float64 if f64 else torch.float32
+    if not f64 and masks.dtype != torch.float32:
+        raise TypeError(f'masks must be float32 or float64, got {masks.dtype}')
+    if out is None:
+        out = torch.zeros((F, M), dtype=res_dtype, device=tile.device)
+        accumulate = False
+    else:
+        _require_cuda(out, 'out')
+        if out.shape != (F, M) or out.dtype != res_dtype or (M > 1 and out.stride(1) != 1):
+            raise ValueError('out must be (F, M) of the result dtype with unit inner stride')
+    ld_tile = tile.stride(0) if F > 1 else max(K, 1)
+    ld_masks = masks.stride(0) if M > 1 else max(K, 1)
+    ld_out = out.stride(0) if F > 1 else max(M, 1)
+    with torch.cuda.device(tile.device):
+        st = _stream_ptr(tile.device)
+        if f64:
+            if sig_sum is not None:
+                raise _lib.LTB200Error('sig_sum is only fused on the float32 path')
+            check(lib.ltb200_masks_dense_f64(
+                tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, K, ld_tile, masks.data_ptr(), M,
+                ld_masks, out.data_ptr(), ld_out, int(bool(accumulate)), st))
+            return out
+        need = lib.ltb200_masks_dense_workspace(F, K, M, int(sig_sum is not None))
+        ws = _workspace(tile.device, need) if need else None
+        if sig_sum is not None:
+            _require_cuda(sig_sum, 'sig_sum')
+            if sig_sum.dtype != torch.float32 or sig_sum.numel() != K or not sig_sum.is_contiguous():
+                raise ValueError('sig_sum must be a contiguous float32 tensor of sig_size')
+        check(lib.ltb200_masks_dense(
+            tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, K, ld_tile,
+            masks.data_ptr(), M, ld_masks, out.data_ptr(), ld_out, int(bool(accumulate)),
+            sig_sum.data_ptr() if sig_sum is not None else None,
+            ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, st))
+    return out
+
+
+def synth_fill(shape, dtype, seed, device, start=0):
+    """Device twin of oracle.synth.dataset: counter-based synthetic data."""
+    lib = get_lib()
+    tdt = {np.dtype('float32'): torch.float32, np.dtype('uint16'): torch.uint16}[np.dtype(dtype)]
+    out = torch.empty(tuple(shape), dtype=tdt, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.ltb200_synth_fill(out.data_ptr(), _TORCH_DTYPES[tdt], int(start), out.numel(),
+                                    int(seed) & 0xFFFFFFFF, _stream_ptr(out.device)))
+    return out
+
+
+def last_kernel():
+    return get_lib().ltb200_last_kernel()
+
+
+def launch_count(reset=False):
+    return get_lib().ltb200_launch_count(int(reset))
+
+
+def masks_csc(tile, indptr, indices, values, n_masks, out=None, accumulate=False):
+    """Sparse masks as CSC over (sig_size, n_masks): ``out[f, m] (+)= sum_i tile[f, idx_i] * v_i``."""
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    if tile.dim() != 2:
+        raise ValueError('tile must be 2D (frames, sig_size)')
+    if tile.shape[1] > 0 and tile.stride(1) != 1:
+        tile = tile.contiguous()
+    F, K = tile.shape
+    if out is None:
+        out = torch.zeros((F, n_masks), dtype=torch.float32, device=tile.device)
+        accumulate = False
+    ld_tile = tile.stride(0) if F > 1 else max(K, 1)
+    ld_out = out.stride(0) if F > 1 else max(n_masks, 1)
+    with torch.cuda.device(tile.device):
+        check(lib.ltb200_masks_csc(
+            tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, K, ld_tile, indptr.data_ptr(),
+            indices.data_ptr(), values.data_ptr(), int(n_masks), out.data_ptr(), ld_out,
+            int(bool(accumulate)), _stream_ptr(tile.device)))
+    return out
