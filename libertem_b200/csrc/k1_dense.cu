@@ -7,15 +7,17 @@
 // The contraction is a tall-skinny GEMM (n_masks <= 24 per launch) that is HBM-bound: each
 // frame element is read from HBM exactly once.  Design (sm_100a):
 //   * persistent CTAs (one per SM), work item = (64-frame block, K-split)
-//   * warp 8 = TMA producer: 2D tiled cp.async.bulk.tensor loads of a [64 frames x 128 px]
+//   * warps 0..3 = producer warpgroup (setmaxnreg.dec; one elected lane): 2D tiled cp.async.bulk.tensor loads of a [64 frames x 128 px]
 //     fp32 data box (evict_first) and the matching [n_masks x 128 px] mask box (evict_last,
 //     L2-resident) into a multi-stage shared-memory ring, completion on mbarriers
-//   * warps 0..7 = FFMA consumers.  A lane is (fl = lane/8, q = lane%8): it owns 8 frames
-//     (rows fg*32 + j*4 + fl) and 4 consecutive pixels per step.  The 8 lanes of a quarter warp
+//   * warps 4..11 = FMA consumers (setmaxnreg.inc 232).  A lane is (fl = lane/8, q = lane%8): it owns 4 frames
+//     (rows fg*16 + j*4 + fl) and 4 consecutive pixels per step.  The 8 lanes of a quarter warp
 //     read one contiguous 128 B row segment (conflict-free LDS.128); mask rows are read by
 //     broadcast (1 wavefront per mask per step), so shared memory traffic stays ~1x the data.
-//     acc[8][NM] registers; exact fp32 FMA (TF32 tensor cores cannot hold the 1e-5 parity
-//     tolerance without 3x splitting).
+//     acc[4][NM] float2 registers (even/odd pixel sums) updated with packed fma.rn.f32x2
+//     (FFMA2): exact fp32 FMA at half the issue slots and without the register-bank parity
+//     conflicts scalar FFMA has on float4 components (ncu: dispatch stalls, profiles/).
+//     TF32 tensor cores cannot hold the 1e-5 parity tolerance without 3x splitting.
 //   * blocked accumulation: every 256 terms the per-lane partial sums are transpose-reduced
 //     over the 8 pixel lanes (shuffles) into NM "total" registers, which bounds rounding error
 //     growth (sequential chains <= 256 + few hundred block adds) to ~1e-6 relative.
@@ -30,7 +32,8 @@ namespace ltb {
 constexpr int K1_FB = 64;          // frames per CTA tile
 constexpr int K1_KT = 128;         // pixels per pipeline chunk (512 B per frame row)
 constexpr int K1_CWARPS = 8;       // consumer warps
-constexpr int K1_THREADS = (K1_CWARPS + 1) * 32;
+constexpr int K1_PWARPS = 4;       // producer warpgroup (one elected lane issues TMA)
+constexpr int K1_THREADS = (K1_CWARPS + K1_PWARPS) * 32;
 constexpr int K1_MAX_STAGES = 8;
 constexpr int K1_CHAIN = 256;      // max sequential FMA chain per accumulator between flushes
 
@@ -69,10 +72,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
                     const __grid_constant__ CUtensorMap tm_mask, const K1Params p) {
     constexpr int NROWS = NM * MG;                 // mask rows in a stage
-    constexpr int KS = 4 / MG;                     // k-split across warps
+    constexpr int KS = 2 / MG;                     // k-split across warps
     constexpr int KW = K1_KT / KS;                 // pixels per warp per chunk
     constexpr int SPC = KW / 32;                   // steps per chunk
-    constexpr int FLUSH_EVERY = K1_CHAIN / (4 * SPC);
+    constexpr int FR = 4;                          // frames per lane
+    constexpr int FLUSH_EVERY = K1_CHAIN / (2 * SPC);   // 2 terms per accumulator per step
     constexpr size_t DATA_BYTES = (size_t)K1_FB * K1_KT * 4;
     constexpr size_t STAGE_BYTES = k1_stage_bytes(NROWS);
 
@@ -94,9 +98,10 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
     }
     __syncthreads();
 
-    if (warp == K1_CWARPS) {
-        // ===== TMA producer (one elected lane) =====
-        if (lane == 0) {
+    if (warp < K1_PWARPS) {
+        // ===== producer warpgroup: give registers back, one elected lane issues TMA =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
             prefetch_tmap(&tm_data);
             prefetch_tmap(&tm_mask);
             const uint64_t pol_stream = l2_policy_evict_first();
@@ -124,16 +129,21 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
         return;
     }
 
-    // ===== FFMA consumers =====
-    const int fg = warp / (MG * KS);
-    const int mg = (warp / KS) % MG;
-    const int ks = warp % KS;
+    // ===== FFMA2 consumers (two warpgroups, 232 registers per thread) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // cw = (fg, mg, ks): 16-frame group, mask group, pixel split.  lane = (fl, q).
+    const int cw = warp - K1_PWARPS;
+    const int fg = cw / (MG * KS);
+    const int mg = (cw / KS) % MG;
+    const int ks = cw % KS;
     const int fl = lane >> 3;
     const int q = lane & 7;
-    const int row_base = fg * 32 + fl;             // + j*4
+    const int row_base = fg * 16 + fl;             // + j*4
     const int kk_base = ks * KW + q * 4;           // + s*32
 
-    float acc[8][NM];
+    // acc[j][m] = (sum over even pixels, sum over odd pixels): packed fma.rn.f32x2 keeps both
+    // register banks busy without the parity conflicts scalar FFMA on float4 components has.
+    float2 acc[FR][NM];
     float tot[NM];
     uint32_t it = 0;
 
@@ -149,25 +159,27 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
         for (int m = 0; m < NM; m++) {
             tot[m] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[j][m] = 0.f;
+            for (int j = 0; j < FR; j++) acc[j][m] = make_float2(0.f, 0.f);
         }
         int since_flush = 0;
 
+        // blocked accumulation: fold the lane partials of the 8 pixel lanes into tot[]
+        // (transpose-reduce: 4*NM -> 2*NM -> NM values, then a 2-lane butterfly)
         auto flush = [&]() {
-            float v[8 * NM];
+            float v[FR * NM];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
+            for (int j = 0; j < FR; j++)
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
-                    v[j * NM + m] = acc[j][m];
-                    acc[j][m] = 0.f;
+                    v[j * NM + m] = acc[j][m].x + acc[j][m].y;
+                    acc[j][m] = make_float2(0.f, 0.f);
                 }
-            float r1[4 * NM], r2[2 * NM], r3[NM];
-            xreduce_half<8 * NM>(v, r1, (q & 4) != 0, 4);
-            xreduce_half<4 * NM>(r1, r2, (q & 2) != 0, 2);
-            xreduce_half<2 * NM>(r2, r3, (q & 1) != 0, 1);
+            float r1[2 * NM], r2[NM];
+            xreduce_half<4 * NM>(v, r1, (q & 4) != 0, 4);
+            xreduce_half<2 * NM>(r1, r2, (q & 2) != 0, 2);
 #pragma unroll
-            for (int m = 0; m < NM; m++) tot[m] += r3[m];
+            for (int m = 0; m < NM; m++)
+                tot[m] += r2[m] + __shfl_xor_sync(0xffffffffu, r2[m], 1);
         };
 
         for (int c = 0; c < nchunks; c++, it++) {
@@ -178,19 +190,18 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
             for (int s = 0; s < SPC; s++) {
                 const int kk = kk_base + s * 32;
-                float4 dv[8];
+                float4 dv[FR];
 #pragma unroll
-                for (int j = 0; j < 8; j++) dv[j] = lds128(d + (row_base + j * 4) * K1_KT + kk);
+                for (int j = 0; j < FR; j++) dv[j] = lds128(d + (row_base + j * 4) * K1_KT + kk);
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
                     const float4 mv = lds128(mk + m * K1_KT + kk);
+                    const float2 mlo = make_float2(mv.x, mv.y), mhi = make_float2(mv.z, mv.w);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float a = acc[j][m];
-                        a = fmaf(dv[j].x, mv.x, a);
-                        a = fmaf(dv[j].y, mv.y, a);
-                        a = fmaf(dv[j].z, mv.z, a);
-                        a = fmaf(dv[j].w, mv.w, a);
+                    for (int j = 0; j < FR; j++) {
+                        float2 a = acc[j][m];
+                        a = __ffma2_rn(make_float2(dv[j].x, dv[j].y), mlo, a);
+                        a = __ffma2_rn(make_float2(dv[j].z, dv[j].w), mhi, a);
                         acc[j][m] = a;
                     }
                 }
@@ -204,20 +215,21 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
         }
         if (since_flush) flush();
 
-        // lane (fl, q) now holds frame row fg*32 + q*4 + fl, masks mg*NM .. +NM, partial over
-        // this warp's pixel share.  Combine the KS pixel-split warps through shared memory.
+        // lanes (fl, q) and (fl, q^1) now hold frame row fg*16 + (q>>1)*4 + fl, masks
+        // mg*NM .. +NM, partial over this warp's pixel share.  Combine the KS pixel-split
+        // warps through shared memory.
 #pragma unroll
-        for (int m = 0; m < NM; m++) red[(warp * NM + m) * 32 + lane] = tot[m];
+        for (int m = 0; m < NM; m++) red[(cw * NM + m) * 32 + lane] = tot[m];
         named_bar_sync(1, K1_CWARPS * 32);
-        if (ks == 0) {
-            const int64_t f = fb * K1_FB + fg * 32 + q * 4 + fl;
+        if (ks == 0 && (q & 1) == 0) {
+            const int64_t f = fb * K1_FB + fg * 16 + (q >> 1) * 4 + fl;
             if (f < p.n_frames) {
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
-                    float sum = red[(warp * NM + m) * 32 + lane];
+                    float sum = red[(cw * NM + m) * 32 + lane];
 #pragma unroll
                     for (int s2 = 1; s2 < KS; s2++)
-                        sum += red[((warp + s2) * NM + m) * 32 + lane];
+                        sum += red[((cw + s2) * NM + m) * 32 + lane];
                     const int col = mg * NM + m;
                     if (col < p.n_masks) {
                         if (p.ksplit == 1) {

@@ -1,0 +1,361 @@
+"""UDFRunner: partitions -> tiles -> process_tile -> merge -> get_results, on one GPU per rank.
+
+Mirrors the ordering of the reference's ``UDFRunner`` / ``UDFPartRunner``
+(src/libertem/udf/base.py:2100-2145 run_for_partition, :2147-2206 tile loop, :2256-2309
+_run_tile, :2311-2335 wrap-up, :2340-2358 merge, :2360-2386 results) with two B200-first
+differences:
+
+* **fused pass** -- the reference loops UDFs per tile, so ApplyMasksUDF, CoMUDF, SumSigUDF and
+  SumUDF each re-read the tile (base.py:2187-2194).  Here every UDF that publishes a
+  ``_fused_spec()`` contributes mask rows to ONE launch of the dense kernel per tile
+  (<= 24 columns per pass over HBM), whose columns are then scattered into the UDFs' own
+  result-buffer views; merge / get_results run unchanged.  UDFs without a spec fall back to
+  their ``process_tile``.
+* **ranks instead of workers** -- with ``torch.distributed`` initialised, rank r processes the
+  contiguous block of partitions r of world_size and the dataset-sized buffers are assembled
+  with one all-gather (nav) / all-reduce (sig) at the end; partial results never
+  leave the device before that.
+"""
+import numpy as np
+import torch
+
+from .common.buffers import BufferWrapper, torch_dtype, to_numpy
+from .common.shape import Shape
+from .udf.base import UDFMeta, UDFData, MergeAttrMapping, UDFException
+from .udf.sumsigudf import ones_row
+from . import engine
+
+MAX_FUSED_COLUMNS = 24
+
+
+def _get_dtype(udfs, dtype):
+    """input dtype of the run: result_type over every UDF's preferred dtype
+    (reference udf/base.py:106-123)"""
+    tmp = np.dtype(dtype)
+    for udf in udfs:
+        pref = udf.get_preferred_input_dtype()
+        if pref is bool or pref is udf.USE_NATIVE_DTYPE:
+            continue
+        tmp = np.result_type(pref, tmp)
+    return tmp
+
+
+class UDFResults:
+    def __init__(self, buffers, damage):
+        self.buffers = buffers
+        self.damage = damage
+
+
+class ResultBuffer(BufferWrapper):
+    """what run_udf hands to the user: numpy-backed, with ``.data`` / ``.raw_data``"""
+
+    @classmethod
+    def wrap(cls, decl, arr, ds_shape, roi):
+        buf = cls(decl.kind, decl.extra_shape, decl.dtype, None, decl.use)
+        buf.set_shape_ds(ds_shape, roi)
+        buf.replace_array(arr)
+        return buf
+
+    @property
+    def raw_data(self):
+        return to_numpy(self._data)
+
+
+class UDFRunner:
+    def __init__(self, udfs, debug=False, fuse=True):
+        self._udfs = list(udfs)
+        self._debug = debug
+        self._fuse = fuse
+        self.stats = {'tiles': 0, 'fused_launch_groups': 0, 'unfused_calls': 0}
+
+    # -- distributed helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+        return None
+
+    @staticmethod
+    def my_partitions(partitions, rank, world):
+        """contiguous block of partitions per rank"""
+        n = len(partitions)
+        b = np.linspace(0, n, world + 1, dtype=int)
+        return partitions[b[rank]:b[rank + 1]]
+
+    # -- main entry -------------------------------------------------------------------------------
+    def run_for_dataset(self, dataset, executor=None, roi=None, progress=False,
+                        corrections=None, backends=None, dry=False, device=None):
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        device = torch.device(device)
+        udfs = self._udfs
+        ds_shape = dataset.shape
+        n_frames = ds_shape.nav.size
+        if roi is not None:
+            roi = np.asarray(roi)
+            if roi.dtype != bool or roi.size != n_frames:
+                raise UDFException('roi must be a boolean array of the navigation shape')
+            roi = roi.reshape(tuple(ds_shape.nav))
+        roi_flat = None if roi is None else roi.reshape(-1)
+        input_dtype = _get_dtype(udfs, dataset.dtype)
+
+        # dataset-level instances + buffers (base.py:2472-2557)
+        for udf in udfs:
+            udf.set_meta(UDFMeta(partition_slice=None, dataset_shape=ds_shape, roi=roi,
+                                 dataset_dtype=dataset.dtype, input_dtype=input_dtype,
+                                 device=device))
+            decl = udf.get_result_buffers()
+            for buf in decl.values():
+                buf.set_shape_ds(ds_shape, roi)
+                if buf.use != 'result_only':
+                    buf.allocate(device)
+            udf.results = UDFData(decl)
+
+        partitions = list(dataset.get_partitions())
+        dist = self._dist()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+        mine = self.my_partitions(partitions, rank, world)
+        damage = np.zeros(n_frames if roi_flat is None else int(roi_flat.sum()), dtype=bool)
+
+        if not dry:
+            for part in mine:
+                part_udfs = self._run_partition(part, dataset, udfs, roi_flat, input_dtype,
+                                                device)
+                self._merge_partition(part, udfs, part_udfs, roi_flat, damage)
+        if dist:
+            self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device)
+        else:
+            pass
+        return UDFResults(buffers=self._make_results(udfs, ds_shape, roi, damage), damage=damage)
+
+    # -- per partition ------------------------------------------------------------------------------
+    def _roi_range(self, part, roi_flat):
+        if roi_flat is None:
+            return part.start, part.stop
+        a = int(roi_flat[:part.start].sum())
+        return a, a + int(roi_flat[part.start:part.stop].sum())
+
+    def _run_partition(self, part, dataset, udfs, roi_flat, input_dtype, device):
+        ds_shape = dataset.shape
+        r0, r1 = self._roi_range(part, roi_flat)
+        n_part = r1 - r0
+        part_udfs = []
+        for udf in udfs:
+            pu = udf.copy_for_partition()
+            pu.set_meta(UDFMeta(partition_slice=part.slice, dataset_shape=ds_shape,
+                                roi=udf.meta.roi, dataset_dtype=dataset.dtype,
+                                input_dtype=input_dtype, device=device))
+            decl = pu.get_result_buffers()
+            for buf in decl.values():
+                buf.set_shape_partition(ds_shape, n_part)
+                if buf.use != 'result_only':
+                    buf.allocate(device)
+            pu.results = UDFData(decl)
+            pu.task_data = pu.get_task_data()
+            part_udfs.append(pu)
+        if n_part == 0:
+            return part_udfs
+        for pu in part_udfs:
+            pu.preprocess()
+
+        specs = [self._spec(pu) for pu in part_udfs] if self._fuse else [None] * len(part_udfs)
+        for tile, f0, f1, tslice in part.get_tiles(device, roi=roi_flat):
+            self.stats['tiles'] += 1
+            t0 = tslice.origin[0] - r0           # first row of this tile in partition buffers
+            t1 = t0 + tslice.shape[0]
+            for pu in part_udfs:
+                pu.meta.slice = tslice
+                pu.results.clear_views()
+                for name, buf in pu.results.items():
+                    if buf.has_data():
+                        pu.results.set_view(name, buf.rows(t0, t1))
+            self._run_tile(part_udfs, specs, tile, tslice, ds_shape, device)
+        for pu in part_udfs:
+            pu.results.clear_views()
+            pu.meta.slice = None
+            pu.postprocess()
+        return part_udfs
+
+    @staticmethod
+    def _spec(pu):
+        fn = getattr(pu, '_fused_spec', None)
+        if fn is None:
+            return None
+        if getattr(pu, 'get_method', lambda: 'tile')() == 'frame':
+            return None
+        return fn()
+
+    def _run_tile(self, part_udfs, specs, tile, tslice, ds_shape, device):
+        flat = tile.reshape(tile.shape[0], -1)
+        full_frame = tslice.shape.sig.size == ds_shape.sig.size
+        sig_slice = tslice.discard_nav()
+        fusable_dtype = flat.dtype in (torch.float32, torch.uint16, torch.uint8, torch.int16,
+                                       torch.int8)
+        dense = []       # (pu, spec, rows tensor)
+        sig_sum_view = None
+        for pu, spec in zip(part_udfs, specs):
+            if spec is None or not fusable_dtype:
+                self._run_unfused(pu, tile)
+                continue
+            kind = spec['kind']
+            if kind == 'dense':
+                dense.append((pu, spec, spec['engine'].dense_rows(sig_slice)))
+            elif kind == 'ones':
+                dense.append((pu, spec, ones_row(flat.shape[1], device)))
+            elif kind == 'sig_sum':
+                if full_frame and sig_sum_view is None:
+                    sig_sum_view = getattr(pu.results, spec['buffer']).reshape(-1)
+                else:
+                    self._run_unfused(pu, tile)
+            elif kind == 'csc':
+                view = getattr(pu.results, spec['buffer'])
+                spec['engine'].process_flat(flat, out=view, accumulate=True,
+                                            sig_slice=sig_slice)
+                self.stats['fused_launch_groups'] += 1
+            else:
+                self._run_unfused(pu, tile)
+        if not dense and sig_sum_view is None:
+            return
+        # one pass over the tile per group of <= 24 columns
+        groups, cur, ncols = [], [], 0
+        for item in dense:
+            c = item[2].shape[0]
+            if cur and ncols + c > MAX_FUSED_COLUMNS:
+                groups.append(cur)
+                cur, ncols = [], 0
+            cur.append(item)
+            ncols += c
+        if cur:
+            groups.append(cur)
+        if not groups:
+            groups = [[]]
+        for gi, grp in enumerate(groups):
+            ss = sig_sum_view if gi == 0 else None
+            if len(grp) == 1 and ss is None:
+                pu, spec, rows = grp[0]
+                view = getattr(pu.results, spec['buffer'])
+                out = self._real_view(view, rows.shape[0])
+                engine.masks_dense(flat, rows, out=out, accumulate=True)
+            else:
+                rows = (torch.cat([g[2] for g in grp], dim=0) if grp else
+                        torch.empty((0, flat.shape[1]), dtype=torch.float32, device=device))
+                res = engine.masks_dense(flat, rows, sig_sum=ss)
+                c0 = 0
+                for pu, spec, r in grp:
+                    c = r.shape[0]
+                    view = getattr(pu.results, spec['buffer'])
+                    out = self._real_view(view, c)
+                    out += res[:, c0:c0 + c]
+                    c0 += c
+            self.stats['fused_launch_groups'] += 1
+
+    @staticmethod
+    def _real_view(view, ncols):
+        """(F, ...) result view as real (F, ncols) matrix (complex64 -> interleaved floats)"""
+        if view.is_complex():
+            return torch.view_as_real(view).reshape(view.shape[0], ncols)
+        return view.reshape(view.shape[0], ncols)
+
+    def _run_unfused(self, pu, tile):
+        self.stats['unfused_calls'] += 1
+        if getattr(pu, 'get_method', lambda: 'tile')() == 'frame':
+            shifts = pu.params.shifts
+            tslice = pu.meta.slice
+            views = dict(pu.results._views)
+            for i in range(tile.shape[0]):
+                pu.results.clear_views()
+                for name, v in views.items():
+                    buf = pu.results.get_buffer(name)
+                    pu.results.set_view(name, v[i] if buf.kind == 'nav' else v)
+                if hasattr(shifts, 'for_frames'):
+                    arr = shifts.for_frames(pu.meta.dataset_shape, pu.meta.roi)
+                    pu._current_shift = arr[tslice.origin[0] + i].astype(int)
+                else:
+                    pu._current_shift = np.asarray(shifts).astype(int)
+                pu.process_frame(tile[i])
+            for name, v in views.items():
+                pu.results.set_view(name, v)
+        else:
+            pu.process_tile(tile)
+
+    # -- merging ---------------------------------------------------------------------------------
+    def _merge_partition(self, part, udfs, part_udfs, roi_flat, damage):
+        r0, r1 = self._roi_range(part, roi_flat)
+        for udf, pu in zip(udfs, part_udfs):
+            dest, src = {}, {}
+            for name, buf in udf.results.items():
+                if buf.use == 'result_only' or not buf.has_data():
+                    continue
+                dest[name] = buf.rows(r0, r1)
+                src[name] = pu.results.get_buffer(name).tensor
+            udf.merge(dest=MergeAttrMapping(dest), src=MergeAttrMapping(src))
+        damage[r0:r1] = True
+
+    def _merge_ranks(self, dist, udfs, partitions, roi_flat, damage, device):
+        """assemble the dataset-sized buffers across ranks: nav -> all-gather of each rank's
+        contiguous row block (equal blocks) or all-reduce over disjoint zero-padded rows
+        (ragged blocks); sig -> all-reduce(sum) (mirrors SumUDF.merge, udf/sum.py:51-53)"""
+        world = dist.get_world_size()
+        backend = dist.get_backend()
+        bounds = []
+        for r in range(world):
+            mine = self.my_partitions(partitions, r, world)
+            if mine:
+                a, _ = self._roi_range(mine[0], roi_flat)
+                _, b = self._roi_range(mine[-1], roi_flat)
+            else:
+                a = b = 0
+            bounds.append((a, b))
+        sizes = [b - a for a, b in bounds]
+        equal = len(set(sizes)) == 1 and sizes[0] > 0
+        for udf in udfs:
+            for name, buf in udf.results.items():
+                if buf.use == 'result_only' or not buf.has_data():
+                    continue
+                t = buf.tensor
+                comm = t if backend == 'nccl' else t.cpu()
+                if buf.kind == 'nav' and equal and not comm.is_complex():
+                    a, b = bounds[dist.get_rank()]
+                    block = comm[a:b].contiguous()
+                    dist.all_gather_into_tensor(comm.view(-1), block.view(-1))
+                else:
+                    if comm.is_complex():
+                        r = torch.view_as_real(comm)
+                        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+                    else:
+                        dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+                if comm is not t:
+                    t.copy_(comm)
+        damage[:] = True
+
+    # -- results ---------------------------------------------------------------------------------
+    def _make_results(self, udfs, ds_shape, roi, damage):
+        out = []
+        for udf in udfs:
+            udf.meta._valid_nav_mask = damage
+            decl = udf.get_result_buffers()
+            res = udf.get_results()
+            for k, v in decl.items():
+                if k not in res and v.use is None:
+                    res[k] = udf.results.get_buffer(k).raw_data
+            wrapped = {}
+            for name, arr in res.items():
+                d = decl[name]
+                arr_np = to_numpy(arr) if not isinstance(arr, np.ndarray) else arr
+                if np.dtype(arr_np.dtype).kind != np.dtype(d.dtype).kind:
+                    raise UDFException(
+                        "the returned ndarray '%s' has a different dtype kind (%s) than "
+                        "declared (%s)" % (name, arr_np.dtype, d.dtype))
+                wrapped[name] = ResultBuffer.wrap(d, arr_np, ds_shape, roi)
+            out.append(wrapped)
+        return out
+
+
+def run_udf(dataset, udf, roi=None, device=None, fuse=True):
+    """``Context.run_udf`` for this runtime (reference api.py:914-1051): one UDF -> dict of
+    result buffers, a list of UDFs -> list of dicts."""
+    many = isinstance(udf, (list, tuple))
+    udfs = list(udf) if many else [udf]
+    res = UDFRunner(udfs, fuse=fuse).run_for_dataset(dataset, roi=roi, device=device)
+    return res.buffers if many else res.buffers[0]

@@ -1,0 +1,330 @@
+"""UDF-level parity on the GPU: the host mirror of the reference API (ApplyMasksUDF, CoMUDF,
+SumUDF, SumSigUDF, analyses) against golden vectors produced by the unmodified reference and
+against the CPU oracle.  pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from golden_inputs import mixed_masks, roi_from_seed, ring_stack
+from oracle import synth, udf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5          # north_star tolerance for float32 mask / CoM results
+COM_KEYS = ('raw_com', 'raw_shifts', 'field', 'field_y', 'field_x', 'magnitude', 'divergence',
+            'curl', 'regression')
+
+
+@pytest.fixture(scope='module')
+def lt():
+    import libertem_b200.udf as udf
+    from libertem_b200.io import MemoryDataSet, SyntheticDataSet
+    from libertem_b200.runner import run_udf, UDFRunner
+    from libertem_b200.api import Context
+
+    class NS:
+        pass
+    ns = NS()
+    ns.udf, ns.MemoryDataSet, ns.SyntheticDataSet = udf, MemoryDataSet, SyntheticDataSet
+    ns.run_udf, ns.UDFRunner, ns.Context = run_udf, UDFRunner, Context
+    return ns
+
+
+def close_cols(res, ref, rtol=RTOL):
+    """per-column tolerance relative to the column's magnitude (masks may be signed)"""
+    res = np.asarray(res, dtype=np.float64).reshape(ref.shape)
+    ref64 = np.asarray(ref, dtype=np.float64)
+    scale = np.abs(ref64).reshape(-1, ref.shape[-1]).max(axis=0) + 1e-30
+    err = (np.abs(res - ref64).reshape(-1, ref.shape[-1]) / scale).max()
+    assert err <= rtol, f'max rel err {err:.3e}'
+
+
+def check_com(res, g, prefix='com_', atol=2e-4):
+    for k in COM_KEYS:
+        ref = g[prefix + k]
+        got = res[k].raw_data
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        assert got.dtype == ref.dtype, (k, got.dtype, ref.dtype)
+        # shifts/field lose ~7 bits to cancellation -> absolute tolerance
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=atol, err_msg=k, equal_nan=True)
+
+
+@pytest.mark.parametrize('nparts', [1, 8])
+@pytest.mark.parametrize('where', ['device', 'host'])
+def test_cfg1(lt, nparts, where):
+    meta, g = load_golden(f'cfg1_p{nparts}')
+    data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
+    mask = synth.uniform_f32(0, 64 * 64, meta['mask_seed']).reshape(64, 64)
+    src = torch.from_numpy(data).cuda() if where == 'device' else data
+    ds = lt.MemoryDataSet(data=src, num_partitions=nparts, sig_dims=2)
+    res = lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=[lambda: mask]))
+    inten = res['intensity']
+    assert inten.data.shape == (32, 32, 1) and inten.data.dtype == np.float32
+    close_cols(inten.raw_data, g['intensity'])
+
+
+@pytest.mark.parametrize('fuse', [True, False])
+def test_cfg2_small(lt, fuse):
+    meta, g = load_golden('cfg2_small')
+    data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
+    stack = mixed_masks(256, 256, meta['n_masks'], meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(),
+                          num_partitions=meta['num_partitions'], sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.ApplyMasksUDF(mask_factories=lambda: stack),
+                           lt.udf.CoMUDF(), lt.udf.SumUDF(), lt.udf.SumSigUDF()], fuse=fuse)
+    from libertem_b200 import engine
+    engine.launch_count(reset=True)
+    res = runner.run_for_dataset(ds).buffers
+    launches = engine.launch_count()
+    if fuse:
+        # ONE pass of the dense kernel (+ its split-K finalize for these 64-frame partitions)
+        # and the two column-sum launches of SumUDF per partition -- not one pass per UDF
+        assert runner.stats['unfused_calls'] == 0
+        assert launches <= 4 * meta['num_partitions'], launches
+    close_cols(res[0]['intensity'].raw_data, g['intensity'])
+    assert 'raw_mask_result' not in res[1]          # private buffer stays private
+    check_com(res[1], g)
+    np.testing.assert_allclose(res[2]['intensity'].data, g['sum'], rtol=RTOL)
+    np.testing.assert_allclose(res[3]['intensity'].raw_data, g['sumsig'], rtol=RTOL)
+    assert res[3]['intensity'].data.shape == (16, 16)
+    # raw_com to 1e-5 relative (north_star: CoM output within 1e-5 of reference)
+    np.testing.assert_allclose(res[1]['raw_com'].raw_data, g['com_raw_com'], rtol=RTOL)
+
+
+def test_cfg3_small_bit_exact(lt):
+    meta, g = load_golden('cfg3_small')
+    data = synth.dataset(meta['shape'], np.uint16, meta['data_seed'])
+    rings = meta['rings']
+    from libertem_b200 import masks as M
+    facs = [lambda ri=ri, ro=ro: M.ring(64, 64, 128, 128, ro, ri) for ri, ro in rings]
+    for src in (data, torch.from_numpy(data.view(np.int16)).cuda().view(torch.uint16)):
+        ds = lt.MemoryDataSet(data=src, num_partitions=meta['num_partitions'], sig_dims=2)
+        res = lt.run_udf(ds, [lt.udf.SumUDF(), lt.udf.SumSigUDF(),
+                              lt.udf.ApplyMasksUDF(mask_factories=facs, use_sparse=True,
+                                                   mask_dtype=np.float32)])
+        assert res[0]['intensity'].data.dtype == np.float32
+        assert np.array_equal(res[0]['intensity'].data, g['sum'])
+        assert np.array_equal(res[1]['intensity'].raw_data, g['sumsig'])
+        assert np.array_equal(res[2]['intensity'].raw_data, g['intensity'])
+
+
+@pytest.mark.parametrize('kind', ['sparse', 'dense'])
+def test_cfg4_small_radial_fourier(lt, kind):
+    meta, g = load_golden('cfg4_small_' + kind)
+    data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(),
+                          num_partitions=meta['num_partitions'], sig_dims=2)
+    ctx = lt.Context()
+    a = ctx.create_radial_fourier_analysis(ds, n_bins=8, use_sparse=(kind == 'sparse'))
+    for k in ('cx', 'cy', 'ri', 'ro', 'n_bins', 'max_order', 'mask_count'):
+        assert a.parameters[k] == meta['params'][k], k
+    res = ctx.run(a)
+    raw = res.raw_results
+    assert raw.shape == g['raw_results'].shape and raw.dtype == np.complex64
+    scale = np.abs(g['raw_results'][:, 0]).max()
+    assert np.abs(raw - g['raw_results']).max() <= RTOL * scale
+    assert res['absolute_0_0'].raw_data.shape == (6, 6)
+    assert np.allclose(res['phase_3_2'].raw_data, np.angle(g['raw_results'][3, 2]), atol=1e-3)
+
+
+@pytest.mark.parametrize('i', [0, 1, 2])
+def test_com_params(lt, i):
+    meta, g = load_golden(f'com_params_{i}')
+    c = meta['com']
+    if c['r'] == 'inf':
+        c['r'] = float('inf')
+    data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
+    ds = lt.MemoryDataSet(data=data, num_partitions=meta['num_partitions'], sig_dims=2)
+    res = lt.run_udf(ds, lt.udf.CoMUDF.with_params(**c))
+    check_com(res, g, prefix='', atol=5e-5)
+
+
+def test_com_analysis_matches_udf(lt):
+    # tests/udf/test_com.py:16-103: CoMUDF == COMAnalysis (field is (x, y) in the analysis)
+    data = synth.dataset((6, 7, 16, 16), np.float32, 31)
+    ds = lt.MemoryDataSet(data=data, num_partitions=2, sig_dims=2)
+    ctx = lt.Context()
+    a = ctx.create_com_analysis(ds, cx=8, cy=8, mask_radius=6, scan_rotation=12.)
+    ares = ctx.run(a)
+    ures = ctx.run_udf(ds, lt.udf.CoMUDF.with_params(cy=8, cx=8, r=6, scan_rotation=12.))
+    fx, fy = ares['field'].raw_data
+    np.testing.assert_allclose(ures['field'].data[..., 0], fy, atol=1e-6)
+    np.testing.assert_allclose(ures['field'].data[..., 1], fx, atol=1e-6)
+    np.testing.assert_allclose(ures['divergence'].data, ares['divergence'].raw_data, atol=1e-6)
+    np.testing.assert_allclose(ures['curl'].data, ares['curl'].raw_data, atol=1e-6)
+    np.testing.assert_allclose(ures['magnitude'].data, ares['magnitude'].raw_data, atol=1e-6)
+
+
+def test_com_zero_frames_no_nan(lt):
+    # tests/analysis/test_analysis_com.py:36-52
+    data = np.zeros((4, 4, 8, 8), dtype=np.float32)
+    ds = lt.MemoryDataSet(data=data, num_partitions=2, sig_dims=2)
+    res = lt.run_udf(ds, lt.udf.CoMUDF())
+    for k in ('raw_com', 'raw_shifts', 'field', 'magnitude', 'divergence', 'curl'):
+        assert not np.any(np.isnan(res[k].data)), k
+    assert np.allclose(res['raw_shifts'].data, 0)
+    assert np.allclose(res['raw_com'].data, 4)
+
+
+def test_com_known_answer(lt):
+    # hand-crafted: single bright pixel per frame -> CoM is that pixel
+    data = np.zeros((3, 3, 16, 16), dtype=np.float32)
+    ys = np.arange(9).reshape(3, 3) + 2
+    xs = 12 - np.arange(9).reshape(3, 3)
+    for i in range(3):
+        for j in range(3):
+            data[i, j, ys[i, j], xs[i, j]] = 5.
+    ds = lt.MemoryDataSet(data=data, num_partitions=3, sig_dims=2)
+    res = lt.run_udf(ds, lt.udf.CoMUDF())
+    assert np.array_equal(res['raw_com'].data[..., 0], ys.astype(np.float32))
+    assert np.array_equal(res['raw_com'].data[..., 1], xs.astype(np.float32))
+    assert np.array_equal(res['raw_shifts'].data[..., 0], (ys - 8).astype(np.float32))
+    # linear field -> constant divergence, zero curl
+    np.testing.assert_allclose(res['divergence'].data, 3 - 1, atol=1e-6)
+
+
+def test_roi(lt):
+    meta, g = load_golden('roi')
+    shape = meta['shape']
+    data = synth.dataset(shape, np.float32, meta['data_seed'])
+    roi = roi_from_seed(shape[:2], meta['roi_seed'])
+    stack = mixed_masks(shape[2], shape[3], meta['n_masks'], meta['mask_seed'])
+    for src in (data, torch.from_numpy(data).cuda()):
+        ds = lt.MemoryDataSet(data=src, num_partitions=meta['num_partitions'], sig_dims=2)
+        res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=lambda: stack),
+                              lt.udf.CoMUDF.with_params(regression=1), lt.udf.SumUDF(),
+                              lt.udf.SumSigUDF()], roi=roi)
+        close_cols(res[0]['intensity'].raw_data, g['intensity'])
+        full = res[0]['intensity'].data
+        assert full.shape == g['intensity_full'].shape
+        assert np.array_equal(np.isnan(full), np.isnan(g['intensity_full']))
+        check_com(res[1], g, atol=5e-5)
+        np.testing.assert_allclose(res[1]['divergence'].data, g['com_divergence_full'],
+                                   rtol=RTOL, atol=5e-5, equal_nan=True)
+        np.testing.assert_allclose(res[2]['intensity'].data, g['sum'], rtol=RTOL)
+        np.testing.assert_allclose(res[3]['intensity'].raw_data, g['sumsig'], rtol=RTOL)
+
+
+@pytest.mark.parametrize('dt', ['float32', 'uint16'])
+def test_odd_shapes(lt, dt):
+    meta, g = load_golden('odd_' + dt)
+    shape = meta['shape']
+    data = synth.dataset(shape, np.dtype(dt), meta['data_seed'])
+    stack = mixed_masks(shape[2], shape[3], meta['n_masks'], meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=data, num_partitions=meta['num_partitions'], sig_dims=2,
+                          tileshape=(4, 17, 23))
+    res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=lambda: stack), lt.udf.CoMUDF(),
+                          lt.udf.SumUDF(), lt.udf.SumSigUDF()])
+    close_cols(res[0]['intensity'].raw_data, g['intensity'])
+    np.testing.assert_allclose(res[1]['raw_com'].raw_data, g['com_raw_com'], rtol=RTOL)
+    np.testing.assert_allclose(res[2]['intensity'].data, g['sum'], rtol=RTOL)
+    np.testing.assert_allclose(res[3]['intensity'].raw_data, g['sumsig'], rtol=RTOL)
+    if dt == 'uint16':
+        assert np.array_equal(res[2]['intensity'].data, g['sum'])
+        assert np.array_equal(res[3]['intensity'].raw_data, g['sumsig'])
+
+
+def test_subframe_tiles_accumulate(lt):
+    meta, g = load_golden('subframe')
+    shape = meta['shape']
+    data = synth.dataset(shape, np.float32, meta['data_seed'])
+    stack = mixed_masks(shape[2], shape[3], meta['n_masks'], meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=data, num_partitions=meta['num_partitions'], sig_dims=2,
+                          tileshape=tuple(meta['tileshape']))
+    res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=lambda: stack), lt.udf.SumUDF(),
+                          lt.udf.SumSigUDF()])
+    close_cols(res[0]['intensity'].raw_data, g['intensity'])
+    np.testing.assert_allclose(res[1]['intensity'].data, g['sum'], rtol=RTOL)
+    np.testing.assert_allclose(res[2]['intensity'].raw_data, g['sumsig'], rtol=RTOL)
+
+
+def test_dtype_rules(lt):
+    meta, g = load_golden('dtypes')
+    shape = meta['shape']
+    n = int(np.prod(shape))
+    stack32 = mixed_masks(8, 8, 2, meta['mask_seed'])
+
+    def run(data, stack, **kw):
+        ds = lt.MemoryDataSet(data=data, num_partitions=2, sig_dims=2)
+        return lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=lambda: stack, **kw))
+
+    d_i32 = (synth.hash_u32(0, n, meta['seeds']['i32']) % 1000).astype(np.int32).reshape(shape)
+    r = run(d_i32, stack32)['intensity'].raw_data
+    assert r.dtype == np.float64
+    np.testing.assert_allclose(r, g['i32_f32'], rtol=1e-12)
+    d_f32 = synth.dataset(shape, np.float32, meta['seeds']['f32'])
+    stack64 = stack32.astype(np.float64) * 1.000000123
+    r = run(d_f32, stack64)['intensity'].raw_data
+    assert r.dtype == np.float64
+    np.testing.assert_allclose(r, g['f32_f64'], rtol=1e-12)
+    r = run(d_f32, stack64, mask_dtype=np.float32)['intensity'].raw_data
+    assert r.dtype == np.float32
+    close_cols(r, g['f32_f64_forced32'])
+    stackc = (stack32 + 1j * stack32[::-1]).astype(np.complex64)
+    r = run(d_f32, stackc)['intensity'].raw_data
+    assert r.dtype == np.complex64
+    np.testing.assert_allclose(r, g['f32_c64'], rtol=RTOL)
+    d_u8 = (synth.hash_u32(0, n, meta['seeds']['u8']) % 256).astype(np.uint8).reshape(shape)
+    ds = lt.MemoryDataSet(data=d_u8, num_partitions=2, sig_dims=2)
+    res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=lambda: stack32), lt.udf.SumUDF(),
+                          lt.udf.SumSigUDF()])
+    close_cols(res[0]['intensity'].raw_data, g['u8_f32'])
+    assert np.array_equal(res[1]['intensity'].data, g['u8_sum'])
+    assert np.array_equal(res[2]['intensity'].raw_data, g['u8_sumsig'])
+
+
+def test_shifts(lt):
+    meta, g = load_golden('shifts')
+    shape = meta['shape']
+    data = synth.dataset(shape, np.float32, meta['data_seed'])
+    stack = mixed_masks(shape[2], shape[3], meta['n_masks'], meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=data, num_partitions=2, sig_dims=2)
+    r = lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=lambda: stack,
+                                            shifts=tuple(meta['const'])))
+    close_cols(r['intensity'].raw_data, g['const'])
+    sh = g['shifts']
+    udf = lt.udf.ApplyMasksUDF(
+        mask_factories=lambda: stack,
+        shifts=lt.udf.ApplyMasksUDF.aux_data(sh.ravel(), kind='nav', extra_shape=(2,),
+                                             dtype=sh.dtype))
+    r = lt.run_udf(ds, udf)
+    close_cols(r['intensity'].raw_data, g['perframe'])
+    assert np.all(r['intensity'].raw_data[3] == 0)      # no overlap -> 0
+    with pytest.raises(ValueError):
+        lt.udf.ApplyMasksUDF(mask_factories=lambda: stack, shifts=(1, 1),
+                             use_sparse='scipy.sparse')
+
+
+def test_process_tile_seam_with_numpy_tile(lt):
+    """drop-in seam: UDF.process_tile(tile) with a host numpy tile, as the reference's
+    BACKEND_CUDA runtime would call it"""
+    from libertem_b200.udf.base import UDFMeta, UDFData
+    from libertem_b200.common import Shape
+    data = synth.dataset((5, 4, 32, 32), np.float32, 41)
+    mask = synth.uniform_f32(0, 1024, 42).reshape(32, 32)
+    udf = lt.udf.ApplyMasksUDF(mask_factories=[lambda: mask])
+    dsh = Shape(data.shape, sig_dims=2)
+    udf.set_meta(UDFMeta(dataset_shape=dsh, dataset_dtype=np.float32, input_dtype=np.float32,
+                         device=torch.device('cuda')))
+    decl = udf.get_result_buffers()
+    for b in decl.values():
+        b.set_shape_partition(dsh, 20)
+        b.allocate(torch.device('cuda'))
+    udf.results = UDFData(decl)
+    udf.task_data = udf.get_task_data()
+    udf.results.set_view('intensity', decl['intensity'].rows(0, 20))
+    udf.process_tile(data.reshape(20, 32, 32))
+    udf.process_tile(data.reshape(20, 32, 32))         # += semantics
+    ref = O.apply_masks(data, mask[None])
+    close_cols(decl['intensity'].raw_data, 2 * ref)
+
+
+def test_synthetic_dataset_matches_oracle(lt):
+    ds = lt.SyntheticDataSet((8, 8, 64, 64), np.float32, seed=55, num_partitions=4)
+    mask = synth.uniform_f32(0, 4096, 56).reshape(64, 64)
+    res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=[lambda: mask]), lt.udf.CoMUDF()])
+    data = synth.dataset((8, 8, 64, 64), np.float32, 55)
+    close_cols(res[0]['intensity'].raw_data, O.apply_masks(data, mask[None], num_partitions=4))
+    ref = O.com_udf(data, num_partitions=4)
+    np.testing.assert_allclose(res[1]['raw_com'].raw_data, ref['raw_com'], rtol=RTOL)
