@@ -18,6 +18,10 @@ _TORCH_DTYPES = {
 
 _workspaces = {}
 
+#: when set to a list, masks_dense appends (start_event, end_event, n_frames, sig_size,
+#: itemsize) around its launches (bench.py uses this to time the dominant kernel live)
+EVENT_LOG = None
+
 
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
@@ -84,11 +88,19 @@ def masks_dense(tile, masks, out=None, accumulate=False, sig_sum=None):
             _require_cuda(sig_sum, 'sig_sum')
             if sig_sum.dtype != torch.float32 or sig_sum.numel() != K or not sig_sum.is_contiguous():
                 raise ValueError('sig_sum must be a contiguous float32 tensor of sig_size')
+        log = EVENT_LOG
+        if log is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(tile.device))
         check(lib.ltb200_masks_dense(
             tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, K, ld_tile,
             masks.data_ptr(), M, ld_masks, out.data_ptr(), ld_out, int(bool(accumulate)),
             sig_sum.data_ptr() if sig_sum is not None else None,
             ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, st))
+        if log is not None:
+            e1.record(torch.cuda.current_stream(tile.device))
+            log.append((e0, e1, F, K, tile.element_size()))
     return out
 
 

@@ -67,6 +67,7 @@ class UDFRunner:
         self._debug = debug
         self._fuse = fuse
         self.stats = {'tiles': 0, 'fused_launch_groups': 0, 'unfused_calls': 0}
+        self._cat_cache = {}
 
     # -- distributed helpers ---------------------------------------------------------------------
     @staticmethod
@@ -85,7 +86,8 @@ class UDFRunner:
 
     # -- main entry -------------------------------------------------------------------------------
     def run_for_dataset(self, dataset, executor=None, roi=None, progress=False,
-                        corrections=None, backends=None, dry=False, device=None):
+                        corrections=None, backends=None, dry=False, device=None,
+                        finalize=True):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
@@ -125,8 +127,10 @@ class UDFRunner:
                 self._merge_partition(part, udfs, part_udfs, roi_flat, damage)
         if dist:
             self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device)
-        else:
-            pass
+        if not finalize:
+            # hot path only (tiles -> kernels -> merge [-> collectives]); results stay in
+            # the UDFs' device buffers (udf.results)
+            return UDFResults(buffers=None, damage=damage)
         return UDFResults(buffers=self._make_results(udfs, ds_shape, roi, damage), damage=damage)
 
     # -- per partition ------------------------------------------------------------------------------
@@ -238,8 +242,7 @@ class UDFRunner:
                 out = self._real_view(view, rows.shape[0])
                 engine.masks_dense(flat, rows, out=out, accumulate=True)
             else:
-                rows = (torch.cat([g[2] for g in grp], dim=0) if grp else
-                        torch.empty((0, flat.shape[1]), dtype=torch.float32, device=device))
+                rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
                 res = engine.masks_dense(flat, rows, sig_sum=ss)
                 c0 = 0
                 for pu, spec, r in grp:
@@ -249,6 +252,17 @@ class UDFRunner:
                     out += res[:, c0:c0 + c]
                     c0 += c
             self.stats['fused_launch_groups'] += 1
+
+    def _cat_rows(self, row_tensors, k, device):
+        """stacked mask rows of one fused group, cached across tiles / partitions / runs"""
+        if not row_tensors:
+            return torch.empty((0, k), dtype=torch.float32, device=device)
+        key = tuple((t.data_ptr(), t.shape[0]) for t in row_tensors)
+        hit = self._cat_cache.get(key)
+        if hit is None:
+            hit = (torch.cat(row_tensors, dim=0), row_tensors)   # keep sources alive
+            self._cat_cache[key] = hit
+        return hit[0]
 
     @staticmethod
     def _real_view(view, ncols):

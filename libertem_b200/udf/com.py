@@ -157,6 +157,12 @@ class CoMUDF(UDF):
 
     def __init__(self, com_params: CoMParams = CoMParams()):
         super().__init__(com_params=com_params)
+        self._containers = {}
+
+    def copy_for_partition(self):
+        new = super().copy_for_partition()
+        new._containers = self._containers      # share the cached CoM mask stack
+        return new
 
     @classmethod
     def with_params(cls, *, cy=None, cx=None, r=float('inf'), ri=0., scan_rotation=0.,
@@ -206,8 +212,12 @@ class CoMUDF(UDF):
                 base_mask_factory=lambda: masks.ring(
                     imageSizeY=sig_shape[0], imageSizeX=sig_shape[1], centerY=p.cy,
                     centerX=p.cx, radius=p.r, radius_inner=p.ri))
-        container = MaskContainer(mask_factories=fac, dtype=np.float32, use_sparse=False,
-                                  count=3, backend='cuda')
+        key = (sig_shape, p.cy, p.cx, p.r, p.ri)
+        container = self._containers.get(key)
+        if container is None:
+            container = MaskContainer(mask_factories=fac, dtype=np.float32, use_sparse=False,
+                                      count=3, backend='cuda')
+            self._containers[key] = container
         return {'com_params': p,
                 'engine': ApplyMasksEngine(masks=container, meta=self.meta, use_torch=True)}
 

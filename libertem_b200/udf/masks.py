@@ -137,6 +137,13 @@ class ApplyMasksUDF(UDF):
                          preferred_dtype=preferred_dtype, backends=backends, shifts=shifts,
                          **kwargs)
 
+    def copy_for_partition(self):
+        # partition instances of one process share the (lazily computed, cached) mask
+        # container: masks are built and uploaded once per run, not once per partition
+        new = super().copy_for_partition()
+        new._mask_container = self.masks
+        return new
+
     def get_preferred_input_dtype(self):
         if self.params.preferred_dtype is None:
             return super().get_preferred_input_dtype()
