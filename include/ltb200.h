@@ -99,8 +99,13 @@ LTB_API int ltb200_masks_dense_f64(const void* tile, int tile_dtype, int64_t n_f
                            int64_t ld_masks, double* out, int64_t ld_out, int accumulate,
                            void* stream);
 
+/* tuning / test knob: register tile of the TMA-staged dense kernel.
+ * 0 = auto (default), 1 = even/odd-pixel accumulator pairs, 2 = mask-pair accumulators */
+LTB_API int ltb200_set_k1_variant(int variant);
+
 /* which kernel the last ltb200_masks_dense call on this thread selected:
- * 1 = TMA-staged FFMA kernel, 2 = generic kernel (diagnostics / tests) */
+ * 1 = TMA-staged kernel (even/odd tile), 3 = TMA-staged kernel (mask-pair tile),
+ * 2 = generic kernel (diagnostics / tests) */
 LTB_API int ltb200_last_kernel(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 LTB_API int64_t ltb200_launch_count(int reset);

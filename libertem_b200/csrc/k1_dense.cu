@@ -26,6 +26,8 @@
 // Anything the TMA path cannot take (K % 4 != 0, unaligned or strided tiles, integer or
 // float64 inputs) goes through the generic kernel below (same arithmetic, no staging).
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace ltb {
 
@@ -49,6 +51,7 @@ struct K1Params {
     float* part;           // (ksplit, n_frames, n_masks) when ksplit > 1
     int accumulate;
     int n_stages;
+    float* sig_part;       // pair kernel only: (gridDim.x, sig_size) per-CTA frame sums or NULL
 };
 
 __host__ __device__ constexpr size_t k1_stage_bytes(int nrows) {
@@ -66,6 +69,10 @@ __device__ __forceinline__ void xreduce_half(const float (&v)[N], float (&r)[N /
         r[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, lane_xor);
     }
 }
+
+}  // namespace ltb
+#include "k1_pair.cuh"
+namespace ltb {
 
 template <int NM, int MG>
 __global__ void __launch_bounds__(K1_THREADS, 1)
@@ -366,6 +373,115 @@ static size_t colsum_bytes(int64_t n_frames, int64_t sig_size) {
     return (size_t)splits * sig_size * sizeof(float);
 }
 
+constexpr size_t K1_SIG_SMEM_MAX = 96 * 1024;   // fused SumUDF needs sig_size*4 bytes of smem
+
+struct WsLayout {
+    size_t part_off, pack_off, sig_off, total;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static WsLayout ws_layout(int64_t n_frames, int64_t sig_size, int n_masks, int with_sig) {
+    WsLayout w;
+    const int nm = n_masks > 24 ? 24 : n_masks;
+    w.part_off = 0;
+    size_t part = nm > 0 ? k1_part_bytes(n_frames, sig_size, nm) : 0;
+    w.pack_off = align256(part);
+    size_t pack = nm > 0 ? (size_t)24 * (((sig_size + 31) / 32) * 32) * sizeof(float) : 0;
+    w.sig_off = w.pack_off + align256(pack);
+    size_t sig = 0;
+    if (with_sig) {
+        sig = colsum_bytes(n_frames, sig_size);
+        const size_t fused = (size_t)sm_count() * sig_size * sizeof(float);
+        if (fused > sig) sig = fused;
+    }
+    w.total = w.sig_off + align256(sig);
+    return w;
+}
+
+template <typename TIN, int NP, int FR, int MG>
+static int launch_k1_pair(const CUtensorMap& tmd, const CUtensorMap& tmm, const K1Params& p0,
+                          int grid, cudaStream_t st) {
+    using C = K1PairCfg<TIN, NP, FR, MG>;
+    K1Params p = p0;
+    int dev = 0, smem_max = 0;
+    LTB_CUDA_CHECK(cudaGetDevice(&dev));
+    LTB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t sig_bytes = p.sig_part ? (size_t)p.sig_size * 4 : 0;
+    const size_t fixed = C::FIXED_BYTES + sig_bytes + 128;
+    int stages = (int)(((size_t)smem_max - fixed) / C::STAGE_BYTES);
+    if (stages > 6) stages = 6;
+    if (stages < 2) {
+        set_error("k1 pair: not enough shared memory for 2 stages");
+        return LTB_ERR_UNSUPPORTED;
+    }
+    p.n_stages = stages;
+    const size_t smem = (size_t)stages * C::STAGE_BYTES + C::FIXED_BYTES + sig_bytes;
+    auto kern = k1_pair_kernel<TIN, NP, FR, MG>;
+    static thread_local int configured_dev = -1;
+    if (configured_dev != dev) {
+        LTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            smem_max));
+        configured_dev = dev;
+    }
+    kern<<<grid, K1_THREADS, smem, st>>>(tmd, tmm, p);
+    count_launch();
+    LTB_CUDA_CHECK(cudaGetLastError());
+    return LTB_OK;
+}
+
+typedef int (*K1PairLauncher)(const CUtensorMap&, const CUtensorMap&, const K1Params&, int,
+                              cudaStream_t);
+
+struct PairChoice {
+    K1PairLauncher fn;
+    int np, fr, mg;
+    int kt() const { return fr == 16 ? 256 : 128; }
+};
+
+// n_masks -> (pairs per lane, frames per lane, mask groups)
+template <typename TIN>
+static PairChoice pair_choice(int n_masks, bool want_fr16) {
+    const int npt = (n_masks + 1) / 2;
+    if (want_fr16 && npt <= 3) {
+        switch (npt) {
+            case 1: return {launch_k1_pair<TIN, 1, 16, 1>, 1, 16, 1};
+            case 2: return {launch_k1_pair<TIN, 2, 16, 1>, 2, 16, 1};
+            default: return {launch_k1_pair<TIN, 3, 16, 1>, 3, 16, 1};
+        }
+    }
+    if (npt <= 6) {
+        switch (npt) {
+            case 1: return {launch_k1_pair<TIN, 1, 8, 1>, 1, 8, 1};
+            case 2: return {launch_k1_pair<TIN, 2, 8, 1>, 2, 8, 1};
+            case 3: return {launch_k1_pair<TIN, 3, 8, 1>, 3, 8, 1};
+            case 4: return {launch_k1_pair<TIN, 4, 8, 1>, 4, 8, 1};
+            case 5: return {launch_k1_pair<TIN, 5, 8, 1>, 5, 8, 1};
+            default: return {launch_k1_pair<TIN, 6, 8, 1>, 6, 8, 1};
+        }
+    }
+    const int np = (npt + 1) / 2;   // two mask groups
+    switch (np) {
+        case 4: return {launch_k1_pair<TIN, 4, 8, 2>, 4, 8, 2};
+        case 5: return {launch_k1_pair<TIN, 5, 8, 2>, 5, 8, 2};
+        default: return {launch_k1_pair<TIN, 6, 8, 2>, 6, 8, 2};
+    }
+}
+
+static int g_k1_variant = -1;
+
+static int k1_variant() {
+    // which FFMA2 register tile the dense path uses: 0 auto, 1 even/odd-pixel pairs ("eo"),
+    // 2 mask pairs ("pair"); LTB200_K1=eo|pair|auto or ltb200_set_k1_variant()
+    if (g_k1_variant < 0) {
+        const char* e = getenv("LTB200_K1");
+        g_k1_variant = 0;
+        if (e && !strcmp(e, "eo")) g_k1_variant = 1;
+        if (e && !strcmp(e, "pair")) g_k1_variant = 2;
+    }
+    return g_k1_variant;
+}
+
 template <int NM, int MG>
 static int launch_k1_tma(const CUtensorMap& tmd, const CUtensorMap& tmm, const K1Params& p0,
                          int grid, cudaStream_t st) {
@@ -485,14 +601,115 @@ static size_t dtype_size(int dtype) {
 
 using namespace ltb;
 
+extern "C" int ltb200_set_k1_variant(int variant) {
+    LTB_REQUIRE(variant >= 0 && variant <= 2, "set_k1_variant: 0 auto, 1 eo, 2 pair");
+    ltb::g_k1_variant = variant;
+    return LTB_OK;
+}
+
 extern "C" size_t ltb200_masks_dense_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
                                                int with_sig_sum) {
     if (n_frames <= 0 || sig_size <= 0 || n_masks < 0) return 0;
-    size_t a = n_masks > 0 ? k1_part_bytes(n_frames, sig_size, n_masks > 24 ? 24 : n_masks) : 0;
-    size_t b = with_sig_sum ? colsum_bytes(n_frames, sig_size) : 0;
-    a = (a + 255) & ~(size_t)255;
-    return a + b;
+    return ws_layout(n_frames, sig_size, n_masks, with_sig_sum).total;
 }
+
+namespace ltb {
+
+// one launch of a TMA-staged kernel over <= 24 mask columns; returns whether the frame sum
+// (SumUDF) was fused into it
+template <typename TIN>
+static int run_tma_group(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+                         const float* mk, int nm, int64_t ld_masks, float* o, int64_t ld_out,
+                         int accumulate, float* sig_sum, uint8_t* ws, const WsLayout& wl,
+                         bool allow_eo, cudaStream_t st, bool* sig_fused) {
+    const int sms = sm_count();
+    const int64_t n_fb = (n_frames + K1_FB - 1) / K1_FB;
+    K1Params p;
+    p.n_frames = n_frames;
+    p.sig_size = sig_size;
+    p.n_masks = nm;
+    p.ksplit = choose_ksplit(n_fb, sig_size, sms);
+    const int64_t chunks = (sig_size + K1_KT - 1) / K1_KT;
+    p.k_per_split = ((chunks + p.ksplit - 1) / p.ksplit) * K1_KT;
+    p.n_items = n_fb * p.ksplit;
+    p.out = o;
+    p.ld_out = ld_out;
+    p.part = (float*)(ws + wl.part_off);
+    p.accumulate = accumulate;
+    p.n_stages = 0;
+    p.sig_part = nullptr;
+    const int grid = (int)(p.n_items < sms ? p.n_items : sms);
+    *sig_fused = false;
+
+    const bool want_sig = sig_sum != nullptr && (size_t)sig_size * 4 <= K1_SIG_SMEM_MAX &&
+                          nm <= 6;
+    const int variant = k1_variant();
+    bool use_pair = !allow_eo || variant == 2 || (variant == 0 && (nm >= 12 || want_sig));
+    if (variant == 1 && allow_eo) use_pair = false;
+
+    CUtensorMap tmd, tmm;
+    int rc;
+    if (use_pair) {
+        PairChoice pc = pair_choice<TIN>(nm, want_sig);
+        const int kt = pc.kt();
+        const int64_t chunks_kt = (sig_size + kt - 1) / kt;
+        p.k_per_split = ((chunks_kt + p.ksplit - 1) / p.ksplit) * kt;
+        rc = encode_tmap_2d(&tmd, tile, K1In<TIN>::TMAP, sizeof(TIN), (uint64_t)sig_size,
+                            (uint64_t)n_frames, (uint64_t)ld_tile * sizeof(TIN), (uint32_t)kt,
+                            K1_FB);
+        if (rc != LTB_OK) return rc;
+        const int n_pairs = pc.np * pc.mg;
+        float* packed = (float*)(ws + wl.pack_off);
+        const int64_t sig_pad = ((sig_size + 31) / 32) * 32;
+        {
+            const int64_t total = (int64_t)n_pairs * sig_pad;
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > sms * 8) blocks = sms * 8;
+            k1_pack_masks_kernel<<<blocks, 256, 0, st>>>(mk, nm, ld_masks, sig_size, sig_pad,
+                                                         n_pairs, packed);
+            count_launch();
+        }
+        rc = encode_tmap_2d(&tmm, packed, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                            (uint64_t)sig_pad * 2, (uint64_t)n_pairs, (uint64_t)sig_pad * 8,
+                            256, (uint32_t)n_pairs);
+        if (rc != LTB_OK) return rc;
+        if (want_sig && pc.fr == 16) {
+            p.sig_part = (float*)(ws + wl.sig_off);
+            *sig_fused = true;
+        }
+        rc = pc.fn(tmd, tmm, p, grid, st);
+        if (rc != LTB_OK) return rc;
+        set_last_kernel(3);
+    } else {
+        rc = encode_tmap_2d(&tmd, tile, K1In<TIN>::TMAP, sizeof(TIN), (uint64_t)sig_size,
+                            (uint64_t)n_frames, (uint64_t)ld_tile * sizeof(TIN), K1_KT, K1_FB);
+        if (rc != LTB_OK) return rc;
+        const int nrows = nm <= 12 ? nm : 2 * ((nm + 1) / 2);
+        rc = encode_tmap_2d(&tmm, mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)sig_size,
+                            (uint64_t)nm, (uint64_t)ld_masks * 4, K1_KT, (uint32_t)nrows);
+        if (rc != LTB_OK) return rc;
+        rc = k1_launcher_for(nm)(tmd, tmm, p, grid, st);
+        if (rc != LTB_OK) return rc;
+        set_last_kernel(1);
+    }
+    if (p.ksplit > 1) {
+        const int64_t total = n_frames * nm;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        k1_finalize_kernel<<<blocks, 256, 0, st>>>(p.part, p.ksplit, n_frames, nm, o, ld_out,
+                                                   accumulate);
+        count_launch();
+    }
+    if (*sig_fused) {
+        colsum_final_kernel<<<(unsigned)((sig_size + 255) / 256), 256, 0, st>>>(
+            p.sig_part, grid, sig_size, sig_sum);
+        count_launch();
+    }
+    LTB_CUDA_CHECK(cudaGetLastError());
+    return LTB_OK;
+}
+
+}  // namespace ltb
 
 extern "C" int ltb200_masks_dense(const void* tile, int tile_dtype, int64_t n_frames,
                                   int64_t sig_size, int64_t ld_tile, const float* masks,
@@ -522,74 +739,51 @@ extern "C" int ltb200_masks_dense(const void* tile, int tile_dtype, int64_t n_fr
                                              n_masks * sizeof(float), n_frames, st));
         return LTB_OK;
     }
+    const WsLayout wl = ws_layout(n_frames, sig_size, n_masks, sig_sum != nullptr);
+    uint8_t* ws = (uint8_t*)workspace;
 
-    const bool tma_ok = tile_dtype == LTB_F32 && (sig_size % 4 == 0) && (ld_tile % 4 == 0) &&
-                        (ld_masks % 4 == 0) && ((uintptr_t)tile % 16 == 0) &&
-                        ((uintptr_t)masks % 16 == 0) && sig_size >= K1_KT && n_frames >= 8 &&
-                        sig_size < (1ll << 31) && n_frames < (1ll << 31);
+    const size_t esz = dtype_size(tile_dtype);
+    const bool tma_shape_ok = (sig_size * esz) % 16 == 0 && (ld_tile * esz) % 16 == 0 &&
+                              (uintptr_t)tile % 16 == 0 && sig_size >= K1_KT && n_frames >= 8 &&
+                              sig_size < (1ll << 30) && n_frames < (1ll << 31) &&
+                              sig_size % 4 == 0;
+    const bool tma_f32 = tile_dtype == LTB_F32 && tma_shape_ok && (ld_masks % 4 == 0) &&
+                         ((uintptr_t)masks % 16 == 0);
+    const bool tma_u16 = tile_dtype == LTB_U16 && tma_shape_ok;
 
+    bool sig_done = sig_sum == nullptr;
     // mask columns are processed in groups of <= 24 (one pass over the frames per group)
     for (int m0 = 0; m0 < n_masks; m0 += 24) {
         const int nm = (n_masks - m0) > 24 ? 24 : (n_masks - m0);
         const float* mk = masks + (int64_t)m0 * ld_masks;
         float* o = out + m0;
-        if (tma_ok) {
-            const int sms = sm_count();
-            const int64_t n_fb = (n_frames + K1_FB - 1) / K1_FB;
-            K1Params p;
-            p.n_frames = n_frames;
-            p.sig_size = sig_size;
-            p.n_masks = nm;
-            p.ksplit = choose_ksplit(n_fb, sig_size, sms);
-            const int64_t chunks = (sig_size + K1_KT - 1) / K1_KT;
-            p.k_per_split = ((chunks + p.ksplit - 1) / p.ksplit) * K1_KT;
-            p.n_items = n_fb * p.ksplit;
-            p.out = o;
-            p.ld_out = ld_out;
-            p.part = (float*)workspace;
-            p.accumulate = accumulate;
-            p.n_stages = 0;
-            CUtensorMap tmd, tmm;
-            int rc = encode_tmap_2d(&tmd, tile, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                                    (uint64_t)sig_size, (uint64_t)n_frames,
-                                    (uint64_t)ld_tile * 4, K1_KT, K1_FB);
-            if (rc != LTB_OK) return rc;
-            const int nrows = nm <= 12 ? nm : 2 * ((nm + 1) / 2);
-            rc = encode_tmap_2d(&tmm, mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)sig_size,
-                                (uint64_t)nm, (uint64_t)ld_masks * 4, K1_KT, (uint32_t)nrows);
-            if (rc != LTB_OK) return rc;
-            const int grid = (int)(p.n_items < sms ? p.n_items : sms);
-            K1Launcher launch = k1_launcher_for(nm);
-            rc = launch(tmd, tmm, p, grid, st);
-            if (rc != LTB_OK) return rc;
-            if (p.ksplit > 1) {
-                const int64_t total = n_frames * nm;
-                int blocks = (int)((total + 255) / 256);
-                if (blocks > sms * 8) blocks = sms * 8;
-                k1_finalize_kernel<<<blocks, 256, 0, st>>>(p.part, p.ksplit, n_frames, nm, o,
-                                                           ld_out, accumulate);
-                count_launch();
-                LTB_CUDA_CHECK(cudaGetLastError());
-            }
-            set_last_kernel(1);
+        bool fused = false;
+        int rc;
+        if (tma_f32) {
+            rc = run_tma_group<float>(tile, n_frames, sig_size, ld_tile, mk, nm, ld_masks, o,
+                                      ld_out, accumulate, sig_done ? nullptr : sig_sum, ws, wl,
+                                      true, st, &fused);
+        } else if (tma_u16) {
+            rc = run_tma_group<uint16_t>(tile, n_frames, sig_size, ld_tile, mk, nm, ld_masks, o,
+                                         ld_out, accumulate, sig_done ? nullptr : sig_sum, ws,
+                                         wl, false, st, &fused);
         } else {
-            int rc = dispatch_generic<float>(tile, tile_dtype, n_frames, sig_size, ld_tile, mk, nm,
-                                             ld_masks, o, ld_out, accumulate, st);
-            if (rc != LTB_OK) return rc;
+            rc = dispatch_generic<float>(tile, tile_dtype, n_frames, sig_size, ld_tile, mk, nm,
+                                         ld_masks, o, ld_out, accumulate, st);
             set_last_kernel(2);
         }
+        if (rc != LTB_OK) return rc;
+        if (fused) sig_done = true;
     }
 
-    if (sig_sum != nullptr) {
-        size_t off = n_masks > 0 ? k1_part_bytes(n_frames, sig_size, n_masks > 24 ? 24 : n_masks) : 0;
-        off = (off + 255) & ~(size_t)255;
-        float* ws = (float*)((uint8_t*)workspace + off);
+    if (!sig_done) {
+        float* wsf = (float*)(ws + wl.sig_off);
         switch (tile_dtype) {
-            case LTB_F32: return launch_colsum<float>(tile, n_frames, sig_size, ld_tile, sig_sum, ws, st);
-            case LTB_U16: return launch_colsum<uint16_t>(tile, n_frames, sig_size, ld_tile, sig_sum, ws, st);
-            case LTB_U8: return launch_colsum<uint8_t>(tile, n_frames, sig_size, ld_tile, sig_sum, ws, st);
-            case LTB_I8: return launch_colsum<int8_t>(tile, n_frames, sig_size, ld_tile, sig_sum, ws, st);
-            case LTB_I16: return launch_colsum<int16_t>(tile, n_frames, sig_size, ld_tile, sig_sum, ws, st);
+            case LTB_F32: return launch_colsum<float>(tile, n_frames, sig_size, ld_tile, sig_sum, wsf, st);
+            case LTB_U16: return launch_colsum<uint16_t>(tile, n_frames, sig_size, ld_tile, sig_sum, wsf, st);
+            case LTB_U8: return launch_colsum<uint8_t>(tile, n_frames, sig_size, ld_tile, sig_sum, wsf, st);
+            case LTB_I8: return launch_colsum<int8_t>(tile, n_frames, sig_size, ld_tile, sig_sum, wsf, st);
+            case LTB_I16: return launch_colsum<int16_t>(tile, n_frames, sig_size, ld_tile, sig_sum, wsf, st);
             default:
                 set_error("masks_dense: sig_sum not supported for tile dtype %d (float32 path)",
                           tile_dtype);

@@ -143,3 +143,8 @@ def masks_csc(tile, indptr, indices, values, n_masks, out=None, accumulate=False
             indices.data_ptr(), values.data_ptr(), int(n_masks), out.data_ptr(), ld_out,
             int(bool(accumulate)), _stream_ptr(tile.device)))
     return out
+
+
+def set_k1_variant(variant):
+    """0 auto, 1 even/odd-pixel tile, 2 mask-pair tile (tuning / tests)"""
+    check(get_lib().ltb200_set_k1_variant(int(variant)))

@@ -213,10 +213,18 @@ class UDFRunner:
                 else:
                     self._run_unfused(pu, tile)
             elif kind == 'csc':
-                view = getattr(pu.results, spec['buffer'])
-                spec['engine'].process_flat(flat, out=view, accumulate=True,
-                                            sig_slice=sig_slice)
-                self.stats['fused_launch_groups'] += 1
+                eng = spec['engine']
+                tma_able = (flat.dtype in (torch.float32, torch.uint16)
+                            and flat.shape[1] % 8 == 0 and flat.shape[1] >= 128
+                            and flat.shape[0] >= 8)
+                if tma_able and len(eng.masks) <= MAX_FUSED_COLUMNS:
+                    # the frames are streamed once anyway: a few sparse masks ride along as
+                    # dense rows of the fused pass (exact same sums; zeros contribute nothing)
+                    dense.append((pu, spec, eng.dense_rows(sig_slice)))
+                else:
+                    view = getattr(pu.results, spec['buffer'])
+                    eng.process_flat(flat, out=view, accumulate=True, sig_slice=sig_slice)
+                    self.stats['fused_launch_groups'] += 1
             else:
                 self._run_unfused(pu, tile)
         if not dense and sig_sum_view is None:
