@@ -11,11 +11,11 @@
  *                              (udf/sumsigudf.py:28-38) is an all-ones mask row.
  *   ltb200_masks_dense_f64  <- the same seam when np.result_type(input, mask) is float64
  *                              (udf/masks.py:360-368 dtype rule).
- *   ltb200_masks_csr        <- ApplyMasksEngine._process_flat_spsp -> rmatmul
+ *   ltb200_masks_csc        <- ApplyMasksEngine._process_flat_spsp -> rmatmul
  *                              (udf/masks.py:68-69, common/numba/__init__.py:90-184).
- *   ltb200_frame_pass       <- one fused pass for [SumUDF, SumSigUDF, ApplyMasksUDF(sparse)]:
- *                              udf/sum.py:44-49, udf/sumsigudf.py:28-38, udf/masks.py:383-392.
- *   ltb200_radial_fourier   <- ApplyMasksUDF with radial_mask_factory masks
+ *                              (`sig_sum` of ltb200_masks_dense fuses SumUDF, udf/sum.py:44-49,
+ *                              into the same pass; uint16 tiles are ingested natively.)
+ *   ltb200_group_masks      <- ApplyMasksUDF with radial_mask_factory masks
  *                              (analysis/radialfourier.py:106-146,184-194).
  *   ltb200_synth_fill       <- test/bench data source standing in for MemoryDataSet contents
  *                              (io/dataset/memory.py:202-452); twin of oracle/synth.py.
@@ -119,6 +119,24 @@ LTB_API int ltb200_masks_csc(const void* tile, int tile_dtype, int64_t n_frames,
                      int64_t ld_tile, const int32_t* indptr, const int32_t* indices,
                      const float* values, int n_masks, float* out, int64_t ld_out,
                      int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Group-sparse masked reduction (K4) -- RadialFourierAnalysis: masks come in groups (rings)
+ * whose members (orders) share one pixel support.  Per group g: entries
+ * [group_off[g], group_off[g+1]) (multiples of 128, zero-weight padded) with pixel index
+ * entry_px[e]; table_packed holds 28 "pair rows" x (2 * n_entries) floats: row p = the
+ * (re, im) / (col 2p, col 2p+1) weights of every entry, in the bank-conflict-free order
+ * documented in libertem_b200/group_masks.py.  out[f, (g*n_pairs + p)*2 + {0,1}] (+)= sums,
+ * i.e. a complex64 (n_frames, n_groups*n_pairs) matrix.  float32 tiles only.
+ * group_off is passed twice: host copy (validated) and device copy (read by the kernel).
+ * ------------------------------------------------------------------------------------- */
+LTB_API size_t ltb200_group_masks_workspace(void);
+LTB_API int ltb200_group_masks(const void* tile, int tile_dtype, int64_t n_frames,
+                               int64_t sig_size, int64_t ld_tile, const int32_t* entry_px,
+                               const float* table_packed, const int32_t* group_off_host,
+                               const int32_t* group_off_dev, int n_groups, int n_pairs,
+                               float* out, int64_t ld_out, int accumulate, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic data (twin of oracle/synth.py): fills dst[0..count) with value(start + i).

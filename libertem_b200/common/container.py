@@ -202,6 +202,24 @@ class MaskContainer:
             self._device_cache[key] = hit
         return hit
 
+    def get_group_plan(self, slice_, device):
+        """group-sparse plan for the K4 kernel (libertem_b200/group_masks.py) or None when
+        the stack has no uniform group structure / is not sparse enough to pay off"""
+        from .. import group_masks as gm
+        key = ('group', slice_, str(device))
+        if key in self._device_cache:
+            return self._device_cache[key]
+        stack = np.asarray(self._dense_stack_for(slice_))
+        size = gm.find_groups(stack)
+        plan = None
+        if size is not None and size >= 2:
+            support = np.any(stack.reshape(stack.shape[0] // size, size, -1) != 0, axis=1)
+            # worth it when the gathered entries are few compared with columns x pixels
+            if np.count_nonzero(support) * size < 0.5 * stack.shape[0] * stack.shape[1]:
+                plan = gm.build_plan(stack, size, device)
+        self._device_cache[key] = plan
+        return plan
+
     def get_device_csc(self, slice_, device):
         import torch
         import scipy.sparse as sp

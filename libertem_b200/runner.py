@@ -212,6 +212,16 @@ class UDFRunner:
                     sig_sum_view = getattr(pu.results, spec['buffer']).reshape(-1)
                 else:
                     self._run_unfused(pu, tile)
+            elif kind == 'own_pass':
+                # group-sparse complex masks (K4): a pass of their own through the engine
+                if flat.dtype == torch.float32:
+                    view = getattr(pu.results, spec['buffer'])
+                    out = self._real_view(view, 2 * view.shape[1])
+                    spec['engine'].process_flat(flat, out=out, accumulate=True,
+                                                sig_slice=sig_slice)
+                    self.stats['fused_launch_groups'] += 1
+                else:
+                    self._run_unfused(pu, tile)
             elif kind == 'csc':
                 eng = spec['engine']
                 tma_able = (flat.dtype in (torch.float32, torch.uint16)

@@ -45,6 +45,15 @@ class ApplyMasksEngine:
         else:
             self.compute = np.float64
 
+    def group_plan(self, sig_slice=None):
+        """K4 plan when the masks are complex64, numerous and group-sparse (all members of a
+        run of consecutive masks share one support -- radial Fourier rings), else None.
+        Built once per MaskContainer (shared by the partition copies of the UDF)."""
+        if self.result_dtype != np.complex64 or len(self.masks) <= 12:
+            return None
+        sl = self.meta.sig_slice if sig_slice is None else sig_slice
+        return self.masks.get_group_plan(sl, self.device)
+
     @property
     def device(self):
         return self.meta.device if self.meta.device is not None else torch.device('cuda')
@@ -65,6 +74,15 @@ class ApplyMasksEngine:
 
     def process_flat(self, flat_tile, out=None, accumulate=False, sig_slice=None):
         """the seam of masks.py:31-83: ``flat_tile (F, K) -> (F, R)`` real columns"""
+        if flat_tile.dtype == torch.float32:
+            plan = self.group_plan(sig_slice)
+            if plan is not None:
+                from .. import group_masks as gm
+                cout = None
+                if out is not None:
+                    cout = torch.view_as_complex(out.reshape(out.shape[0], -1, 2))
+                res = gm.group_masks(flat_tile, plan, out=cout, accumulate=accumulate)
+                return torch.view_as_real(res).reshape(res.shape[0], -1)
         if self.sparse and flat_tile.dtype in (torch.float32, torch.uint16, torch.uint8,
                                                torch.int16, torch.int8):
             sl = self.meta.sig_slice if sig_slice is None else sig_slice
@@ -211,5 +229,7 @@ class ApplyMasksUDF(UDF):
             return {'kind': 'csc', 'buffer': 'intensity', 'engine': eng}
         if eng.compute != np.float32:
             return None
+        if eng.group_plan() is not None:
+            return {'kind': 'own_pass', 'buffer': 'intensity', 'engine': eng}
         return {'kind': 'dense', 'buffer': 'intensity', 'engine': eng,
                 'columns': eng.n_real_columns()}

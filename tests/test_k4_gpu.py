@@ -1,0 +1,58 @@
+"""GPU parity of the group-sparse kernel K4 (ltb200_group_masks) against numpy."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_stack(n_groups, size, K, seed, empty_group=None):
+    rng = np.random.default_rng(seed)
+    stack = np.zeros((n_groups * size, K), dtype=np.complex64)
+    for g in range(n_groups):
+        if g == empty_group:
+            continue
+        n = int(rng.integers(1, max(2, K // 3)))
+        px = np.sort(rng.choice(K, size=n, replace=False))
+        vals = (rng.random((size, n)) - 0.5 + 1j * (rng.random((size, n)) - 0.5))
+        vals[np.abs(vals) == 0] = 0.25
+        stack[g * size:(g + 1) * size, px] = vals.astype(np.complex64)
+    return stack
+
+
+@pytest.mark.parametrize('F,K,n_groups,size', [(64, 512, 3, 25), (100, 1000, 5, 7), (7, 300, 2, 28),
+                                               (200, 4096, 32, 25), (65, 640, 4, 1)])
+def test_group_masks_matches_numpy(F, K, n_groups, size):
+    from libertem_b200 import group_masks as gm
+    stack = make_stack(n_groups, size, K, seed=F + K, empty_group=1 if n_groups > 3 else None)
+    assert gm.find_groups(stack) in (size, None) or size == 1
+    plan = gm.build_plan(stack, size, torch.device('cuda'))
+    data = synth.uniform_f32(0, F * K, 9).reshape(F, K)
+    t = torch.from_numpy(data).cuda()
+    out = gm.group_masks(t, plan).cpu().numpy()
+    ref = data.astype(np.float64) @ stack.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(stack).astype(np.float64).T).max() + 1e-30
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    # accumulate
+    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True).cpu().numpy()
+    assert np.abs(out2 - 2 * ref).max() / scale <= 4e-6
+    # strided tile
+    big = torch.zeros((F, K + 24), device='cuda')
+    big[:, 8:8 + K] = t
+    out3 = gm.group_masks(big[:, 8:8 + K], plan).cpu().numpy()
+    assert np.array_equal(out3, out)
+
+
+def test_find_groups():
+    from libertem_b200 import group_masks as gm
+    s = make_stack(4, 5, 200, seed=3)
+    assert gm.find_groups(s) == 5
+    s[7, :] = 1           # breaks the uniform structure
+    assert gm.find_groups(s) is None
+    packed = gm.pack_rows(np.arange(2 * 64 * 2, dtype=np.float32).reshape(2, 64, 2))
+    # entry 4q+c of block 0, component w -> (c//2)*32 + q*4 + (c%2)*2 + w
+    for (q, c, w) in [(0, 0, 0), (3, 1, 1), (7, 2, 0), (5, 3, 1)]:
+        assert packed[0, (c // 2) * 32 + q * 4 + (c % 2) * 2 + w] == (4 * q + c) * 2 + w
