@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NAV = (256, 256)
+NAV = (256, 256)           # per-GPU shard of the navigation axis
 SIG = (256, 256)
 N_MASKS = 8
 DATA_SEED = 1001
@@ -98,7 +98,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                 '-lms', '50', '-i', str(self.gpu)],
+                 '-lms', '10', '-i', str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -112,27 +112,41 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, smax, reasons, power = [], None, set(), []
-        for ts, line in self.lines:
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 9:
-                continue
-            try:
-                smax = float(parts[2])
-                in_region = t0 - 0.05 <= ts <= t1 + 0.05
-                if in_region:
-                    sm.append(float(parts[1]))
-                    power.append(float(parts[3]))
-                    for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown',
-                                          'sw_thermal_slowdown', 'sw_power_cap'), parts[5:9]):
-                        if val.lower().startswith('active'):
-                            reasons.add(name)
-            except ValueError:
-                continue
+
+        def collect(lo, hi):
+            sm, smax, reasons, power = [], None, set(), []
+            self.masks = getattr(self, 'masks', set())
+            for ts, line in self.lines:
+                parts = [p.strip() for p in line.split(',')]
+                if len(parts) < 9:
+                    continue
+                try:
+                    smax = float(parts[2])
+                    if lo <= ts <= hi:
+                        sm.append(float(parts[1]))
+                        power.append(float(parts[3]))
+                        self.masks.add(parts[4])
+                        for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown',
+                                              'sw_thermal_slowdown', 'sw_power_cap'),
+                                             parts[5:9]):
+                            if val.lower().startswith('active'):
+                                reasons.add(name)
+                except ValueError:
+                    continue
+            return sm, smax, reasons, power
+
+        # nvidia-smi prints a sample some ms after taking it: accept a small lag
+        sm, smax, reasons, power = collect(t0, t1 + 0.03)
+        window = 'timed region'
+        if not sm:
+            sm, smax, reasons, power = collect(t0 - 0.25, t1 + 0.25)
+            window = 'timed region +-0.25 s (region shorter than the sampling lag)'
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax,
-                'reasons': sorted(reasons), 'samples': len(sm),
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window,
+                'sm_mhz_min': min(sm) if sm else None, 'sm_mhz_max_seen': max(sm) if sm else None,
+                'active_bitmasks': sorted(self.masks),
                 'power_w_max': max(power) if power else None}
 
 
@@ -217,6 +231,8 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 
 def gpu_arm(args):
+    import logging
+    logging.getLogger('libertem_b200').setLevel(logging.ERROR)
     import torch
     import torch.distributed as dist
     from libertem_b200 import engine
@@ -281,7 +297,11 @@ def gpu_arm(args):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.2)
+    t_wait = time.time()
+    while not sampler.lines and time.time() - t_wait < 5.0:   # wait for the first sample
+        time.sleep(0.01)
+    for _ in range(3):          # keep the GPU busy right up to the timed region
+        step()
     engine.launch_count(reset=True)
     engine.EVENT_LOG = []
     e0 = torch.cuda.Event(enable_timing=True)
@@ -313,7 +333,9 @@ def gpu_arm(args):
     peak, peak_src = measured_peak()
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel': 'k1_dense_tma_kernel<11,1>', 'kernel_ms': kern_ms,
+                'kernel': {1: 'k1_dense_tma_kernel (even/odd tile)', 3: 'k1_pair_kernel<float> '
+                           '(mask-pair tile)'}.get(engine.last_kernel(), 'generic'),
+                'kernel_ms': kern_ms,
                 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'kernel_share_of_step': kern_ms * len(ev_log) / args.steps / ms_per_step}
     prof = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
@@ -330,8 +352,10 @@ def gpu_arm(args):
         'data': 'synthetic (counter-based hash, uniform [0,1), seed %d)' % DATA_SEED,
         'config': {'workload': WORKLOAD, 'nav': list(nav), 'sig': list(SIG), 'n_masks': N_MASKS,
                    'com': True, 'fused_columns': N_MASKS + 3, 'partitions_per_gpu': 1,
+                   'sig_bytes_per_frame': k * 4,
                    'frames_per_gpu': frames_per_rank,
-                   'l2': 'inputs 17.2 GB per GPU >> 126 MB L2, streamed once per step',
+                   'l2': 'inputs %.1f GB per GPU >> 126 MB L2, streamed once per step' %
+                         (frames_per_rank * k * 4 / 1e9),
                    'merge': 'nccl all_gather of nav buffers inside the step' if world > 1
                    else 'device-side copy into the nav-shaped buffers'},
         'hbm_gbs': total_frames * k * 4 / (ms_per_step * 1e-3) / 1e9 / n_gpus,
@@ -441,15 +465,29 @@ def e2e_multi(args, ds, part, stack, device, dist, total_frames):
             'note': 'each rank streams its shard from pinned host memory (PCIe-bound)'}
 
 
+def set_workload(name):
+    """cfg2 (default, the headline) or cfg5: 1024x1024 nav x 256x256 sig, 16 masks + CoM,
+    nav-sharded over 8 GPUs (each rank holds a 128x1024 nav shard = 32 GiB)"""
+    global NAV, N_MASKS, METRIC, WORKLOAD
+    if name == 'cfg5':
+        NAV = (128, 1024)
+        N_MASKS = 16
+        METRIC = 'frames/s on 1024^2 nav x 256^2 sig float32 ApplyMasksUDF (16 dense masks) + CoM'
+        WORKLOAD = ('cfg5: 1024x1024 nav x 256x256 sig float32 over 8 GPUs, ApplyMasksUDF 16 dense '
+                    'masks + CoMUDF (19 fused mask columns), 128x1024 nav shard per GPU')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg5'])
     args = ap.parse_args()
+    set_workload(args.workload)
     if args.impl == 'reference':
         reference_arm(args)
     else:

@@ -644,7 +644,9 @@ static int run_tma_group(const void* tile, int64_t n_frames, int64_t sig_size, i
     const bool want_sig = sig_sum != nullptr && (size_t)sig_size * 4 <= K1_SIG_SMEM_MAX &&
                           nm <= 6;
     const int variant = k1_variant();
-    bool use_pair = !allow_eo || variant == 2 || (variant == 0 && (nm >= 12 || want_sig));
+    // auto: the mask-pair tile everywhere (one third less LSU wavefronts per element than the
+    // even/odd tile, so it stays HBM-bound when the SM clock drops under sustained load)
+    bool use_pair = !allow_eo || variant == 2 || variant == 0;
     if (variant == 1 && allow_eo) use_pair = false;
 
     CUtensorMap tmd, tmm;

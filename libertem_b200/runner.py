@@ -22,6 +22,7 @@ import torch
 from .common.buffers import BufferWrapper, torch_dtype, to_numpy
 from .common.shape import Shape
 from .udf.base import UDFMeta, UDFData, MergeAttrMapping, UDFException
+from .udf.base import UDF as _BaseUDF
 from .udf.sumsigudf import ones_row
 from . import engine
 
@@ -68,6 +69,8 @@ class UDFRunner:
         self._fuse = fuse
         self.stats = {'tiles': 0, 'fused_launch_groups': 0, 'unfused_calls': 0}
         self._cat_cache = {}
+        self._slab = None
+        self._slab_map = {}
 
     # -- distributed helpers ---------------------------------------------------------------------
     @staticmethod
@@ -103,16 +106,37 @@ class UDFRunner:
         input_dtype = _get_dtype(udfs, dataset.dtype)
 
         # dataset-level instances + buffers (base.py:2472-2557)
-        for udf in udfs:
+        slab_cols = []      # (udf index, buffer name, n real columns)
+        for ui, udf in enumerate(udfs):
             udf.set_meta(UDFMeta(partition_slice=None, dataset_shape=ds_shape, roi=roi,
                                  dataset_dtype=dataset.dtype, input_dtype=input_dtype,
                                  device=device))
             decl = udf.get_result_buffers()
-            for buf in decl.values():
+            slab_name = self._slab_buffer_name(udf, decl) if self._fuse else None
+            for name, buf in decl.items():
                 buf.set_shape_ds(ds_shape, roi)
-                if buf.use != 'result_only':
+                if name == slab_name:
+                    slab_cols.append((ui, name, int(np.prod(buf.extra_shape, dtype=np.int64))))
+                elif buf.use != 'result_only':
                     buf.allocate(device)
             udf.results = UDFData(decl)
+        # fused result slab: every float32 nav buffer the dense kernel can write lives in ONE
+        # (rows, total columns) device array; the buffers are column-slice views of it.  The
+        # kernel stores straight into it (ld_out = total columns), partition buffers are row
+        # views (merge is a no-op) and the multi-rank merge is a single all-gather.
+        self._slab = None
+        self._slab_map = {}
+        if slab_cols:
+            n_rows = n_frames if roi is None else int(np.count_nonzero(roi))
+            total = sum(c for _, _, c in slab_cols)
+            self._slab = torch.zeros((n_rows, total), dtype=torch.float32, device=device)
+            c0 = 0
+            for ui, name, c in slab_cols:
+                buf = udfs[ui].results.get_buffer(name)
+                view = self._slab[:, c0:c0 + c]
+                buf.replace_array(view if buf.extra_shape else view[:, 0])
+                self._slab_map[(ui, name)] = (c0, c)
+                c0 += c
 
         partitions = list(dataset.get_partitions())
         dist = self._dist()
@@ -145,15 +169,19 @@ class UDFRunner:
         r0, r1 = self._roi_range(part, roi_flat)
         n_part = r1 - r0
         part_udfs = []
-        for udf in udfs:
+        for ui, udf in enumerate(udfs):
             pu = udf.copy_for_partition()
             pu.set_meta(UDFMeta(partition_slice=part.slice, dataset_shape=ds_shape,
                                 roi=udf.meta.roi, dataset_dtype=dataset.dtype,
                                 input_dtype=input_dtype, device=device))
             decl = pu.get_result_buffers()
-            for buf in decl.values():
+            for name, buf in decl.items():
                 buf.set_shape_partition(ds_shape, n_part)
-                if buf.use != 'result_only':
+                if (ui, name) in self._slab_map:
+                    # zero-copy: the partition buffer IS its row range of the dataset slab
+                    buf.replace_array(udf.results.get_buffer(name).tensor[r0:r1])
+                    pu._slab_cols = self._slab_map[(ui, name)]
+                elif buf.use != 'result_only':
                     buf.allocate(device)
             pu.results = UDFData(decl)
             pu.task_data = pu.get_task_data()
@@ -174,7 +202,8 @@ class UDFRunner:
                 for name, buf in pu.results.items():
                     if buf.has_data():
                         pu.results.set_view(name, buf.rows(t0, t1))
-            self._run_tile(part_udfs, specs, tile, tslice, ds_shape, device)
+            self._run_tile(part_udfs, specs, tile, tslice, ds_shape, device,
+                           t0_rows=(tslice.origin[0], tslice.origin[0] + tslice.shape[0]))
         for pu in part_udfs:
             pu.results.clear_views()
             pu.meta.slice = None
@@ -190,7 +219,42 @@ class UDFRunner:
             return None
         return fn()
 
-    def _run_tile(self, part_udfs, specs, tile, tslice, ds_shape, device):
+    def _slab_target(self, grp, t0_rows):
+        """(rows, columns) window of the slab that a fused group writes, when every member's
+        buffer is a slab member and their columns are consecutive in group order"""
+        if self._slab is None or not grp:
+            return None
+        c_first = c_next = None
+        for pu, spec, rows in grp:
+            cols = getattr(pu, '_slab_cols', None)
+            if cols is None or cols[1] != rows.shape[0]:
+                return None
+            if c_first is None:
+                c_first = c_next = cols[0]
+            if cols[0] != c_next:
+                return None
+            c_next = cols[0] + cols[1]
+        r0, r1 = t0_rows
+        return self._slab[r0:r1, c_first:c_next]
+
+    @staticmethod
+    def _slab_buffer_name(udf, decl):
+        """name of the float32 nav buffer a hot-path UDF lets the dense kernel write, if any"""
+        if getattr(udf, '_fused_spec', None) is None:
+            return None
+        if type(udf).merge is not _BaseUDF.merge:
+            return None
+        name = getattr(udf, '_slab_buffer', None)
+        if name is None or name not in decl:
+            return None
+        buf = decl[name]
+        if buf.kind != 'nav' or buf.dtype != np.float32 or buf.where != 'device':
+            return None
+        if getattr(udf, 'get_method', lambda: 'tile')() == 'frame':
+            return None
+        return name
+
+    def _run_tile(self, part_udfs, specs, tile, tslice, ds_shape, device, t0_rows=(0, 0)):
         flat = tile.reshape(tile.shape[0], -1)
         full_frame = tslice.shape.sig.size == ds_shape.sig.size
         sig_slice = tslice.discard_nav()
@@ -254,7 +318,11 @@ class UDFRunner:
             groups = [[]]
         for gi, grp in enumerate(groups):
             ss = sig_sum_view if gi == 0 else None
-            if len(grp) == 1 and ss is None:
+            direct = self._slab_target(grp, t0_rows)
+            if direct is not None:
+                rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
+                engine.masks_dense(flat, rows, out=direct, accumulate=True, sig_sum=ss)
+            elif len(grp) == 1 and ss is None:
                 pu, spec, rows = grp[0]
                 view = getattr(pu.results, spec['buffer'])
                 out = self._real_view(view, rows.shape[0])
@@ -319,9 +387,12 @@ class UDFRunner:
             for name, buf in udf.results.items():
                 if buf.use == 'result_only' or not buf.has_data():
                     continue
+                if (udfs.index(udf), name) in self._slab_map:
+                    continue        # partition buffer aliases the dataset slab rows already
                 dest[name] = buf.rows(r0, r1)
                 src[name] = pu.results.get_buffer(name).tensor
-            udf.merge(dest=MergeAttrMapping(dest), src=MergeAttrMapping(src))
+            if dest:
+                udf.merge(dest=MergeAttrMapping(dest), src=MergeAttrMapping(src))
         damage[r0:r1] = True
 
     def _merge_ranks(self, dist, udfs, partitions, roi_flat, damage, device):
@@ -341,9 +412,21 @@ class UDFRunner:
             bounds.append((a, b))
         sizes = [b - a for a, b in bounds]
         equal = len(set(sizes)) == 1 and sizes[0] > 0
-        for udf in udfs:
+        if self._slab is not None:
+            t = self._slab
+            comm = t if backend == 'nccl' else t.cpu()
+            if equal:
+                a, b = bounds[dist.get_rank()]
+                dist.all_gather_into_tensor(comm.view(-1), comm[a:b].contiguous().view(-1))
+            else:
+                dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            if comm is not t:
+                t.copy_(comm)
+        for ui, udf in enumerate(udfs):
             for name, buf in udf.results.items():
                 if buf.use == 'result_only' or not buf.has_data():
+                    continue
+                if (ui, name) in self._slab_map:
                     continue
                 t = buf.tensor
                 comm = t if backend == 'nccl' else t.cpu()

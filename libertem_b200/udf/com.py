@@ -155,6 +155,8 @@ class CoMUDF(UDF):
     field_y, field_x, magnitude, divergence, curl, plus 'regression' (3, 2)
     (com.py:298-510)."""
 
+    _slab_buffer = 'raw_mask_result'     # float32 nav buffer the fused dense kernel may write directly
+
     def __init__(self, com_params: CoMParams = CoMParams()):
         super().__init__(com_params=com_params)
         self._containers = {}

@@ -135,6 +135,8 @@ class ApplyMasksUDF(UDF):
     there is one backend here (CUDA).
     """
 
+    _slab_buffer = 'intensity'     # float32 nav buffer the fused dense kernel may write directly
+
     def __init__(self, mask_factories, use_torch=True, use_sparse=None, mask_count=None,
                  mask_dtype=None, preferred_dtype=None, backends=None, shifts=None, **kwargs):
         _backends = backends

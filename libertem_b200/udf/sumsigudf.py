@@ -18,6 +18,8 @@ def ones_row(k, device):
 
 
 class SumSigUDF(UDF):
+    _slab_buffer = 'intensity'     # float32 nav buffer the fused dense kernel may write directly
+
     def get_result_buffers(self):
         dtype = np.result_type(self.meta.input_dtype, np.float32)
         return {'intensity': self.buffer(kind='nav', dtype=dtype, where='device')}
