@@ -84,8 +84,9 @@ struct K1PairCfg {
     static constexpr size_t MASK_BYTES = (size_t)NPR * 2 * KT * 4;
     static constexpr size_t STAGE_BYTES = DATA_BYTES + MASK_BYTES;
     static constexpr int RED_ROWS = K1_CWARPS - FG * MG > 0 ? K1_CWARPS - FG * MG : 1;
+    static constexpr int RED_BUFS = 2;                   // double-buffered by item parity
     static constexpr size_t FIXED_BYTES =
-        2 * K1_MAX_STAGES * sizeof(uint64_t) + (size_t)RED_ROWS * NV * 32 * 4;
+        2 * K1_MAX_STAGES * sizeof(uint64_t) + (size_t)RED_BUFS * RED_ROWS * NV * 32 * 4;
     static_assert(FG >= 1 && KS >= 1 && SPC >= 1, "bad K1 pair geometry");
     static_assert(FG * MG * KS == K1_CWARPS, "warps must tile the CTA");
 };
@@ -104,8 +105,8 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
     const int S = p.n_stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + K1_MAX_STAGES;
-    float* red = reinterpret_cast<float*>(empty_bar + K1_MAX_STAGES);   // [RED_ROWS][NV][32]
-    float* sig_s = red + C::RED_ROWS * NV * 32;                         // [sig_size] (optional)
+    float* red_base = reinterpret_cast<float*>(empty_bar + K1_MAX_STAGES);  // [2][RED_ROWS][NV][32]
+    float* sig_s = red_base + C::RED_BUFS * C::RED_ROWS * NV * 32;          // [sig_size] (optional)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -166,8 +167,9 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
         float2 acc[FR][NP];
         float tot[NV];
         uint32_t it = 0;
+        uint32_t item_parity = 0;
 
-        for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, item_parity ^= 1) {
             const int64_t fb = item / p.ksplit;
             const int ksi = (int)(item % p.ksplit);
             const int64_t k0 = (int64_t)ksi * p.k_per_split;
@@ -271,12 +273,26 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
 
             // lane (fl, q) holds frames j = q*(FR/8) + jj, columns mg*2NP .. ; combine the KS
             // pixel-split warps: warps with ks > 0 publish, the ks == 0 warp adds in fixed order
+            // The exchange buffer is double-buffered by item parity and the barrier is split:
+            // publishing warps only ARRIVE and move on to the next item, the collecting warp
+            // SYNCs.  A publisher cannot lap the collector by two items because every pipeline
+            // stage needs all eight warps (safe whenever an item has more chunks than stages).
+            float* red = red_base + item_parity * (C::RED_ROWS * NV * 32);
             const int red_row = (cw / KS) * (KS - 1) + (ks - 1);
+            const bool split_bar = KS > 1 && nchunks >= 2 * S;
             if (ks > 0) {
 #pragma unroll
                 for (int i = 0; i < NV; i++) red[(red_row * NV + i) * 32 + lane] = tot[i];
+                if (split_bar) {
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + (int)(cw / KS)), "r"(KS * 32)
+                                 : "memory");
+                } else {
+                    named_bar_sync(1 + (int)(cw / KS), KS * 32);
+                }
+            } else if (KS > 1) {
+                named_bar_sync(1 + (int)(cw / KS), KS * 32);
             }
-            named_bar_sync(1, K1_CWARPS * 32);
             if (ks == 0) {
 #pragma unroll
                 for (int jj = 0; jj < FR / 8; jj++) {
@@ -303,7 +319,7 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
                     }
                 }
             }
-            named_bar_sync(1, K1_CWARPS * 32);
+            if (KS > 1 && !split_bar) named_bar_sync(9 + (int)(cw / KS), KS * 32);
         }
     }
     if (do_sig) {
