@@ -19,7 +19,7 @@ class Context:
         return MemoryDataSet(*args, **kwargs)
 
     def run_udf(self, dataset, udf, roi=None, progress=False, corrections=None, backends=None):
-        return _run_udf(dataset, udf, roi=roi, device=self.device)
+        return _run_udf(dataset, udf, roi=roi, device=self.device, corrections=corrections)
 
     def run(self, analysis, roi=None):
         udf = analysis.get_udf()

@@ -29,10 +29,13 @@ from . import engine
 MAX_FUSED_COLUMNS = 24
 
 
-def _get_dtype(udfs, dtype):
+def _get_dtype(udfs, dtype, corrections=None):
     """input dtype of the run: result_type over every UDF's preferred dtype
     (reference udf/base.py:106-123)"""
-    tmp = np.dtype(dtype)
+    if corrections is not None and corrections.have_corrections():
+        tmp = np.result_type(np.float32, dtype)
+    else:
+        tmp = np.dtype(dtype)
     for udf in udfs:
         pref = udf.get_preferred_input_dtype()
         if pref is bool or pref is udf.USE_NATIVE_DTYPE:
@@ -71,6 +74,11 @@ class UDFRunner:
         self._cat_cache = {}
         self._slab = None
         self._slab_map = {}
+        self._corr = None
+        self._corr_fold = False
+        self._fold_cache = {}
+        self._slice_corr = {}
+        self._sig_sum_folded = []
 
     # -- distributed helpers ---------------------------------------------------------------------
     @staticmethod
@@ -103,7 +111,14 @@ class UDFRunner:
                 raise UDFException('roi must be a boolean array of the navigation shape')
             roi = roi.reshape(tuple(ds_shape.nav))
         roi_flat = None if roi is None else roi.reshape(-1)
-        input_dtype = _get_dtype(udfs, dataset.dtype)
+        if corrections is not None and not corrections.have_corrections():
+            corrections = None
+        input_dtype = _get_dtype(udfs, dataset.dtype, corrections)
+        self._corr = corrections
+        # corrections fold into the masks (libertem_b200/corrections.py) when every tile is a
+        # full frame; sub-frame tilings get explicitly corrected tiles like in the reference
+        self._corr_fold = corrections is not None and getattr(dataset, 'tileshape', None) is None
+        self._sig_sum_folded = []
 
         # dataset-level instances + buffers (base.py:2472-2557)
         slab_cols = []      # (udf index, buffer name, n real columns)
@@ -151,6 +166,13 @@ class UDFRunner:
                 self._merge_partition(part, udfs, part_udfs, roi_flat, damage)
         if dist:
             self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device)
+        if self._corr is not None and self._sig_sum_folded:
+            n_done = int(damage.sum())
+            for udf, name in self._sig_sum_folded:
+                buf = udf.results.get_buffer(name)
+                fixed = self._corr.correct_frame_sum(to_numpy(buf.tensor), n_done)
+                buf.tensor.copy_(torch.from_numpy(fixed.astype(np.float32)).reshape(
+                    buf.tensor.shape))
         if not finalize:
             # hot path only (tiles -> kernels -> merge [-> collectives]); results stay in
             # the UDFs' device buffers (udf.results)
@@ -219,13 +241,43 @@ class UDFRunner:
             return None
         return fn()
 
+    def _folded(self, rows, fold):
+        """(rows', constant) with the corrections folded into the mask rows, cached"""
+        if not fold:
+            return (rows, None)
+        key = (rows.data_ptr(), rows.shape[0], id(self._corr))
+        hit = self._fold_cache.get(key)
+        if hit is None:
+            r64, const = self._corr.fold_masks(rows.detach().cpu().numpy())
+            hit = (torch.from_numpy(r64.astype(np.float32)).to(rows.device),
+                   torch.from_numpy(const.astype(np.float32)).to(rows.device), rows)
+            self._fold_cache[key] = hit
+        return (hit[0], hit[1])
+
+    def _corr_for_slice(self, sig_slice):
+        """CorrectionSet restricted to a sub-frame tile: repair environments are clipped to the
+        tile, as the reference does per tile (corrset.py:171-180)"""
+        from .corrections import CorrectionSet
+        key = sig_slice
+        hit = self._slice_corr.get(key)
+        if hit is None:
+            sl = sig_slice.get()
+            c = self._corr
+            hit = CorrectionSet(
+                dark=None if c.get_dark_frame() is None else c.get_dark_frame()[sl],
+                gain=None if c.get_gain_map() is None else c.get_gain_map()[sl],
+                excluded_pixels=None if c.get_excluded_pixels() is None
+                else c.get_excluded_pixels()[sl], allow_empty=True)
+            self._slice_corr[key] = hit
+        return hit
+
     def _slab_target(self, grp, t0_rows):
         """(rows, columns) window of the slab that a fused group writes, when every member's
         buffer is a slab member and their columns are consecutive in group order"""
         if self._slab is None or not grp:
             return None
         c_first = c_next = None
-        for pu, spec, rows in grp:
+        for pu, spec, rows, _const in grp:
             cols = getattr(pu, '_slab_cols', None)
             if cols is None or cols[1] != rows.shape[0]:
                 return None
@@ -260,22 +312,47 @@ class UDFRunner:
         sig_slice = tslice.discard_nav()
         fusable_dtype = flat.dtype in (torch.float32, torch.uint16, torch.uint8, torch.int16,
                                        torch.int8)
-        dense = []       # (pu, spec, rows tensor)
+        dense = []       # (pu, spec, rows tensor[, constant per column])
         sig_sum_view = None
+        corr = self._corr
+        fold = corr is not None and self._corr_fold and full_frame
+        corrected_tile = None
+
+        def explicit_tile():
+            # reference behaviour: the UDF sees a corrected float tile (corrset.py:141-169)
+            nonlocal corrected_tile
+            if corr is None:
+                return tile
+            if corrected_tile is None:
+                cs = corr if full_frame else self._corr_for_slice(sig_slice)
+                corrected_tile = cs.apply(tile)
+            return corrected_tile
+
         for pu, spec in zip(part_udfs, specs):
             if spec is None or not fusable_dtype:
-                self._run_unfused(pu, tile)
+                self._run_unfused(pu, explicit_tile())
                 continue
             kind = spec['kind']
+            if corr is not None and not fold:
+                self._run_unfused(pu, explicit_tile())
+                continue
+            if corr is not None and kind not in ('dense', 'ones', 'sig_sum', 'csc'):
+                self._run_unfused(pu, explicit_tile())
+                continue
             if kind == 'dense':
-                dense.append((pu, spec, spec['engine'].dense_rows(sig_slice)))
+                dense.append((pu, spec) + self._folded(spec['engine'].dense_rows(sig_slice),
+                                                      fold))
             elif kind == 'ones':
-                dense.append((pu, spec, ones_row(flat.shape[1], device)))
+                dense.append((pu, spec) + self._folded(ones_row(flat.shape[1], device), fold))
             elif kind == 'sig_sum':
                 if full_frame and sig_sum_view is None:
                     sig_sum_view = getattr(pu.results, spec['buffer']).reshape(-1)
+                    if fold:
+                        key = (self._udfs[part_udfs.index(pu)], spec['buffer'])
+                        if key not in self._sig_sum_folded:
+                            self._sig_sum_folded.append(key)
                 else:
-                    self._run_unfused(pu, tile)
+                    self._run_unfused(pu, explicit_tile())
             elif kind == 'own_pass':
                 # group-sparse complex masks (K4): a pass of their own through the engine
                 if flat.dtype == torch.float32:
@@ -294,13 +371,15 @@ class UDFRunner:
                 if tma_able and len(eng.masks) <= MAX_FUSED_COLUMNS:
                     # the frames are streamed once anyway: a few sparse masks ride along as
                     # dense rows of the fused pass (exact same sums; zeros contribute nothing)
-                    dense.append((pu, spec, eng.dense_rows(sig_slice)))
+                    dense.append((pu, spec) + self._folded(eng.dense_rows(sig_slice), fold))
+                elif corr is not None:
+                    self._run_unfused(pu, explicit_tile())
                 else:
                     view = getattr(pu.results, spec['buffer'])
                     eng.process_flat(flat, out=view, accumulate=True, sig_slice=sig_slice)
                     self.stats['fused_launch_groups'] += 1
             else:
-                self._run_unfused(pu, tile)
+                self._run_unfused(pu, explicit_tile())
         if not dense and sig_sum_view is None:
             return
         # one pass over the tile per group of <= 24 columns
@@ -319,23 +398,32 @@ class UDFRunner:
         for gi, grp in enumerate(groups):
             ss = sig_sum_view if gi == 0 else None
             direct = self._slab_target(grp, t0_rows)
+            consts = [g[3] for g in grp]
             if direct is not None:
                 rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
                 engine.masks_dense(flat, rows, out=direct, accumulate=True, sig_sum=ss)
+                if any(c is not None for c in consts):
+                    direct += torch.cat([c if c is not None else
+                                         torch.zeros(g[2].shape[0], device=device)
+                                         for c, g in zip(consts, grp)])
             elif len(grp) == 1 and ss is None:
-                pu, spec, rows = grp[0]
+                pu, spec, rows, const = grp[0]
                 view = getattr(pu.results, spec['buffer'])
                 out = self._real_view(view, rows.shape[0])
                 engine.masks_dense(flat, rows, out=out, accumulate=True)
+                if const is not None:
+                    out += const
             else:
                 rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
                 res = engine.masks_dense(flat, rows, sig_sum=ss)
                 c0 = 0
-                for pu, spec, r in grp:
+                for pu, spec, r, const in grp:
                     c = r.shape[0]
                     view = getattr(pu.results, spec['buffer'])
                     out = self._real_view(view, c)
                     out += res[:, c0:c0 + c]
+                    if const is not None:
+                        out += const
                     c0 += c
             self.stats['fused_launch_groups'] += 1
 
@@ -467,10 +555,11 @@ class UDFRunner:
         return out
 
 
-def run_udf(dataset, udf, roi=None, device=None, fuse=True):
+def run_udf(dataset, udf, roi=None, device=None, fuse=True, corrections=None):
     """``Context.run_udf`` for this runtime (reference api.py:914-1051): one UDF -> dict of
     result buffers, a list of UDFs -> list of dicts."""
     many = isinstance(udf, (list, tuple))
     udfs = list(udf) if many else [udf]
-    res = UDFRunner(udfs, fuse=fuse).run_for_dataset(dataset, roi=roi, device=device)
+    res = UDFRunner(udfs, fuse=fuse).run_for_dataset(dataset, roi=roi, device=device,
+                                                     corrections=corrections)
     return res.buffers if many else res.buffers[0]

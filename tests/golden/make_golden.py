@@ -306,6 +306,45 @@ def g_rmatmul():
          csr=rmatmul(left, csr), csc=rmatmul(left, csc))
 
 
+
+
+def g_corrections():
+    # detector corrections (io/corrections/corrset.py): dark, gain, excluded pixels
+    from libertem.io.corrections import CorrectionSet
+    shape = (4, 5, 16, 12)
+    stack = mixed_masks(16, 12, 3, seed=215)
+    dark = synth.uniform_f32(0, 16 * 12, 415).reshape(16, 12) * 0.3
+    gain = 0.5 + synth.uniform_f32(0, 16 * 12, 515).reshape(16, 12)
+    excl = np.zeros((16, 12), dtype=bool)
+    for (y, x) in [(0, 0), (3, 4), (3, 5), (15, 11), (8, 0), (9, 7)]:
+        excl[y, x] = True
+    out = {}
+    for dt, seed in ((np.float32, 115), (np.uint16, 116)):
+        data = synth.dataset(shape, dt, seed=seed)
+        for name, corr in (
+            ('dg', CorrectionSet(dark=dark, gain=gain)),
+            ('dge', CorrectionSet(dark=dark, gain=gain, excluded_pixels=excl)),
+            ('e', CorrectionSet(excluded_pixels=excl)),
+        ):
+            ex = InlineJobExecutor()
+            # NOTE a fresh copy per run: for C-contiguous float32 input the reference corrects
+            # the MemoryDataSet's array IN PLACE (io/dataset/memory.py:99-106 hands the view to
+            # preprocess), so re-using `data` would stack corrections across runs
+            ds = MemoryDataSet(data=data.copy(), num_partitions=2, sig_dims=2)
+            ds.initialize(ex)
+            res = UDFRunner([ApplyMasksUDF(mask_factories=lambda: stack), CoMUDF(), SumUDF(),
+                             SumSigUDF()]).run_for_dataset(ds, ex, corrections=corr)
+            b = res.buffers
+            key = f'{np.dtype(dt).name}_{name}_'
+            out[key + 'intensity'] = b[0]['intensity'].raw_data
+            out[key + 'raw_com'] = b[1]['raw_com'].raw_data
+            out[key + 'sum'] = b[2]['intensity'].raw_data
+            out[key + 'sumsig'] = b[3]['intensity'].raw_data
+    save('corrections', dict(shape=shape, mask_seed=215, dark_seed=415, gain_seed=515,
+                             seeds=dict(float32=115, uint16=116),
+                             excluded=[(0, 0), (3, 4), (3, 5), (15, 11), (8, 0), (9, 7)]), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or None
     for name, fn in list(globals().items()):

@@ -207,3 +207,40 @@ def test_rmatmul():
     np.testing.assert_allclose(O.rmatmul(left, sp.csc_matrix(dense)), g['csc'], rtol=RTOL)
     with pytest.raises(ValueError):
         O.rmatmul(left[:, :10], sp.csr_matrix(dense))
+
+
+@pytest.mark.parametrize('dt', ['float32', 'uint16'])
+def test_corrections(dt):
+    """oracle restatement of the detector corrections AND the product's mask folding
+    (libertem_b200/corrections.py, pure host math) against the reference's outputs"""
+    from oracle import corrections as OC
+    from libertem_b200.corrections import CorrectionSet
+    meta, g = load_golden('corrections')
+    shape = meta['shape']
+    stack = mixed_masks(16, 12, 3, meta['mask_seed'])
+    dark = synth.uniform_f32(0, 192, meta['dark_seed']).reshape(16, 12) * 0.3
+    gain = 0.5 + synth.uniform_f32(0, 192, meta['gain_seed']).reshape(16, 12)
+    excl = np.zeros((16, 12), dtype=bool)
+    for y, x in meta['excluded']:
+        excl[y, x] = True
+    data = synth.dataset(shape, np.dtype(dt), meta['seeds'][dt])
+    for name, kw in (('dg', dict(dark=dark, gain=gain)),
+                     ('dge', dict(dark=dark, gain=gain, excluded_mask=excl)),
+                     ('e', dict(excluded_mask=excl))):
+        key = f'{dt}_{name}_'
+        c = OC.correct(data, **kw)
+        np.testing.assert_allclose(O.apply_masks(c, stack, num_partitions=2),
+                                   g[key + 'intensity'], rtol=RTOL, atol=1e-4)
+        np.testing.assert_allclose(O.sum_udf(c, num_partitions=2), g[key + 'sum'], rtol=1e-5)
+        np.testing.assert_allclose(O.sumsig_udf(c, num_partitions=2), g[key + 'sumsig'],
+                                   rtol=1e-5)
+        np.testing.assert_allclose(O.com_udf(c, num_partitions=2)['raw_com'],
+                                   g[key + 'raw_com'], rtol=1e-5)
+        cs = CorrectionSet(dark=kw.get('dark'), gain=kw.get('gain'),
+                           excluded_pixels=kw.get('excluded_mask'))
+        rows, const = cs.fold_masks(stack.reshape(3, -1))
+        folded = data.reshape(20, -1).astype(np.float64) @ rows.T + const
+        scale = np.abs(g[key + 'intensity']).max(axis=0)
+        assert (np.abs(folded - g[key + 'intensity']) / scale).max() <= 1e-6
+        fs = cs.correct_frame_sum(data.reshape(20, -1).astype(np.float64).sum(0), 20)
+        np.testing.assert_allclose(fs.reshape(16, 12), g[key + 'sum'], rtol=1e-5, atol=1e-4)

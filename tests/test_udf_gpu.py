@@ -330,3 +330,55 @@ def test_synthetic_dataset_matches_oracle(lt):
     close_cols(res[0]['intensity'].raw_data, O.apply_masks(data, mask[None], num_partitions=4))
     ref = O.com_udf(data, num_partitions=4)
     np.testing.assert_allclose(res[1]['raw_com'].raw_data, ref['raw_com'], rtol=RTOL)
+
+
+def _corr_inputs(meta):
+    dark = synth.uniform_f32(0, 192, meta['dark_seed']).reshape(16, 12) * 0.3
+    gain = 0.5 + synth.uniform_f32(0, 192, meta['gain_seed']).reshape(16, 12)
+    excl = np.zeros((16, 12), dtype=bool)
+    for y, x in meta['excluded']:
+        excl[y, x] = True
+    return dark, gain, excl
+
+
+@pytest.mark.parametrize('dt', ['float32', 'uint16'])
+@pytest.mark.parametrize('name', ['dg', 'dge', 'e'])
+def test_corrections_folded_into_masks(lt, dt, name):
+    """dark / gain / dead-pixel corrections (io/corrections/corrset.py) folded into the masks:
+    same results as the reference's per-tile correction, frames still read once"""
+    from libertem_b200.corrections import CorrectionSet
+    meta, g = load_golden('corrections')
+    dark, gain, excl = _corr_inputs(meta)
+    kw = {'dg': dict(dark=dark, gain=gain), 'dge': dict(dark=dark, gain=gain, excluded_pixels=excl),
+          'e': dict(excluded_pixels=excl)}[name]
+    data = synth.dataset(meta['shape'], np.dtype(dt), meta['seeds'][dt])
+    stack = mixed_masks(16, 12, 3, meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=data.copy(), num_partitions=2, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.ApplyMasksUDF(mask_factories=lambda: stack), lt.udf.CoMUDF(),
+                           lt.udf.SumUDF(), lt.udf.SumSigUDF()])
+    res = runner.run_for_dataset(ds, corrections=CorrectionSet(**kw)).buffers
+    assert runner.stats['unfused_calls'] == 0          # fused: no corrected copy of the tile
+    key = f'{dt}_{name}_'
+    close_cols(res[0]['intensity'].raw_data, g[key + 'intensity'])
+    np.testing.assert_allclose(res[1]['raw_com'].raw_data, g[key + 'raw_com'], rtol=RTOL)
+    np.testing.assert_allclose(res[2]['intensity'].data, g[key + 'sum'], rtol=RTOL, atol=1e-4)
+    np.testing.assert_allclose(res[3]['intensity'].raw_data, g[key + 'sumsig'], rtol=RTOL)
+    assert np.array_equal(ds.data, data)               # the input is never modified
+
+
+def test_corrections_explicit_path_subframe_tiles(lt):
+    from libertem_b200.corrections import CorrectionSet, RepairValueError
+    from oracle import corrections as OC
+    meta, g = load_golden('corrections')
+    dark, gain, excl = _corr_inputs(meta)
+    data = synth.dataset(meta['shape'], np.float32, meta['seeds']['float32'])
+    stack = mixed_masks(16, 12, 3, meta['mask_seed'])
+    ds = lt.MemoryDataSet(data=data, num_partitions=2, sig_dims=2, tileshape=(4, 8, 12))
+    res = lt.run_udf(ds, [lt.udf.ApplyMasksUDF(mask_factories=lambda: stack), lt.udf.SumUDF()],
+                     corrections=CorrectionSet(dark=dark, gain=gain))
+    c = OC.correct(data, dark=dark, gain=gain)
+    close_cols(res[0]['intensity'].raw_data, O.apply_masks(c, stack))
+    np.testing.assert_allclose(res[1]['intensity'].data, c.reshape(20, 16, 12).sum(0), rtol=RTOL)
+    bad = np.ones((16, 12), dtype=bool)
+    with pytest.raises(RepairValueError):
+        CorrectionSet(excluded_pixels=bad)
