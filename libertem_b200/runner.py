@@ -447,8 +447,15 @@ class UDFRunner:
 
     def _run_unfused(self, pu, tile):
         self.stats['unfused_calls'] += 1
-        if getattr(pu, 'get_method', lambda: 'tile')() == 'frame':
-            shifts = pu.params.shifts
+        method = pu.get_method()
+        if method == 'partition':
+            part = pu.meta.partition_slice
+            if tile.shape[0] != part.shape[0] and pu.meta.roi is None:
+                raise UDFException('process_partition needs the whole partition in one tile '
+                                   '(device-resident data or tile_depth >= partition size)')
+            pu.process_partition(tile)
+        elif method == 'frame':
+            shifts = pu.params.get('shifts')
             tslice = pu.meta.slice
             views = dict(pu.results._views)
             for i in range(tile.shape[0]):
@@ -459,7 +466,7 @@ class UDFRunner:
                 if hasattr(shifts, 'for_frames'):
                     arr = shifts.for_frames(pu.meta.dataset_shape, pu.meta.roi)
                     pu._current_shift = arr[tslice.origin[0] + i].astype(int)
-                else:
+                elif shifts is not None:
                     pu._current_shift = np.asarray(shifts).astype(int)
                 pu.process_frame(tile[i])
             for name, v in views.items():

@@ -191,6 +191,15 @@ class UDF:
     def get_tiling_preferences(self):
         return {'depth': self.TILE_DEPTH_DEFAULT, 'total_size': self.TILE_SIZE_MAX}
 
+    def get_method(self):
+        """'tile' | 'frame' | 'partition': which process_* method this UDF implements
+        (base.py:1148-1176)"""
+        cls = type(self)
+        for name in ('tile', 'frame', 'partition'):
+            if getattr(cls, 'process_' + name, None) is not None:
+                return name
+        raise UDFException('UDF should implement one of the process_* methods')
+
     def preprocess(self):
         pass
 

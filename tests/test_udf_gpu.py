@@ -382,3 +382,43 @@ def test_corrections_explicit_path_subframe_tiles(lt):
     bad = np.ones((16, 12), dtype=bool)
     with pytest.raises(RepairValueError):
         CorrectionSet(excluded_pixels=bad)
+
+
+def test_user_defined_udfs_through_the_plugin_api(lt):
+    """the UDF protocol is generic: user UDFs with process_tile / process_frame /
+    process_partition run next to the fused hot-path UDFs (tiles are CUDA tensors)"""
+    UDF = lt.udf.UDF
+
+    class MaxTileUDF(UDF):
+        def get_result_buffers(self):
+            return {'maxval': self.buffer(kind='nav', dtype=np.float32, where='device')}
+
+        def process_tile(self, tile):
+            self.results.maxval[:] = tile.reshape(tile.shape[0], -1).amax(dim=1)
+
+    class FrameStdUDF(UDF):
+        def get_result_buffers(self):
+            return {'std': self.buffer(kind='nav', dtype=np.float32, where='device')}
+
+        def process_frame(self, frame):
+            self.results.std[...] = frame.std(unbiased=False)
+
+    class PartSumUDF(UDF):
+        def get_result_buffers(self):
+            return {'total': self.buffer(kind='single', dtype=np.float64, where='device')}
+
+        def process_partition(self, partition):
+            self.results.total[:] += partition.double().sum()
+
+        def merge(self, dest, src):
+            dest.total[:] += src.total
+
+    data = synth.dataset((6, 5, 16, 16), np.float32, 71)
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=3, sig_dims=2)
+    res = lt.run_udf(ds, [MaxTileUDF(), FrameStdUDF(), PartSumUDF(), lt.udf.SumSigUDF()])
+    np.testing.assert_allclose(res[0]['maxval'].data, data.max(axis=(2, 3)))
+    np.testing.assert_allclose(res[1]['std'].data, data.std(axis=(2, 3)), rtol=1e-5)
+    np.testing.assert_allclose(res[2]['total'].data[0], data.astype(np.float64).sum(), rtol=1e-10)
+    np.testing.assert_allclose(res[3]['intensity'].data, data.sum(axis=(2, 3)), rtol=RTOL)
+    assert MaxTileUDF().get_method() == 'tile' and FrameStdUDF().get_method() == 'frame'
+    assert PartSumUDF().get_method() == 'partition'
