@@ -11,6 +11,7 @@
  *                              (udf/sumsigudf.py:28-38) is an all-ones mask row.
  *   ltb200_masks_dense_f64  <- the same seam when np.result_type(input, mask) is float64
  *                              (udf/masks.py:360-368 dtype rule).
+ *   ltb200_masks_shifted    <- ApplyMasksEngine.process_frame_shifted (udf/masks.py:85-124).
  *   ltb200_masks_csc        <- ApplyMasksEngine._process_flat_spsp -> rmatmul
  *                              (udf/masks.py:68-69, common/numba/__init__.py:90-184).
  *                              (`sig_sum` of ltb200_masks_dense fuses SumUDF, udf/sum.py:44-49,
@@ -119,6 +120,16 @@ LTB_API int ltb200_masks_csc(const void* tile, int tile_dtype, int64_t n_frames,
                      int64_t ld_tile, const int32_t* indptr, const int32_t* indices,
                      const float* values, int n_masks, float* out, int64_t ld_out,
                      int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Shifted masks (K5): per frame f the masks are displaced by (dy, dx) = shifts[f] (or shifts[0]
+ * when per_frame == 0): out[f, m] (+)= sum over the overlap of tile[f, y, x] * masks[m, y-dy, x-dx]
+ * (ApplyMasksEngine.process_frame_shifted, udf/masks.py:85-124).  2D signals, float32 masks.
+ * ------------------------------------------------------------------------------------- */
+LTB_API int ltb200_masks_shifted(const void* tile, int tile_dtype, int64_t n_frames, int sig_y,
+                                 int sig_x, int64_t ld_tile, const float* masks, int n_masks,
+                                 int64_t ld_masks, const int32_t* shifts, int per_frame,
+                                 float* out, int64_t ld_out, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Group-sparse masked reduction (K4) -- RadialFourierAnalysis: masks come in groups (rings)

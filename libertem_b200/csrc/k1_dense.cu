@@ -411,6 +411,10 @@ static int launch_k1_pair(const CUtensorMap& tmd, const CUtensorMap& tmm, const 
     const size_t fixed = C::FIXED_BYTES + sig_bytes + 128;
     int stages = (int)(((size_t)smem_max - fixed) / C::STAGE_BYTES);
     if (stages > 6) stages = 6;
+    if (const char* e = getenv("LTB200_MAX_STAGES")) {      // tuning knob
+        const int cap = atoi(e);
+        if (cap >= 2 && cap < stages) stages = cap;
+    }
     if (stages < 2) {
         set_error("k1 pair: not enough shared memory for 2 stages");
         return LTB_ERR_UNSUPPORTED;

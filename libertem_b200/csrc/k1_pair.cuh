@@ -24,6 +24,7 @@ struct K1In;
 template <>
 struct K1In<float> {
     static constexpr CUtensorMapDataType TMAP = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    static constexpr bool INTEGER = false;
     __device__ static __forceinline__ float4 load4(const uint8_t* base, int row, int kk,
                                                     int kt) {
         return *reinterpret_cast<const float4*>(base + ((size_t)row * kt + kk) * 4);
@@ -33,16 +34,31 @@ struct K1In<float> {
 template <>
 struct K1In<uint16_t> {
     static constexpr CUtensorMapDataType TMAP = CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    static constexpr bool INTEGER = true;
+    static constexpr uint32_t MAGIC = 0x4B000000u;     // float bits of 2^23
+    // 4 pixels as "magic words" 0x4B00vvvv: as floats they are 2^23 + v exactly, as integers
+    // their payloads add without carries for up to 128 terms
+    __device__ static __forceinline__ uint4 load_magic(const uint8_t* base, int row, int kk,
+                                                       int kt) {
+        const uint2 w = *reinterpret_cast<const uint2*>(base + ((size_t)row * kt + kk) * 2);
+        uint4 m;
+        m.x = __byte_perm(w.x, MAGIC, 0x7610);
+        m.y = __byte_perm(w.x, MAGIC, 0x7632);
+        m.z = __byte_perm(w.y, MAGIC, 0x7610);
+        m.w = __byte_perm(w.y, MAGIC, 0x7632);
+        return m;
+    }
+    __device__ static __forceinline__ float4 magic_to_float(const uint4 m) {
+        float4 r;
+        r.x = __uint_as_float(m.x) - 8388608.f;
+        r.y = __uint_as_float(m.y) - 8388608.f;
+        r.z = __uint_as_float(m.z) - 8388608.f;
+        r.w = __uint_as_float(m.w) - 8388608.f;
+        return r;
+    }
     __device__ static __forceinline__ float4 load4(const uint8_t* base, int row, int kk,
                                                     int kt) {
-        const uint2 w = *reinterpret_cast<const uint2*>(base + ((size_t)row * kt + kk) * 2);
-        // float bits 0x4B000000 | v == 2^23 + v exactly; subtract 2^23
-        float4 r;
-        r.x = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7610)) - 8388608.f;
-        r.y = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7632)) - 8388608.f;
-        r.z = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7610)) - 8388608.f;
-        r.w = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7632)) - 8388608.f;
-        return r;
+        return magic_to_float(load_magic(base, row, kk, kt));
     }
 };
 
@@ -215,25 +231,54 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
                 for (int s = 0; s < SPC; s++) {
                     const int kk = kk_base + s * 32;
                     float4 dv[FR];
+                    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (K1In<TIN>::INTEGER) {
+                        // u16: the frame sum is taken on the integer pipe (exact, and it keeps
+                        // ~60 FADDs per step off the FP32 pipe that feeds the FFMA2s)
+                        uint4 isum = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int j = 0; j < FR; j++)
-                        dv[j] = K1In<TIN>::load4(d, row_base + j * 4, kk, KT);
+                        for (int j = 0; j < FR; j++) {
+                            const uint4 mw = K1In<TIN>::load_magic(d, row_base + j * 4, kk, KT);
+                            dv[j] = K1In<TIN>::magic_to_float(mw);
+                            if (FG == 1 && do_sig) {
+                                isum.x += mw.x; isum.y += mw.y; isum.z += mw.z; isum.w += mw.w;
+                            }
+                        }
+                        if (FG == 1 && do_sig) {
+                            const uint32_t off = (uint32_t)FR * K1In<TIN>::MAGIC;   // mod 2^32
+                            isum.x -= off; isum.y -= off; isum.z -= off; isum.w -= off;
+#pragma unroll
+                            for (int o = 8; o <= 16; o <<= 1) {
+                                isum.x += __shfl_xor_sync(0xffffffffu, isum.x, o);
+                                isum.y += __shfl_xor_sync(0xffffffffu, isum.y, o);
+                                isum.z += __shfl_xor_sync(0xffffffffu, isum.z, o);
+                                isum.w += __shfl_xor_sync(0xffffffffu, isum.w, o);
+                            }
+                            sg = make_float4(__uint2float_rn(isum.x), __uint2float_rn(isum.y),
+                                             __uint2float_rn(isum.z), __uint2float_rn(isum.w));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < FR; j++)
+                            dv[j] = K1In<TIN>::load4(d, row_base + j * 4, kk, KT);
+                        if (FG == 1 && do_sig) {
+                            sg = dv[0];
+#pragma unroll
+                            for (int j = 1; j < FR; j++) {
+                                sg.x += dv[j].x; sg.y += dv[j].y; sg.z += dv[j].z; sg.w += dv[j].w;
+                            }
+#pragma unroll
+                            for (int o = 8; o <= 16; o <<= 1) {
+                                sg.x += __shfl_xor_sync(0xffffffffu, sg.x, o);
+                                sg.y += __shfl_xor_sync(0xffffffffu, sg.y, o);
+                                sg.z += __shfl_xor_sync(0xffffffffu, sg.z, o);
+                                sg.w += __shfl_xor_sync(0xffffffffu, sg.w, o);
+                            }
+                        }
+                    }
                     if (FG == 1 && do_sig) {
-                        // SumUDF: per-pixel sum over this warp's 64 frames (FR lane frames, then
-                        // the 4 frame lanes), accumulated in shared memory by the fl == 0 lanes;
-                        // this warp is the only writer of its pixel range
-                        float4 sg = dv[0];
-#pragma unroll
-                        for (int j = 1; j < FR; j++) {
-                            sg.x += dv[j].x; sg.y += dv[j].y; sg.z += dv[j].z; sg.w += dv[j].w;
-                        }
-#pragma unroll
-                        for (int o = 8; o <= 16; o <<= 1) {
-                            sg.x += __shfl_xor_sync(0xffffffffu, sg.x, o);
-                            sg.y += __shfl_xor_sync(0xffffffffu, sg.y, o);
-                            sg.z += __shfl_xor_sync(0xffffffffu, sg.z, o);
-                            sg.w += __shfl_xor_sync(0xffffffffu, sg.w, o);
-                        }
+                        // SumUDF: this warp is the only writer of its pixel range; the fl == 0
+                        // lanes accumulate the 64-frame sums in shared memory
                         if (fl == 0) {
                             const int64_t kg = k0 + (int64_t)c * KT + kk;
                             if (kg < p.sig_size) {   // sig_size % 4 == 0 on this path

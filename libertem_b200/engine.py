@@ -148,3 +148,29 @@ def masks_csc(tile, indptr, indices, values, n_masks, out=None, accumulate=False
 def set_k1_variant(variant):
     """0 auto, 1 even/odd-pixel tile, 2 mask-pair tile (tuning / tests)"""
     check(get_lib().ltb200_set_k1_variant(int(variant)))
+
+
+def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
+    """per-frame shifted masks: tile (F, sy, sx), masks (M, sy*sx) float32, shifts int32
+    (F, 2) or (1, 2) (dy, dx) -> out (F, M)"""
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    _require_cuda(masks, 'masks')
+    F, sy, sx = tile.shape
+    tile = tile.contiguous()
+    masks = masks.contiguous()
+    M = masks.shape[0]
+    shifts = shifts.to(device=tile.device, dtype=torch.int32).contiguous()
+    per_frame = int(shifts.shape[0] != 1)
+    if per_frame and shifts.shape[0] != F:
+        raise ValueError('need one (dy, dx) per frame or a single pair')
+    if out is None:
+        out = torch.zeros((F, M), dtype=torch.float32, device=tile.device)
+        accumulate = False
+    ld_out = out.stride(0) if F > 1 else max(M, 1)
+    with torch.cuda.device(tile.device):
+        check(lib.ltb200_masks_shifted(
+            tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, sy, sx, sy * sx, masks.data_ptr(), M,
+            masks.shape[1], shifts.data_ptr(), per_frame, out.data_ptr(), ld_out,
+            int(bool(accumulate)), _stream_ptr(tile.device)))
+    return out

@@ -457,6 +457,14 @@ class UDFRunner:
         elif method == 'frame':
             shifts = pu.params.get('shifts')
             tslice = pu.meta.slice
+            if shifts is not None and hasattr(pu, 'process_tile_shifted'):
+                if hasattr(shifts, 'for_frames'):
+                    arr = shifts.for_frames(pu.meta.dataset_shape, pu.meta.roi)
+                    arr = arr[tslice.origin[0]:tslice.origin[0] + tile.shape[0]]
+                else:
+                    arr = np.asarray(shifts).reshape(1, 2)
+                if pu.process_tile_shifted(tile, arr.astype(np.int64)):
+                    return
             views = dict(pu.results._views)
             for i in range(tile.shape[0]):
                 pu.results.clear_views()

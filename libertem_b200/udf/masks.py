@@ -216,6 +216,21 @@ class ApplyMasksUDF(UDF):
         else:
             view[:] += self.forbuf(eng.process_tile(tile), view)
 
+    def process_tile_shifted(self, tile, shifts):
+        """all frames of a full-frame tile with their own (dy, dx) in ONE launch (K5) instead
+        of the reference's frame-by-frame loop; returns False if this case needs the loop"""
+        eng = self.task_data['engine']
+        view = self.results.intensity
+        sig = tuple(self.meta.dataset_shape.sig)
+        if (eng.compute != np.float32 or eng.result_dtype != np.float32 or len(sig) != 2
+                or tuple(tile.shape[1:]) != sig or not view.is_cuda
+                or tile.dtype not in (torch.float32, torch.uint16, torch.uint8, torch.int16)):
+            return False
+        rows = eng.dense_rows()
+        sh = torch.from_numpy(np.ascontiguousarray(shifts, dtype=np.int32).reshape(-1, 2))
+        engine.masks_shifted(tile, rows, sh, out=view, accumulate=True)
+        return True
+
     def process_frame(self, frame):
         shifts = self._current_shift
         view = self.results.intensity

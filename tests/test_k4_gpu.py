@@ -56,3 +56,44 @@ def test_find_groups():
     # entry 4q+c of block 0, component w -> (c//2)*32 + q*4 + (c%2)*2 + w
     for (q, c, w) in [(0, 0, 0), (3, 1, 1), (7, 2, 0), (5, 3, 1)]:
         assert packed[0, (c // 2) * 32 + q * 4 + (c % 2) * 2 + w] == (4 * q + c) * 2 + w
+
+
+def _shifted_ref(data, masks, shifts):
+    F, sy, sx = data.shape
+    out = np.zeros((F, masks.shape[0]))
+    for f in range(F):
+        dy, dx = shifts[f if len(shifts) > 1 else 0]
+        y0, y1 = max(0, dy), min(sy, sy + dy)
+        x0, x1 = max(0, dx), min(sx, sx + dx)
+        if y1 <= y0 or x1 <= x0:
+            continue
+        d = data[f, y0:y1, x0:x1].astype(np.float64)
+        m = masks[:, y0 - dy:y1 - dy, x0 - dx:x1 - dx].astype(np.float64)
+        out[f] = (m * d).sum(axis=(1, 2))
+    return out
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.uint16])
+def test_masks_shifted_kernel(dt):
+    from libertem_b200 import engine
+    F, sy, sx, M = 50, 24, 40, 6
+    if dt == np.float32:
+        data = synth.uniform_f32(0, F * sy * sx, 5).reshape(F, sy, sx)
+        t = torch.from_numpy(data).cuda()
+    else:
+        data = synth.poisson3_u16(0, F * sy * sx, 5).reshape(F, sy, sx)
+        t = torch.from_numpy(data.view(np.int16)).cuda().view(torch.uint16)
+    masks = synth.uniform_f32(0, M * sy * sx, 6).reshape(M, sy, sx) - 0.3
+    sh = (synth.hash_u32(0, 2 * F, 7) % 31).astype(np.int64).reshape(F, 2) - 15
+    sh[0] = (0, 0)
+    sh[1] = (100, 0)        # no overlap
+    sh[2] = (-23, 39)       # single pixel
+    out = engine.masks_shifted(t, torch.from_numpy(masks.reshape(M, -1)).cuda(),
+                               torch.from_numpy(sh)).cpu().numpy()
+    ref = _shifted_ref(data, masks, sh)
+    scale = np.abs(ref).max() + 1e-30
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    assert np.all(out[1] == 0)
+    const = engine.masks_shifted(t, torch.from_numpy(masks.reshape(M, -1)).cuda(),
+                                 torch.tensor([[3, -7]])).cpu().numpy()
+    assert np.abs(const - _shifted_ref(data, masks, [(3, -7)])).max() / scale <= 2e-6

@@ -296,6 +296,17 @@ def test_shifts(lt):
     with pytest.raises(ValueError):
         lt.udf.ApplyMasksUDF(mask_factories=lambda: stack, shifts=(1, 1),
                              use_sparse='scipy.sparse')
+    # the whole tile goes through ONE launch of the shifted-mask kernel, not a frame loop
+    from libertem_b200 import engine
+    engine.launch_count(reset=True)
+    lt.run_udf(ds, udf)
+    assert engine.launch_count() == 2          # one per partition
+    # float64 masks: falls back to the reference-style frame loop, same numbers
+    stack64 = stack.astype(np.float64)
+    r64 = lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=lambda: stack64,
+                                              shifts=tuple(meta['const'])))
+    assert r64['intensity'].raw_data.dtype == np.float64
+    close_cols(r64['intensity'].raw_data, g['const'])
 
 
 def test_process_tile_seam_with_numpy_tile(lt):
