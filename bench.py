@@ -334,7 +334,8 @@ def gpu_arm(args):
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                 'kernel': {1: 'k1_dense_tma_kernel (even/odd tile)', 3: 'k1_pair_kernel<float> '
-                           '(mask-pair tile)'}.get(engine.last_kernel(), 'generic'),
+                           '(mask-pair tile)', 6: 'k6_tensor_kernel (tcgen05 kind::tf32, '
+                           'split-TF32, TMEM accumulators)'}.get(engine.last_kernel(), 'generic'),
                 'kernel_ms': kern_ms,
                 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'kernel_share_of_step': kern_ms * len(ev_log) / args.steps / ms_per_step}

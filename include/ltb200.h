@@ -100,13 +100,30 @@ LTB_API int ltb200_masks_dense_f64(const void* tile, int tile_dtype, int64_t n_f
                            int64_t ld_masks, double* out, int64_t ld_out, int accumulate,
                            void* stream);
 
-/* tuning / test knob: register tile of the TMA-staged dense kernel.
- * 0 = auto (default), 1 = even/odd-pixel accumulator pairs, 2 = mask-pair accumulators */
+/* ---------------------------------------------------------------------------------------
+ * The same dense contraction on the tensor cores (K6): tcgen05.mma kind::tf32 with the
+ * split-TF32 scheme (hi/lo parts of tile and masks, float32 accumulation in TMEM cut into
+ * chains of `chain` x 32 pixels that are summed in float32 registers; chain <= 0 -> default).
+ * float32 tiles, sig_size % 4 == 0, 16-byte aligned rows.  ltb200_masks_dense routes wide
+ * float32 stacks here by itself (see ltb200_set_k1_variant); this entry point is the
+ * explicit form used by the parity tests.  Returns LTB_ERR_UNSUPPORTED for shapes the TMA /
+ * UMMA layouts cannot take.
+ * ------------------------------------------------------------------------------------- */
+LTB_API size_t ltb200_masks_dense_tc_workspace(int64_t n_frames, int64_t sig_size, int n_masks);
+LTB_API int ltb200_masks_dense_tc(const float* tile, int64_t n_frames, int64_t sig_size,
+                                  int64_t ld_tile, const float* masks, int n_masks,
+                                  int64_t ld_masks, float* out, int64_t ld_out, int accumulate,
+                                  int chain, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* tuning / test knob: which dense kernel ltb200_masks_dense uses for float32 tiles.
+ * 0 = auto (default), 1 = FFMA2 even/odd-pixel accumulator pairs, 2 = FFMA2 mask-pair
+ * accumulators, 3 = tcgen05 tensor-core kernel (K6) whenever the shape allows */
 LTB_API int ltb200_set_k1_variant(int variant);
 
 /* which kernel the last ltb200_masks_dense call on this thread selected:
  * 1 = TMA-staged kernel (even/odd tile), 3 = TMA-staged kernel (mask-pair tile),
- * 2 = generic kernel (diagnostics / tests) */
+ * 2 = generic kernel, 6 = tcgen05 tensor-core kernel (diagnostics / tests) */
 LTB_API int ltb200_last_kernel(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 LTB_API int64_t ltb200_launch_count(int reset);

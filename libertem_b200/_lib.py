@@ -21,6 +21,9 @@ SIGNATURES = {
                                   _vp, _vp, _sz, _vp]),
     'ltb200_masks_dense_f64': (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64,
                                       _int, _vp]),
+    'ltb200_masks_dense_tc_workspace': (_sz, [_i64, _i64, _int]),
+    'ltb200_masks_dense_tc': (_int, [_vp, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _int,
+                                     _int, _vp, _sz, _vp]),
     'ltb200_set_k1_variant': (_int, [_int]),
     'ltb200_last_kernel': (_int, []),
     'ltb200_launch_count': (_i64, [_int]),

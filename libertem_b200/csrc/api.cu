@@ -51,6 +51,14 @@ static EncodeTiledFn get_encode_fn() {
 int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, size_t elem_bytes,
                    uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
                    uint32_t box1) {
+    (void)elem_bytes;
+    return encode_tmap_2d_sw(out, base, dt, dim0, dim1, stride1_bytes, box0, box1,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+int encode_tmap_2d_sw(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0,
+                      uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
+                      CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -60,9 +68,8 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, s
     cuuint64_t strides[1] = {stride1_bytes};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    (void)elem_bytes;
     CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, "

@@ -121,5 +121,16 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, size_t elem_bytes,
                    uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
                    uint32_t box1);
+// same with a shared-memory swizzle mode (box0 * element size must not exceed the swizzle span)
+int encode_tmap_2d_sw(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0,
+                      uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
+                      CUtensorMapSwizzle swizzle);
+
+// ---- K6 (tcgen05 dense masked reduction, k6_tensor.cu) used by the K1 dispatcher -----------
+bool k6_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile);
+size_t k6_workspace(int64_t n_frames, int64_t sig_size, int n_masks);
+int k6_run(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+           const float* masks, int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
+           int accumulate, int chain, void* workspace, cudaStream_t st);
 
 }  // namespace ltb

@@ -474,6 +474,16 @@ static PairChoice pair_choice(int n_masks, bool want_fr16) {
 
 static int g_k1_variant = -1;
 
+// smallest column count routed to the tensor-core kernel in auto mode (LTB200_K6_MIN to tune)
+static int k6_min_columns() {
+    static int v = -1;
+    if (v < 0) {
+        v = 1;
+        if (const char* e = getenv("LTB200_K6_MIN")) v = atoi(e) > 0 ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static int k1_variant() {
     // which FFMA2 register tile the dense path uses: 0 auto, 1 even/odd-pixel pairs ("eo"),
     // 2 mask pairs ("pair"); LTB200_K1=eo|pair|auto or ltb200_set_k1_variant()
@@ -482,6 +492,7 @@ static int k1_variant() {
         g_k1_variant = 0;
         if (e && !strcmp(e, "eo")) g_k1_variant = 1;
         if (e && !strcmp(e, "pair")) g_k1_variant = 2;
+        if (e && !strcmp(e, "tc")) g_k1_variant = 3;
     }
     return g_k1_variant;
 }
@@ -606,7 +617,7 @@ static size_t dtype_size(int dtype) {
 using namespace ltb;
 
 extern "C" int ltb200_set_k1_variant(int variant) {
-    LTB_REQUIRE(variant >= 0 && variant <= 2, "set_k1_variant: 0 auto, 1 eo, 2 pair");
+    LTB_REQUIRE(variant >= 0 && variant <= 3, "set_k1_variant: 0 auto, 1 eo, 2 pair, 3 tc");
     ltb::g_k1_variant = variant;
     return LTB_OK;
 }
@@ -614,7 +625,12 @@ extern "C" int ltb200_set_k1_variant(int variant) {
 extern "C" size_t ltb200_masks_dense_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
                                                int with_sig_sum) {
     if (n_frames <= 0 || sig_size <= 0 || n_masks < 0) return 0;
-    return ws_layout(n_frames, sig_size, n_masks, with_sig_sum).total;
+    size_t need = ws_layout(n_frames, sig_size, n_masks, with_sig_sum).total;
+    if (n_masks > 0) {
+        const size_t k6 = k6_workspace(n_frames, sig_size, n_masks);
+        if (k6 > need) need = k6;
+    }
+    return need;
 }
 
 namespace ltb {
@@ -758,6 +774,22 @@ extern "C" int ltb200_masks_dense(const void* tile, int tile_dtype, int64_t n_fr
     const bool tma_u16 = tile_dtype == LTB_U16 && tma_shape_ok;
 
     bool sig_done = sig_sum == nullptr;
+    // float32 tiles of >= 1024 frames go to the tensor cores (K6): HBM-bound up to 32 columns
+    // per pass, where the FFMA2 kernel is bound by the FP32 pipe from ~13 columns;
+    // LTB200_K6_MIN raises the column threshold, variant 3 forces K6 for every shape it takes
+    const bool k6_ok = tile_dtype == LTB_F32 && n_masks > 0 &&
+                       k6_shape_ok(tile, n_frames, sig_size, ld_tile);
+    const int variant_all = k1_variant();
+    // (a frame sum the FFMA2 kernel can fuse into its single pass stays there)
+    const bool k1_fuses_sig = sig_sum != nullptr && (size_t)sig_size * 4 <= K1_SIG_SMEM_MAX &&
+                              n_masks <= 6;
+    if (k6_ok && (variant_all == 3 || (variant_all == 0 && n_masks >= k6_min_columns() &&
+                                       n_frames >= 1024 && !k1_fuses_sig))) {
+        int rc = k6_run(tile, n_frames, sig_size, ld_tile, masks, n_masks, ld_masks, out, ld_out,
+                        accumulate, 0, workspace, st);
+        if (rc != LTB_OK) return rc;
+        n_masks = 0;   // columns done; a requested frame sum still runs below
+    }
     // mask columns are processed in groups of <= 24 (one pass over the frames per group)
     for (int m0 = 0; m0 < n_masks; m0 += 24) {
         const int nm = (n_masks - m0) > 24 ? 24 : (n_masks - m0);

@@ -104,6 +104,39 @@ def masks_dense(tile, masks, out=None, accumulate=False, sig_sum=None):
     return out
 
 
+def masks_dense_tc(tile, masks, out=None, accumulate=False, chain=0):
+    """The dense contraction on the tensor cores (K6, split-TF32 tcgen05): float32 tile (F, K)
+    and masks (M, K) -> out (F, M).  Explicit form of what ``masks_dense`` selects for wide
+    stacks; raises for shapes the kernel does not take."""
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    _require_cuda(masks, 'masks')
+    if tile.dtype != torch.float32 or masks.dtype != torch.float32:
+        raise TypeError('masks_dense_tc takes float32 tiles and masks')
+    if tile.dim() != 2 or masks.dim() != 2 or tile.shape[1] != masks.shape[1]:
+        raise ValueError(f'shape mismatch: tile {tuple(tile.shape)} masks {tuple(masks.shape)}')
+    if tile.stride(1) != 1:
+        tile = tile.contiguous()
+    if masks.stride(1) != 1:
+        masks = masks.contiguous()
+    F, K = tile.shape
+    M = masks.shape[0]
+    if out is None:
+        out = torch.zeros((F, M), dtype=torch.float32, device=tile.device)
+        accumulate = False
+    ld_tile = tile.stride(0) if F > 1 else max(K, 1)
+    ld_masks = masks.stride(0) if M > 1 else max(K, 1)
+    ld_out = out.stride(0) if F > 1 else max(M, 1)
+    with torch.cuda.device(tile.device):
+        need = lib.ltb200_masks_dense_tc_workspace(F, K, M)
+        ws = _workspace(tile.device, need)
+        check(lib.ltb200_masks_dense_tc(
+            tile.data_ptr(), F, K, ld_tile, masks.data_ptr(), M, ld_masks, out.data_ptr(),
+            ld_out, int(bool(accumulate)), int(chain), ws.data_ptr(), ws.numel(),
+            _stream_ptr(tile.device)))
+    return out
+
+
 def synth_fill(shape, dtype, seed, device, start=0):
     """Device twin of oracle.synth.dataset: counter-based synthetic data."""
     lib = get_lib()
@@ -146,7 +179,7 @@ def masks_csc(tile, indptr, indices, values, n_masks, out=None, accumulate=False
 
 
 def set_k1_variant(variant):
-    """0 auto, 1 even/odd-pixel tile, 2 mask-pair tile (tuning / tests)"""
+    """0 auto, 1 FFMA2 even/odd-pixel tile, 2 FFMA2 mask-pair tile, 3 tcgen05 kernel (K6)"""
     check(get_lib().ltb200_set_k1_variant(int(variant)))
 
 

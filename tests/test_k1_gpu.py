@@ -13,12 +13,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5   # north_star: <= 1e-5 rel for float32 mask/CoM results
 
 
-@pytest.fixture(scope='module', params=['auto', 'eo', 'pair'])
+@pytest.fixture(scope='module', params=['auto', 'eo', 'pair', 'tc'])
 def eng(request):
-    """every kernel-level test runs against both register tiles of the TMA kernel"""
+    """every kernel-level test runs against both FFMA2 register tiles of the TMA kernel and
+    against the tcgen05 tensor-core kernel (K6) forced on for every shape it takes"""
     from libertem_b200 import engine
     assert torch.cuda.is_available()
-    engine.set_k1_variant({'auto': 0, 'eo': 1, 'pair': 2}[request.param])
+    engine.set_k1_variant({'auto': 0, 'eo': 1, 'pair': 2, 'tc': 3}[request.param])
     yield engine
     engine.set_k1_variant(0)
 
@@ -60,7 +61,7 @@ def test_cfg1_golden(eng, nparts):
     data = synth.dataset(meta['shape'], np.float32, meta['data_seed']).reshape(1024, 4096)
     mask = synth.uniform_f32(0, 4096, meta['mask_seed']).reshape(1, 4096)
     out = eng.masks_dense(dev(data), dev(mask)).cpu().numpy()
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     np.testing.assert_allclose(out, g['intensity'], rtol=RTOL)
     assert_close_rel(out, f64_truth(data, mask), 2e-6)
 
@@ -74,7 +75,7 @@ def test_cfg2_small_golden(eng):
     allm = np.concatenate([stack, com, ones])          # 12 columns in ONE pass
     sig_sum = torch.zeros(65536, dtype=torch.float32, device='cuda')
     out = eng.masks_dense(dev(data), dev(allm), sig_sum=sig_sum).cpu().numpy()
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     truth = f64_truth(data, allm)
     assert_close_rel(out, truth, 2e-6, abs_scale(data, allm))
     assert_close_rel(out[:, :8], g['intensity'])
@@ -89,7 +90,7 @@ def test_dense_tma_mask_counts(eng, n_masks):
     data = synth.uniform_f32(0, F * K, 1).reshape(F, K)
     masks = synth.uniform_f32(0, n_masks * K, 2).reshape(n_masks, K) - 0.25
     out = eng.masks_dense(dev(data), dev(masks)).cpu().numpy()
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     assert_close_rel(out, f64_truth(data, masks), 2e-6, abs_scale(data, masks))
 
 
@@ -99,7 +100,7 @@ def test_dense_tma_shapes(eng, F, K):
     data = synth.uniform_f32(0, F * K, 3).reshape(F, K)
     masks = synth.uniform_f32(0, 11 * K, 4).reshape(11, K)
     out = eng.masks_dense(dev(data), dev(masks)).cpu().numpy()
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     assert_close_rel(out, f64_truth(data, masks), 2e-6)
 
 
@@ -111,7 +112,7 @@ def test_dense_tma_strided_accumulate(eng):
     out = torch.full((F, M + 2), 1.5, dtype=torch.float32, device='cuda')
     view = out[:, 1:1 + M]
     eng.masks_dense(tile, dev(masks), out=view, accumulate=True)
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     res = out.cpu().numpy()
     assert np.all(res[:, 0] == 1.5) and np.all(res[:, -1] == 1.5)
     assert_close_rel(res[:, 1:1 + M] - 1.5, f64_truth(big[:, 32:32 + K], masks), 2e-6)
@@ -235,7 +236,7 @@ def test_full_size_properties(eng):
     masks = dev(np.concatenate([mixed_masks(256, 256, 8, 22).reshape(8, -1),
                                 O.com_mask_stack((256, 256), 128, 128).reshape(3, -1)]))
     out = eng.masks_dense(data, masks)
-    assert eng.last_kernel() in (1, 3)
+    assert eng.last_kernel() in (1, 3, 6)
     sel = torch.arange(0, F, 97, device='cuda')
     truth = data[sel].double() @ masks.double().T
     scale = (data[sel].double().abs() @ masks.double().abs().T).amax(0, keepdim=True)
