@@ -11,7 +11,8 @@ nav-shaped result buffers are assembled with one NCCL all-gather inside the time
 A *step* = one pass of the hot path over the whole (per-rank) dataset through the plugin API:
 partition -> tile -> fused kernel -> merge (-> all-gather).  JSON keys:
   value      frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  roofline   the dominant kernel (k1_dense_tma) timed live with CUDA events: algorithmic bytes
+  roofline   the dominant kernel (k6_tensor_kernel, the tcgen05 dense masked reduction) timed
+             live with CUDA events: algorithmic bytes
              (frames x sig_size x 4) / mean launch duration vs MEASURED_PEAKS hbm_gbs
   e2e        same metric through run_udf() on a HOST (pinned) numpy dataset: H2D of every frame
              and D2H/get_results of every result inside the timed region
@@ -339,8 +340,11 @@ def gpu_arm(args):
                 'kernel_ms': kern_ms,
                 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'kernel_share_of_step': kern_ms * len(ev_log) / args.steps / ms_per_step}
-    prof = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
-    if os.path.exists(prof):
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
+    # command (cfg2 shape); None for other workloads
+    prof = os.path.join(ROOT, 'profiles',
+                        'k6_traffic.json' if engine.last_kernel() == 6 else 'k1_traffic.json')
+    if os.path.exists(prof) and args.workload == 'cfg2':
         try:
             roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception:

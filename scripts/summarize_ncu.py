@@ -22,6 +22,9 @@ WANT = [
     'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
     'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
+    'l1tex__data_pipe_tc_wavefronts_mem_shared.sum',
     'smsp__issue_active.avg.pct_of_peak_sustained_active',
     'smsp__inst_executed.sum', 'lts__t_bytes.sum',
     'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
