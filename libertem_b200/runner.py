@@ -27,6 +27,7 @@ from .udf.sumsigudf import ones_row
 from . import engine
 
 MAX_FUSED_COLUMNS = 24
+MAX_FUSED_COLUMNS_F32 = 32
 
 
 def _get_dtype(udfs, dtype, corrections=None):
@@ -382,11 +383,13 @@ class UDFRunner:
                 self._run_unfused(pu, explicit_tile())
         if not dense and sig_sum_view is None:
             return
-        # one pass over the tile per group of <= 24 columns
+        # one pass over the tile per group of <= 24 columns (FFMA2 kernel) or <= 32 columns
+        # (float32 tiles: the tensor-core kernel K6 takes 32 per pass)
+        max_cols = MAX_FUSED_COLUMNS_F32 if flat.dtype == torch.float32 else MAX_FUSED_COLUMNS
         groups, cur, ncols = [], [], 0
         for item in dense:
             c = item[2].shape[0]
-            if cur and ncols + c > MAX_FUSED_COLUMNS:
+            if cur and ncols + c > max_cols:
                 groups.append(cur)
                 cur, ncols = [], 0
             cur.append(item)
