@@ -16,8 +16,9 @@
  *                              (udf/masks.py:68-69, common/numba/__init__.py:90-184).
  *                              (`sig_sum` of ltb200_masks_dense fuses SumUDF, udf/sum.py:44-49,
  *                              into the same pass; uint16 tiles are ingested natively.)
- *   ltb200_group_masks      <- ApplyMasksUDF with radial_mask_factory masks
- *                              (analysis/radialfourier.py:106-146,184-194).
+ *   ltb200_group_masks(_tc) <- ApplyMasksUDF with radial_mask_factory masks
+ *                              (analysis/radialfourier.py:106-146,184-194); _tc = tensor cores.
+ *   ltb200_masks_dense_tc   <- the process_flat seam again, explicitly on the tensor cores.
  *   ltb200_synth_fill       <- test/bench data source standing in for MemoryDataSet contents
  *                              (io/dataset/memory.py:202-452); twin of oracle/synth.py.
  *
@@ -165,6 +166,23 @@ LTB_API int ltb200_group_masks(const void* tile, int tile_dtype, int64_t n_frame
                                const int32_t* group_off_dev, int n_groups, int n_pairs,
                                float* out, int64_t ld_out, int accumulate, void* workspace,
                                size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The same group-sparse contraction on the tensor cores (K7): tcgen05.mma kind::tf32 with the
+ * split-TF32 scheme of K6, accumulators in TMEM.  Same entry list / offsets as K4 (offsets
+ * multiples of 64).  table_split is (N, n_entries) float32 row-major with
+ * N = ltb200_group_masks_tc_columns(n_pairs): for the real column r = 2*pair + {0 re, 1 im},
+ * h = r / (N/4), j = r % (N/4): row h*(N/2) + j holds hi(weight), row h*(N/2) + N/4 + j holds
+ * lo(weight) (hi = weight rounded to TF32, lo = weight - hi rounded to TF32; unused rows zero).
+ * chain: 32-entry sub-tiles per TMEM accumulation chain (<= 0 -> default 2).
+ * ------------------------------------------------------------------------------------- */
+LTB_API int ltb200_group_masks_tc_columns(int n_pairs);
+LTB_API int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_t sig_size,
+                                  int64_t ld_tile, const int32_t* entry_px,
+                                  const float* table_split, const int32_t* group_off_host,
+                                  const int32_t* group_off_dev, int n_groups, int n_pairs,
+                                  float* out, int64_t ld_out, int accumulate, int chain,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic data (twin of oracle/synth.py): fills dst[0..count) with value(start + i).

@@ -21,10 +21,37 @@ KT = 128          # entries per pipeline stage (K4_KT)
 MAX_PAIRS = 28    # K4_NPR
 
 
+def tf32_round(a):
+    """float32 array rounded to TF32 precision (10 explicit mantissa bits, nearest, ties away):
+    the values ``tcgen05.mma.kind::tf32`` sees when the low 13 bits are already zero"""
+    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def split_table(table, n_cols):
+    """(pairs, n_entries, 2) complex weights -> the (N, n_entries) hi/lo table of the tensor-core
+    kernel K7 (row order documented in include/ltb200.h, ltb200_group_masks_tc)"""
+    pairs, n, _ = table.shape
+    nq = n_cols // 4
+    real = np.ascontiguousarray(table.transpose(0, 2, 1)).reshape(2 * pairs, n)   # r = 2*pair + w
+    hi = tf32_round(real)
+    lo = tf32_round(real - hi)
+    out = np.zeros((n_cols, n), dtype=np.float32)
+    for r in range(min(2 * pairs, 2 * nq)):
+        h, j = divmod(r, nq)
+        out[h * 2 * nq + j] = hi[r]
+        out[h * 2 * nq + nq + j] = lo[r]
+    return out
+
+
 class GroupPlan:
-    def __init__(self, entry_px, table_packed, group_off, n_groups, n_pairs, n_masks, device):
+    def __init__(self, entry_px, table_packed, group_off, n_groups, n_pairs, n_masks, device,
+                 table_split=None, n_cols=0):
         self.entry_px = torch.from_numpy(entry_px).to(device)
         self.table = torch.from_numpy(table_packed).to(device)
+        #: (N, n_entries) hi/lo weight table of the tensor-core kernel (None: FFMA2 kernel only)
+        self.table_split = None if table_split is None else torch.from_numpy(table_split).to(device)
+        self.n_cols = n_cols
         self.group_off_host = np.ascontiguousarray(group_off, dtype=np.int32)
         self.group_off_dev = torch.from_numpy(self.group_off_host).to(device)
         self.n_groups = n_groups
@@ -90,12 +117,20 @@ def build_plan(stack, group_size, device):
         # keep the TMA descriptor valid: one all-zero stage
         entry_px = np.zeros(KT, dtype=np.int32)
         table = np.zeros((MAX_PAIRS, KT, 2), dtype=np.float32)
+    n_cols = get_lib().ltb200_group_masks_tc_columns(group_size)
+    split = split_table(table[:group_size], n_cols) if n_cols else None
     return GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
-                     group_size, M, device)
+                     group_size, M, device, table_split=split, n_cols=n_cols)
 
 
-def group_masks(tile, plan, out=None, accumulate=False):
-    """out (F, n_masks) complex64 (+)= group-sparse contraction of the float32 tile"""
+#: frames from which the tensor-core kernel (128-frame items) is preferred over the FFMA2 one
+TC_MIN_FRAMES = 96
+
+
+def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
+    """out (F, n_masks) complex64 (+)= group-sparse contraction of the float32 tile.
+
+    kernel: 'auto' (tensor cores, K7, from TC_MIN_FRAMES frames), 'tc' (K7) or 'ffma' (K4)"""
     lib = get_lib()
     if not tile.is_cuda:
         raise _lib.LTB200Error('tile must be a CUDA tensor (no CPU fallback)')
@@ -110,6 +145,20 @@ def group_masks(tile, plan, out=None, accumulate=False):
     real = torch.view_as_real(out).reshape(F, 2 * plan.n_masks)
     ld_tile = tile.stride(0) if F > 1 else max(K, 1)
     ld_out = real.stride(0) if F > 1 else max(2 * plan.n_masks, 1)
+    use_tc = kernel == 'tc' or (kernel == 'auto' and F >= TC_MIN_FRAMES)
+    if use_tc and plan.table_split is None:
+        if kernel == 'tc':
+            raise _lib.LTB200Error('no tensor-core table for this plan')
+        use_tc = False
+    if use_tc:
+        with torch.cuda.device(tile.device):
+            check(lib.ltb200_group_masks_tc(
+                tile.data_ptr(), F, K, ld_tile, plan.entry_px.data_ptr(),
+                plan.table_split.data_ptr(), plan.group_off_host.ctypes.data,
+                plan.group_off_dev.data_ptr(), plan.n_groups, plan.n_pairs, real.data_ptr(),
+                ld_out, int(bool(accumulate)), int(chain), plan.workspace.data_ptr(),
+                plan.workspace.numel() * 4, torch.cuda.current_stream(tile.device).cuda_stream))
+        return out
     with torch.cuda.device(tile.device):
         check(lib.ltb200_group_masks(
             tile.data_ptr(), _lib.LTB_F32, F, K, ld_tile, plan.entry_px.data_ptr(),

@@ -83,10 +83,10 @@ if 'cfg5' in which:
     torch.cuda.empty_cache()
 if 'cfg4' in which:
     # nav sub-sample of 256x256 nav x 512x512 sig (1 MiB / frame)
-    ds = SyntheticDataSet((int(os.environ.get('CFG4_NAV0', '16')), 64, 512, 512), np.float32, seed=104, num_partitions=1)
+    ds = SyntheticDataSet((int(os.environ.get('CFG4_NAV0', '128')), 64, 512, 512), np.float32, seed=104, num_partitions=1)
     ctx = Context()
     a = ctx.create_radial_fourier_analysis(ds, n_bins=32)
     out.append(report('cfg4 (nav %dx64 sub-sample): 512x512 sig f32, radial Fourier 32 bins x 25 orders' % ds.shape[0],
-                      ds, [a.get_udf()], 'K4 group-sparse kernel, %d complex masks' % a.parameters['mask_count'], steps=3))
+                      ds, [a.get_udf()], 'K7 group-sparse tensor-core kernel, %d complex masks' % a.parameters['mask_count'], steps=3))
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(out, open('gpurun_out/configs.json', 'w'), indent=1)

@@ -1,4 +1,5 @@
-"""GPU parity of the group-sparse kernel K4 (ltb200_group_masks) against numpy."""
+"""GPU parity of the group-sparse kernels -- K4 (ltb200_group_masks, FFMA2) and K7
+(ltb200_group_masks_tc, tcgen05 split-TF32) -- against numpy float64."""
 import numpy as np
 import pytest
 import torch
@@ -22,28 +23,64 @@ def make_stack(n_groups, size, K, seed, empty_group=None):
     return stack
 
 
+@pytest.mark.parametrize('kernel', ['ffma', 'tc'])
 @pytest.mark.parametrize('F,K,n_groups,size', [(64, 512, 3, 25), (100, 1000, 5, 7), (7, 300, 2, 28),
-                                               (200, 4096, 32, 25), (65, 640, 4, 1)])
-def test_group_masks_matches_numpy(F, K, n_groups, size):
+                                               (200, 4096, 32, 25), (65, 640, 4, 1),
+                                               (129, 1000, 5, 4), (300, 2048, 6, 16),
+                                               (1000, 4096, 8, 25), (128, 700, 3, 9)])
+def test_group_masks_matches_numpy(F, K, n_groups, size, kernel):
     from libertem_b200 import group_masks as gm
     stack = make_stack(n_groups, size, K, seed=F + K, empty_group=1 if n_groups > 3 else None)
     assert gm.find_groups(stack) in (size, None) or size == 1
     plan = gm.build_plan(stack, size, torch.device('cuda'))
     data = synth.uniform_f32(0, F * K, 9).reshape(F, K)
     t = torch.from_numpy(data).cuda()
-    out = gm.group_masks(t, plan).cpu().numpy()
+    out = gm.group_masks(t, plan, kernel=kernel).cpu().numpy()
     ref = data.astype(np.float64) @ stack.astype(np.complex128).T
     scale = (np.abs(data).astype(np.float64) @ np.abs(stack).astype(np.float64).T).max() + 1e-30
     assert out.shape == ref.shape and out.dtype == np.complex64
     assert np.abs(out - ref).max() / scale <= 2e-6
     # accumulate
-    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True).cpu().numpy()
+    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True,
+                          kernel=kernel).cpu().numpy()
     assert np.abs(out2 - 2 * ref).max() / scale <= 4e-6
     # strided tile
     big = torch.zeros((F, K + 24), device='cuda')
     big[:, 8:8 + K] = t
-    out3 = gm.group_masks(big[:, 8:8 + K], plan).cpu().numpy()
+    out3 = gm.group_masks(big[:, 8:8 + K], plan, kernel=kernel).cpu().numpy()
     assert np.array_equal(out3, out)
+
+
+@pytest.mark.parametrize('chain', [1, 2, 3, 4, 7])
+def test_group_masks_tc_chains(chain):
+    """every TMEM chain length of K7 drains correctly; the two kernels agree"""
+    from libertem_b200 import group_masks as gm
+    F, K, n_groups, size = 400, 3000, 4, 25
+    stack = make_stack(n_groups, size, K, seed=77)
+    plan = gm.build_plan(stack, size, torch.device('cuda'))
+    data = synth.uniform_f32(0, F * K, 10).reshape(F, K)
+    t = torch.from_numpy(data).cuda()
+    ref = data.astype(np.float64) @ stack.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(stack).astype(np.float64).T).max() + 1e-30
+    out = gm.group_masks(t, plan, kernel='tc', chain=chain).cpu().numpy()
+    assert np.abs(out - ref).max() / scale <= 3e-6
+    ffma = gm.group_masks(t, plan, kernel='ffma').cpu().numpy()
+    assert np.abs(out - ffma).max() / scale <= 3e-6
+
+
+def test_split_table_layout():
+    from libertem_b200 import group_masks as gm
+    rng = np.random.default_rng(5)
+    t = (rng.random((25, 64, 2)) - 0.5).astype(np.float32)
+    s = gm.split_table(t, 112)
+    assert s.shape == (112, 64)
+    for r in (0, 1, 27, 28, 49):
+        h, j = divmod(r, 28)
+        hi, lo = s[h * 56 + j], s[h * 56 + 28 + j]
+        assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+        want = t[r // 2, :, r % 2]
+        assert np.abs(hi.astype(np.float64) + lo - want).max() <= 2.0 ** -22 * np.abs(want).max()
+    assert not s[56 + 22:56 + 28].any() and not s[56 + 28 + 22:].any()
 
 
 def test_find_groups():
