@@ -15,16 +15,22 @@
 // Work item = (ring, block of 128 frames), ring-major so that all CTAs read the same slice of
 // the weight table at the same time (the table -- N x n_entries floats, 131 MB for cfg4 -- is
 // larger than L2, a ring's slice is 4 MB).  Items are fetched dynamically; their metadata
-// travels with the pipeline stage.  17 warps:
-//   * warps 0..7  producers: 4-byte cp.async gather of 128 frames x 64 ring entries per stage
+// travels with the pipeline stage.  13 warps:
+//   * warps 0..3  producers: 4-byte cp.async gather of 128 frames x 64 ring entries per stage
 //     (lanes walk the ring's ascending pixel list -> runs coalesce) into two 128-byte-swizzled
 //     [128 x 32] sub-tiles, + TMA of the matching [N x 32] slices of the weight table (K-major,
 //     128-byte swizzle = canonical UMMA layout); both complete on one mbarrier.
-//   * warps 8..15 converters: thread <-> frame row (TMEM lane); warps 8..11 take entries 0..15
-//     of a sub-tile, warps 12..15 entries 16..31: LDS.128, hi/lo split, tcgen05.st into a 4-slot
+//   * warps 4..11 converters: thread <-> frame row (TMEM lane); warps 4..7 take entries 0..15
+//     of a sub-tile, warps 8..11 entries 16..31: LDS.128, hi/lo split, tcgen05.st into a 4-slot
 //     TMEM ring; they also drain the accumulators (each warp half of the columns) and store.
-//   * warp 16     MMA issuer (warp-uniform loop, one elected lane): per sub-tile 4 k-steps x
+//   * warp 12     MMA issuer (warp-uniform loop, one elected lane): per sub-tile 4 k-steps x
 //     (hi, lo) MMAs of M = 128, K = 8, N; tcgen05.commit frees the TMEM slot / the stage.
+// Measured (B200, cfg4 geometry, 8192 frames): 3.9 ms vs 6.3 ms for K4 (0.34 vs 0.21 of the HBM
+// roofline on the algorithmic bytes).  The bound is DRAM traffic, not the tensor pipe (24 %
+// busy): B200 fills L2 from DRAM in 128-byte lines (cudaLimitMaxL2FetchGranularity has no
+// effect), and a ring crosses an image row in runs of ~18 pixels, so a ring-by-ring gather moves
+// 2.2-2.7x the bytes it uses; scheduling adjacent rings of the same frames back to back
+// (rgroup) recovers part of it through L2.
 // Weight-table rows are ordered [hi(cols 0..N/4) | lo(cols 0..N/4) | hi(cols N/4..N/2) | lo(..)]
 // so that each half of the accumulator row holds the hi and lo parts of the same real columns.
 #include "common.cuh"
@@ -36,7 +42,7 @@ constexpr int K7_FB = 128;            // frames per item (TMEM lanes)
 constexpr int K7_KT = 64;             // ring entries per stage (2 sub-tiles of 32)
 constexpr int K7_STAGES = 3;
 constexpr int K7_AS = 4;              // TMEM operand ring (sub-tiles)
-constexpr int K7_PWARPS = 8;
+constexpr int K7_PWARPS = 4;
 constexpr int K7_CWARPS = 8;
 constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + 1) * 32;
 constexpr uint32_t K7_SUB_BYTES = K7_FB * 32 * 4;          // 16 KiB per sub-tile
@@ -256,6 +262,9 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
             }
             const int64_t f_first = fb * K7_FB + fq * FPT;
             const bool ragged = fb * K7_FB + K7_FB > p.n_frames;
+            // the pixel index of this thread's entry is loaded one stage ahead (an L2 round
+            // trip that would otherwise sit between the stage becoming free and its copies)
+            int px_next = done ? 0 : p.entry_px[e0 + sub * 32 + el];
             for (int c = 0; c < nchunks; c++, it++) {
                 const int stage = it % K7_STAGES;
                 mbar_wait(&free_bar[stage], ((it / K7_STAGES) & 1) ^ 1);
@@ -278,24 +287,31 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                     tma_load_2d(dst + K7_DATA_BYTES + N * 128, &tm_table, ebase + 32, 0,
                                 &full_bar[stage], pol_keep);
                 }
-                const int px = p.entry_px[ebase + sub * 32 + el];
+                const int px = px_next;
+                if (c + 1 < nchunks) px_next = p.entry_px[ebase + K7_KT + sub * 32 + el];
                 const uint32_t sdst = smem_u32(dst);
                 if (!ragged) {
                     const float* src = p.tile + px + f_first * p.ld_tile;
+#pragma unroll 1
+                    for (int f8 = 0; f8 < FPT / 8; f8++) {
 #pragma unroll
-                    for (int f = 0; f < FPT; f++) {
-                        k7_cp_async_4(sdst + sw[f & 7] + (uint32_t)(f >> 3) * 1024u, src);
-                        src += p.ld_tile;
+                        for (int c8 = 0; c8 < 8; c8++) {
+                            k7_cp_async_4(sdst + sw[c8] + (uint32_t)f8 * 1024u, src);
+                            src += p.ld_tile;
+                        }
                     }
                 } else {
                     // last frame block: rows past the end re-read the last frame (never stored)
                     const float* src = p.tile + px;
+#pragma unroll 1
+                    for (int f8 = 0; f8 < FPT / 8; f8++) {
 #pragma unroll
-                    for (int f = 0; f < FPT; f++) {
-                        int64_t fr = f_first + f;
-                        if (fr >= p.n_frames) fr = p.n_frames - 1;
-                        k7_cp_async_4(sdst + sw[f & 7] + (uint32_t)(f >> 3) * 1024u,
-                                      src + fr * p.ld_tile);
+                        for (int c8 = 0; c8 < 8; c8++) {
+                            int64_t fr = f_first + f8 * 8 + c8;
+                            if (fr >= p.n_frames) fr = p.n_frames - 1;
+                            k7_cp_async_4(sdst + sw[c8] + (uint32_t)f8 * 1024u,
+                                          src + fr * p.ld_tile);
+                        }
                     }
                 }
                 k7_cp_async_mbar_arrive_noinc(&full_bar[stage]);
@@ -558,20 +574,6 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
     }
     int grid = sm_count();
     if (p.n_items < grid) grid = (int)p.n_items;
-    if (const char* e = getenv("LTB200_K7_L2GRAN")) {      // experiment: L2 fetch granularity
-        static int applied = 0;
-        const int v = atoi(e);
-        if (v != applied && (v == 32 || v == 64 || v == 128)) {
-            size_t before = 0;
-            cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-            cudaError_t er = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-            size_t after = 0;
-            cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-            fprintf(stderr, "[ltb200] L2 fetch granularity %zu -> %zu (%s)\n", before, after,
-                    cudaGetErrorString(er));
-            applied = v;
-        }
-    }
     switch (n) {
         case 16: return k7_launch<16>(tm, p, grid, st);
         case 32: return k7_launch<32>(tm, p, grid, st);
