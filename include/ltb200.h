@@ -18,7 +18,9 @@
  *                              into the same pass; uint16 tiles are ingested natively.)
  *   ltb200_group_masks(_tc) <- ApplyMasksUDF with radial_mask_factory masks
  *                              (analysis/radialfourier.py:106-146,184-194); _tc = tensor cores.
- *   ltb200_masks_dense_tc   <- the process_flat seam again, explicitly on the tensor cores.
+ *   ltb200_masks_dense_tc   <- the process_flat seam again, explicitly on the tensor cores
+ *                              (_tc_u16: uint16 tiles; ltb200_masks_dense_i8: uint16 tiles x
+ *                              int8 masks, exact, on the int8 tensor cores).
  *   ltb200_synth_fill       <- test/bench data source standing in for MemoryDataSet contents
  *                              (io/dataset/memory.py:202-452); twin of oracle/synth.py.
  *
@@ -115,6 +117,38 @@ LTB_API int ltb200_masks_dense_tc(const float* tile, int64_t n_frames, int64_t s
                                   int64_t ld_tile, const float* masks, int n_masks,
                                   int64_t ld_masks, float* out, int64_t ld_out, int accumulate,
                                   int chain, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* uint16 tiles on the same kernel (the dtype conversion of the reference's tile decode,
+ * io/dataset/base/backend.py:69-117, happens in registers: hi = top 11 bits, lo = the rest,
+ * both exact TF32 numbers, so integer data x binary masks is bit-exact), 1..16 columns,
+ * sig_size % 8 == 0 and >= 256.  `sig_sum` (nullable, (sig_size) float32) fuses SumUDF
+ * (udf/sum.py:44-49) into the pass: extra warps sum every staged tile over its frames as exact
+ * 64-bit integers; sig_sum[k] += that sum, rounded once. */
+LTB_API size_t ltb200_masks_dense_tc_u16_workspace(int64_t n_frames, int64_t sig_size,
+                                                   int n_masks, int with_sig_sum);
+LTB_API int ltb200_masks_dense_tc_u16(const uint16_t* tile, int64_t n_frames, int64_t sig_size,
+                                      int64_t ld_tile, const float* masks, int n_masks,
+                                      int64_t ld_masks, float* out, int64_t ld_out,
+                                      int accumulate, int chain, float* sig_sum, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Integer fast path (K8): uint16 tiles x int8 masks (binary virtual-detector masks, all-ones
+ * for SumSigUDF, small integer weights) on the int8 tensor cores (tcgen05.mma kind::i8).  For
+ * integer data and integer masks the reference's float32 sums (udf/masks.py:59-77) are exact,
+ * so exact int32 accumulation reproduces them bit for bit; the bytes of the TMA-staged tile
+ * are the MMA operand as they land in shared memory -- no per-pixel instruction runs.
+ * out = float32 of the exact integer result.  `sig_sum` (nullable) fuses SumUDF
+ * (udf/sum.py:44-49) as a second MMA over the same stage.  1..16 columns, sig_size % 8 == 0,
+ * 256 <= sig_size <= 65536; LTB_ERR_UNSUPPORTED otherwise.
+ * ------------------------------------------------------------------------------------- */
+LTB_API size_t ltb200_masks_dense_i8_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
+                                               int with_sig_sum);
+LTB_API int ltb200_masks_dense_i8(const uint16_t* tile, int64_t n_frames, int64_t sig_size,
+                                  int64_t ld_tile, const int8_t* masks, int n_masks,
+                                  int64_t ld_masks, float* out, int64_t ld_out, int accumulate,
+                                  float* sig_sum, void* workspace, size_t workspace_bytes,
                                   void* stream);
 
 /* tuning / test knob: which dense kernel ltb200_masks_dense uses for float32 tiles.

@@ -132,5 +132,12 @@ size_t k6_workspace(int64_t n_frames, int64_t sig_size, int n_masks);
 int k6_run(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
            const float* masks, int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
            int accumulate, int chain, void* workspace, cudaStream_t st);
+// uint16 tiles (<= 16 columns) with the frame sum (SumUDF) fused into the same pass
+bool k6_u16_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+                     int n_masks);
+size_t k6_u16_workspace(int64_t n_frames, int64_t sig_size, int n_masks, int with_sig_sum);
+int k6_run_u16(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+               const float* masks, int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
+               int accumulate, int chain, float* sig_sum, void* workspace, cudaStream_t st);
 
 }  // namespace ltb

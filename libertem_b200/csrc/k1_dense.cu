@@ -484,6 +484,15 @@ static int k6_min_columns() {
     return v;
 }
 
+static bool k6_u16_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        v = 1;
+        if (const char* e = getenv("LTB200_K6U")) v = atoi(e) != 0;
+    }
+    return v != 0;
+}
+
 static int k1_variant() {
     // which FFMA2 register tile the dense path uses: 0 auto, 1 even/odd-pixel pairs ("eo"),
     // 2 mask pairs ("pair"); LTB200_K1=eo|pair|auto or ltb200_set_k1_variant()
@@ -629,6 +638,10 @@ extern "C" size_t ltb200_masks_dense_workspace(int64_t n_frames, int64_t sig_siz
     if (n_masks > 0) {
         const size_t k6 = k6_workspace(n_frames, sig_size, n_masks);
         if (k6 > need) need = k6;
+        if (n_masks <= 16) {
+            const size_t k6u = k6_u16_workspace(n_frames, sig_size, n_masks, with_sig_sum);
+            if (k6u > need) need = k6u;
+        }
     }
     return need;
 }
@@ -789,6 +802,18 @@ extern "C" int ltb200_masks_dense(const void* tile, int tile_dtype, int64_t n_fr
                         accumulate, 0, workspace, st);
         if (rc != LTB_OK) return rc;
         n_masks = 0;   // columns done; a requested frame sum still runs below
+    }
+    // uint16 tiles of >= 1024 frames and 7..16 columns: the same tensor-core kernel with the
+    // conversion in registers and the frame sum (SumUDF) fused in (LTB200_K6U=0: FFMA2 kernel)
+    // (<= 6 columns stay on the FFMA2 kernel, which is faster there and fuses the frame sum
+    // too -- measured 0.68 vs 0.60 of the HBM roofline at 5 columns + sum; variant 3 forces K6)
+    if (tma_u16 && n_masks > 0 && n_frames >= 1024 && (variant_all == 0 || variant_all == 3) &&
+        (variant_all == 3 || n_masks > 6 || (sig_sum != nullptr && !k1_fuses_sig)) &&
+        k6_u16_enabled() && k6_u16_shape_ok(tile, n_frames, sig_size, ld_tile, n_masks)) {
+        int rc = k6_run_u16(tile, n_frames, sig_size, ld_tile, masks, n_masks, ld_masks, out,
+                            ld_out, accumulate, 0, sig_sum, workspace, st);
+        if (rc != LTB_OK) return rc;
+        return LTB_OK;
     }
     // mask columns are processed in groups of <= 24 (one pass over the frames per group)
     for (int m0 = 0; m0 < n_masks; m0 += 24) {

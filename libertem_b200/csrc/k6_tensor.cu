@@ -64,6 +64,7 @@ constexpr uint32_t K6_DATA_BYTES = K6_FB * K6_KS * 4;   // 32 KiB per sub-stage
 constexpr int K6_TMEM_COLS = 512;
 constexpr int K6_AS = 2;              // TMEM ring of A operands
 constexpr int K6_A_BASE = 256;        // TMEM columns [256, 512): 2 slots x 2 groups x (hi 32 | lo 32)
+constexpr int K6_U16_MAX_COLUMNS = 16; // uint16 form: N in {16, 32}
 
 struct K6Params {
     int64_t n_frames;
@@ -78,6 +79,22 @@ struct K6Params {
     int accumulate;
     int chain;             // sub-stages per TMEM accumulation chain
     int debug;             // bring-up switches (LTB200_K6_DEBUG): 1 no convert, 2 no MMA, 4 no drain
+    unsigned long long* sig_acc;   // uint16 tiles: (sig_size) exact integer frame sums, or NULL
+};
+
+// per input type: a data stage is one 128-byte row per frame = 32 float32 or 64 uint16 pixels,
+// i.e. HALVES sub-stages of 32 pixels (the unit of the mask ring, the TMEM operand ring and the
+// accumulation chains).  uint16 tiles get four extra warps for the fused frame sum (SumUDF).
+template <typename TIN> struct K6In;
+template <> struct K6In<float> {
+    static constexpr int HALVES = 1;
+    static constexpr int THREADS = K6_THREADS;
+    static constexpr int SUM_WARPS = 0;
+};
+template <> struct K6In<uint16_t> {
+    static constexpr int HALVES = 2;
+    static constexpr int THREADS = K6_THREADS + 128;
+    static constexpr int SUM_WARPS = 4;
 };
 
 // ---- tcgen05 wrappers ----------------------------------------------------------------------
@@ -223,11 +240,13 @@ struct K6Smem {
     static constexpr uint32_t total(int n) { return bar_off(n) + 256 + 1024; }   // + align slack
 };
 
-template <int N>
-__global__ void __launch_bounds__(K6_THREADS, 1)
+template <int N, typename TIN>
+__global__ void __launch_bounds__(K6In<TIN>::THREADS, 1)
 k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                  const __grid_constant__ CUtensorMap tm_mask, const K6Params p) {
     constexpr int NH = N / 2;
+    constexpr int HALVES = K6In<TIN>::HALVES;
+    constexpr int PX = K6_KS * HALVES;            // pixels per data stage
     constexpr uint32_t MASK_BYTES = (uint32_t)N * 128u;
     constexpr uint32_t IDESC = umma_idesc_tf32(N);
     static_assert(N % 16 == 0 && N >= 16 && N <= 64, "K6: N in {16, 32, 48, 64}");
@@ -253,7 +272,8 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
     if (threadIdx.x == 0) {
         for (int s = 0; s < K6_DS; s++) {
             mbar_init(&data_full[s], 1);
-            mbar_init(&data_free[s], K6_CONV_WARPS);
+            mbar_init(&data_free[s],
+                      K6_CONV_WARPS + (p.sig_acc != nullptr ? K6In<TIN>::SUM_WARPS : 0));
         }
         for (int s = 0; s < K6_MS; s++) {
             mbar_init(&mask_full[s], 1);
@@ -290,13 +310,13 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 const int64_t k0 = (item % p.ksplit) * p.k_per_split;
                 int64_t k1 = k0 + p.k_per_split;
                 if (k1 > p.sig_size) k1 = p.sig_size;
-                const int n_sub = (int)((k1 - k0 + K6_KS - 1) / K6_KS);
+                const int n_dsub = (int)((k1 - k0 + PX - 1) / PX);
                 const int32_t f0 = (int32_t)(fb * K6_FB);
-                for (int i = 0; i < n_sub; i++, it++) {
+                for (int i = 0; i < n_dsub; i++, it++) {
                     const int ds = it % K6_DS;
                     mbar_wait(&data_free[ds], ((it / K6_DS) & 1) ^ 1);
                     mbar_arrive_expect_tx(&data_full[ds], K6_DATA_BYTES);
-                    tma_load_2d(smem + K6Smem::data_off(ds), &tm_data, (int32_t)(k0 + i * K6_KS),
+                    tma_load_2d(smem + K6Smem::data_off(ds), &tm_data, (int32_t)(k0 + i * PX),
                                 f0, &data_full[ds], pol);
                 }
             }
@@ -311,7 +331,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 const int64_t k0 = (item % p.ksplit) * p.k_per_split;
                 int64_t k1 = k0 + p.k_per_split;
                 if (k1 > p.sig_size) k1 = p.sig_size;
-                const int n_sub = (int)((k1 - k0 + K6_KS - 1) / K6_KS);
+                const int n_sub = (int)((k1 - k0 + PX - 1) / PX) * HALVES;
                 for (int i = 0; i < n_sub; i++, it++) {
                     const int ms = it % K6_MS;
                     mbar_wait(&mask_empty[ms], ((it / K6_MS) & 1) ^ 1);
@@ -328,7 +348,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
             const int64_t k0 = (item % p.ksplit) * p.k_per_split;
             int64_t k1 = k0 + p.k_per_split;
             if (k1 > p.sig_size) k1 = p.sig_size;
-            const int n_sub = (int)((k1 - k0 + K6_KS - 1) / K6_KS);
+            const int n_sub = (int)((k1 - k0 + PX - 1) / PX) * HALVES;
             int in_chain = 0, cbuf = 0;
             for (int i = 0; i < n_sub; i++, it++) {
                 const int ms = it % K6_MS;
@@ -364,7 +384,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + K6_CONV_WARPS) {
         // ===== converters / accumulator drain =====
         const int cw = warp - 4;
         const int g = cw >> 2;
@@ -374,14 +394,16 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
 
-        uint32_t it = 0;
+        uint32_t it = 0;                             // 32-pixel sub-stages
+        uint32_t dit = 0;                            // data stages
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int64_t fb = item / p.ksplit;
             const int ksi = (int)(item % p.ksplit);
             const int64_t k0 = (int64_t)ksi * p.k_per_split;
             int64_t k1 = k0 + p.k_per_split;
             if (k1 > p.sig_size) k1 = p.sig_size;
-            const int n_sub = (int)((k1 - k0 + K6_KS - 1) / K6_KS);
+            const int n_dsub = (int)((k1 - k0 + PX - 1) / PX);
+            const int n_sub = n_dsub * HALVES;
 
             float acc[NH];
 #pragma unroll
@@ -410,79 +432,111 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             };
 
-            for (int i = 0; i < n_sub; i++, it++) {
-                const int ds = it % K6_DS;
-                const int as = it % K6_AS;
-                mbar_wait(&data_full[ds], (it / K6_DS) & 1);
+            for (int di = 0; di < n_dsub; di++, dit++) {
+                const int ds = dit % K6_DS;
+                mbar_wait(&data_full[ds], (dit / K6_DS) & 1);
                 const uint8_t* rp = smem + K6Smem::data_off(ds) + row_off;
-                float4 x[8];
+                uint4 x[8];                           // this frame's 128-byte row of the stage
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                    x[j] = *reinterpret_cast<const float4*>(rp + (((uint32_t)j ^ swz) << 4));
-                // lo slot `as` is free once the MMAs of sub-stage i - AS have completed
-                mbar_wait(&mma_done[as], ((it / K6_AS) & 1) ^ 1);
-                int known = i - K6_AS;
-                // chain i/chain - 2 shares its accumulator with the chain that starts at
-                // sub-stage i: it must be drained before this sub-stage is handed to the MMAs
-                if (i % chain == 0 && i >= 2 * chain) {
-                    const int must = i - chain - 1;
-                    if (must > known) {
-                        const uint32_t itm = it - (uint32_t)(i - must);
-                        mbar_wait(&mma_done[itm % K6_AS], (itm / K6_AS) & 1);
-                        known = must;
-                    }
-                }
-                tc_fence_after();
-                // at most one chain completes per sub-stage: issue its TMEM loads now, use them
-                // after the conversion below (the load latency hides behind the ALU work)
-                uint32_t v[N / 16][16];
-                bool pend = false;
-                if (known >= 0 && !(p.debug & 4) && next_chain * chain < n_sub &&
-                    chain_end(next_chain) <= known) {
-                    const uint32_t d =
-                        tmem_base + lane_sel + (uint32_t)((g * 2 + (next_chain & 1)) * N);
+                    x[j] = *reinterpret_cast<const uint4*>(rp + (((uint32_t)j ^ swz) << 4));
 #pragma unroll
-                    for (int q = 0; q < N / 16; q++) tc_ld16(d + q * 16, v[q]);
-                    pend = true;
-                    next_chain++;
-                }
-                const uint32_t a = tmem_base + lane_sel + (uint32_t)(K6_A_BASE + as * 128 + g * 64);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (p.debug & 1) break;
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float4 xv = x[h * 4 + j];
-                        const float e[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            // hi = top 19 bits (a TF32 number); lo = x - hi exactly, rounded to
-                            // nearest at TF32 precision by adding half a TF32 ulp (kind::tf32
-                            // ignores the low 13 bits of its operands)
-                            const uint32_t hb = __float_as_uint(e[t]) & 0xFFFFE000u;
-                            hi[j * 4 + t] = hb;
-                            lo[j * 4 + t] = __float_as_uint(e[t] - __uint_as_float(hb)) + 0x1000u;
+                for (int h2 = 0; h2 < HALVES; h2++, it++) {
+                    const int i = di * HALVES + h2;
+                    const int as = it % K6_AS;
+                    // lo slot `as` is free once the MMAs of sub-stage i - AS have completed
+                    mbar_wait(&mma_done[as], ((it / K6_AS) & 1) ^ 1);
+                    int known = i - K6_AS;
+                    // chain i/chain - 2 shares its accumulator with the chain that starts at
+                    // sub-stage i: it must be drained before this sub-stage is handed to the MMAs
+                    if (i % chain == 0 && i >= 2 * chain) {
+                        const int must = i - chain - 1;
+                        if (must > known) {
+                            const uint32_t itm = it - (uint32_t)(i - must);
+                            mbar_wait(&mma_done[itm % K6_AS], (itm / K6_AS) & 1);
+                            known = must;
                         }
                     }
-                    tc_st16(a + h * 16, hi);
-                    tc_st16(a + 32 + h * 16, lo);
-                }
-                if (pend) {
-                    tc_wait_ld();
+                    tc_fence_after();
+                    // at most one chain completes per sub-stage: issue its TMEM loads now, use
+                    // them after the conversion below (the load latency hides behind the ALU work)
+                    uint32_t v[N / 16][16];
+                    bool pend = false;
+                    if (known >= 0 && !(p.debug & 4) && next_chain * chain < n_sub &&
+                        chain_end(next_chain) <= known) {
+                        const uint32_t d =
+                            tmem_base + lane_sel + (uint32_t)((g * 2 + (next_chain & 1)) * N);
 #pragma unroll
-                    for (int q = 0; q < N / 16; q++) tc_ld_fence16(v[q]);
+                        for (int q = 0; q < N / 16; q++) tc_ld16(d + q * 16, v[q]);
+                        pend = true;
+                        next_chain++;
+                    }
+                    const uint32_t a =
+                        tmem_base + lane_sel + (uint32_t)(K6_A_BASE + as * 128 + g * 64);
 #pragma unroll
-                    for (int c = 0; c < NH; c++)
-                        acc[c] += __uint_as_float(v[c / 16][c % 16]) +
-                                  __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&a_full[as]);
-                    mbar_arrive(&data_free[ds]);
+                    for (int h = 0; h < 2; h++) {
+                        if (p.debug & 1) break;
+                        uint32_t hi[16], lo[16];
+                        if constexpr (HALVES == 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint4 xv = x[h * 4 + j];
+                                const uint32_t e[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    // hi = top 19 bits (a TF32 number); lo = x - hi exactly,
+                                    // rounded to nearest at TF32 precision by adding half a TF32
+                                    // ulp (kind::tf32 ignores the low 13 bits of its operands)
+                                    const uint32_t hb = e[t] & 0xFFFFE000u;
+                                    hi[j * 4 + t] = hb;
+                                    lo[j * 4 + t] = __float_as_uint(__uint_as_float(e[t]) -
+                                                                    __uint_as_float(hb)) +
+                                                    0x1000u;
+                                }
+                            }
+                        } else {
+                            // uint16 pixels: 0x4B00vvvv is the float 2^23 + v, so v as a float
+                            // costs PRMT + FADD (exact for all 16-bit values); hi = its top 11
+                            // significant bits, lo = v - hi has <= 5 bits: both exact TF32 numbers
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const uint4 xv = x[h2 * 4 + h * 2 + j];
+                                const uint32_t e[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+#pragma unroll
+                                    for (int u = 0; u < 2; u++) {
+                                        const float f =
+                                            __uint_as_float(__byte_perm(e[t], 0x4B000000u,
+                                                                        u ? 0x7632 : 0x7610)) -
+                                            8388608.f;
+                                        const uint32_t hb = __float_as_uint(f) & 0xFFFFE000u;
+                                        hi[j * 8 + t * 2 + u] = hb;
+                                        lo[j * 8 + t * 2 + u] =
+                                            __float_as_uint(f - __uint_as_float(hb));
+                                    }
+                                }
+                            }
+                        }
+                        tc_st16(a + h * 16, hi);
+                        tc_st16(a + 32 + h * 16, lo);
+                    }
+                    if (pend) {
+                        tc_wait_ld();
+#pragma unroll
+                        for (int q = 0; q < N / 16; q++) tc_ld_fence16(v[q]);
+#pragma unroll
+                        for (int c = 0; c < NH; c++)
+                            acc[c] += __uint_as_float(v[c / 16][c % 16]) +
+                                      __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&a_full[as]);
+                        if (h2 == HALVES - 1) mbar_arrive(&data_free[ds]);
+                    }
                 }
             }
             // item tail: the last commit covers every earlier MMA of the item
@@ -509,6 +563,53 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             }
         }
+    } else if (K6In<TIN>::SUM_WARPS > 0 && warp >= 4 + K6_CONV_WARPS) {
+        // ===== fused frame sum (SumUDF, reference udf/sum.py:44-49) of uint16 tiles =====
+        // Warp sw owns the logical 16-byte chunks {2 sw, 2 sw + 1} (16 pixels) of every row of
+        // the stage.  Per step its four lane octets read rows r, r + 2, r + 4, r + 6: the
+        // 128-byte swizzle (chunk ^ (row & 7)) sends the same chunk pair of those rows to four
+        // different bank groups, so the LDS.32 is conflict-free.  Sums are exact integers:
+        // 64 rows x 65535 < 2^32 per lane and stage, then one 64-bit RED per pixel and stage.
+        if (p.sig_acc != nullptr) {
+            const int sw = warp - (4 + K6_CONV_WARPS);
+            const int q = lane >> 3;                 // row octet of the step
+            const int sub = lane & 7;
+            const uint32_t chunk = (uint32_t)(2 * sw + (sub >> 2));
+            const uint32_t word = (uint32_t)(sub & 3) * 4u;
+            uint32_t dit = 0;
+            for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int64_t k0 = (item % p.ksplit) * p.k_per_split;
+                int64_t k1 = k0 + p.k_per_split;
+                if (k1 > p.sig_size) k1 = p.sig_size;
+                const int n_dsub = (int)((k1 - k0 + PX - 1) / PX);
+                for (int di = 0; di < n_dsub; di++, dit++) {
+                    const int ds = dit % K6_DS;
+                    mbar_wait(&data_full[ds], (dit / K6_DS) & 1);
+                    const uint8_t* base = smem + K6Smem::data_off(ds);
+                    uint32_t s0 = 0, s1 = 0;
+#pragma unroll 8
+                    for (int st = 0; st < K6_FB / 4; st++) {
+                        const uint32_t r = (uint32_t)((st >> 1) * 8 + (st & 1) + 2 * q);
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(
+                            base + r * 128u + ((chunk ^ (r & 7u)) << 4) + word);
+                        s0 += v & 0xFFFFu;
+                        s1 += v >> 16;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&data_free[ds]);
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    if (q == 0) {
+                        const int64_t px = k0 + (int64_t)di * PX + chunk * 8 + (sub & 3) * 2;
+                        if (px < p.sig_size) atomicAdd(p.sig_acc + px, (unsigned long long)s0);
+                        if (px + 1 < p.sig_size)
+                            atomicAdd(p.sig_acc + px + 1, (unsigned long long)s1);
+                    }
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -524,11 +625,11 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int k6_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms) {
+static int k6_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms, int px) {
     int best = 1;
     double best_eff = 0.0;
     for (int ks = 1; ks <= 64; ks *= 2) {
-        if (ks > 1 && sig_size / ks < 16 * K6_KS) break;
+        if (ks > 1 && sig_size / ks < 16 * px) break;
         const int64_t items = n_fb * ks;
         const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
         if (eff > best_eff + 1e-9) {
@@ -545,27 +646,29 @@ static size_t k6_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int k6_nh(int n_masks) { return n_masks <= 8 ? 8 : n_masks <= 16 ? 16 : n_masks <= 24 ? 24 : 32; }
 
 struct K6Ws {
-    size_t pack_off, part_off, total;
+    size_t pack_off, part_off, sig_off, total;
 };
 
-static K6Ws k6_ws(int64_t n_frames, int64_t sig_size, int n_masks) {
+// px = pixels per data stage (32 for float32, 64 for uint16 tiles)
+static K6Ws k6_ws(int64_t n_frames, int64_t sig_size, int n_masks, int px, bool with_sig) {
     K6Ws w;
     const int nm = n_masks > 32 ? 32 : n_masks;
-    const int64_t sig_pad = ((sig_size + 31) / 32) * 32;
+    const int64_t sig_pad = ((sig_size + 63) / 64) * 64;
     w.pack_off = 0;
     const size_t pack = (size_t)2 * k6_nh(nm) * sig_pad * sizeof(float);
     w.part_off = k6_align256(pack);
     const int64_t n_fb = (n_frames + K6_FB - 1) / K6_FB;
-    const int ks = k6_choose_ksplit(n_fb, sig_size, sm_count());
+    const int ks = k6_choose_ksplit(n_fb, sig_size, sm_count(), px);
     const size_t part = ks > 1 ? (size_t)ks * n_frames * nm * sizeof(float) : 0;
-    w.total = w.part_off + k6_align256(part);
+    w.sig_off = w.part_off + k6_align256(part);
+    w.total = w.sig_off + (with_sig ? k6_align256((size_t)sig_size * 8) : 0);
     return w;
 }
 
-template <int N>
+template <int N, typename TIN>
 static int k6_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K6Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k6_tensor_kernel<N>;
+    auto kern = k6_tensor_kernel<N, TIN>;
     const size_t smem = K6Smem::total(N);
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -575,7 +678,7 @@ static int k6_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K6Par
                                             (int)smem));
         configured_dev = dev;
     }
-    kern<<<grid, K6_THREADS, smem, st>>>(tmd, tmm, p);
+    kern<<<grid, K6In<TIN>::THREADS, smem, st>>>(tmd, tmm, p);
     count_launch();
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
@@ -587,8 +690,20 @@ bool k6_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t l
            n_frames < (1ll << 31);
 }
 
+// uint16 tiles: 16-byte aligned rows; <= 16 columns (the 512-thread form has 128 registers)
+bool k6_u16_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+                     int n_masks) {
+    return sig_size % 8 == 0 && ld_tile % 8 == 0 && (uintptr_t)tile % 16 == 0 &&
+           sig_size >= 8 * K6_KS && n_frames >= 1 && sig_size < (1ll << 30) &&
+           n_frames < (1ll << 31) && n_masks >= 1 && n_masks <= K6_U16_MAX_COLUMNS;
+}
+
 size_t k6_workspace(int64_t n_frames, int64_t sig_size, int n_masks) {
-    return k6_ws(n_frames, sig_size, n_masks).total;
+    return k6_ws(n_frames, sig_size, n_masks, K6_KS, false).total;
+}
+
+size_t k6_u16_workspace(int64_t n_frames, int64_t sig_size, int n_masks, int with_sig_sum) {
+    return k6_ws(n_frames, sig_size, n_masks, 2 * K6_KS, with_sig_sum != 0).total;
 }
 
 int k6_default_chain() {
@@ -603,23 +718,33 @@ int k6_default_chain() {
     return chain;
 }
 
+// sig_sum[k] += exact integer frame sum (rounded once to float32)
+__global__ void k6_sig_finalize_kernel(const unsigned long long* __restrict__ acc,
+                                       int64_t sig_size, float* __restrict__ sig_sum) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < sig_size) sig_sum[k] += (float)acc[k];
+}
+
 // one pass over the frames for <= 32 mask columns
+template <typename TIN>
 static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
                         const float* mk, int nm, int64_t ld_masks, float* o, int64_t ld_out,
-                        int accumulate, int chain, uint8_t* ws, const K6Ws& wl, cudaStream_t st) {
+                        int accumulate, int chain, float* sig_sum, uint8_t* ws, const K6Ws& wl,
+                        cudaStream_t st) {
+    constexpr int PX = K6_KS * K6In<TIN>::HALVES;
     const int sms = sm_count();
     const int nh = k6_nh(nm);
     const int n = 2 * nh;
-    const int64_t sig_pad = ((sig_size + 31) / 32) * 32;
+    const int64_t sig_pad = ((sig_size + 63) / 64) * 64;
     const int64_t n_fb = (n_frames + K6_FB - 1) / K6_FB;
 
     K6Params p;
     p.n_frames = n_frames;
     p.sig_size = sig_size;
     p.n_masks = nm;
-    p.ksplit = k6_choose_ksplit(n_fb, sig_size, sms);
-    const int64_t subs = (sig_size + K6_KS - 1) / K6_KS;
-    p.k_per_split = ((subs + p.ksplit - 1) / p.ksplit) * K6_KS;
+    p.ksplit = k6_choose_ksplit(n_fb, sig_size, sms, PX);
+    const int64_t subs = (sig_size + PX - 1) / PX;
+    p.k_per_split = ((subs + p.ksplit - 1) / p.ksplit) * PX;
     p.n_items = n_fb * p.ksplit;
     p.out = o;
     p.ld_out = ld_out;
@@ -627,8 +752,13 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
     p.accumulate = accumulate;
     p.chain = chain > 0 ? chain : k6_default_chain();
     p.debug = 0;
+    p.sig_acc = nullptr;
     if (const char* e = getenv("LTB200_K6_DEBUG")) p.debug = atoi(e);
     const int grid = (int)(p.n_items < sms ? p.n_items : sms);
+    if (sig_sum != nullptr) {
+        p.sig_acc = (unsigned long long*)(ws + wl.sig_off);
+        LTB_CUDA_CHECK(cudaMemsetAsync(p.sig_acc, 0, (size_t)sig_size * 8, st));
+    }
 
     float* packed = (float*)(ws + wl.pack_off);
     {
@@ -640,19 +770,29 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
         count_launch();
     }
     CUtensorMap tmd, tmm;
-    int rc = encode_tmap_2d_sw(&tmd, tile, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)sig_size,
-                               (uint64_t)n_frames, (uint64_t)ld_tile * 4, K6_KS, K6_FB,
+    int rc = encode_tmap_2d_sw(&tmd, tile,
+                               sizeof(TIN) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                               (uint64_t)sig_size, (uint64_t)n_frames,
+                               (uint64_t)ld_tile * sizeof(TIN), PX, K6_FB,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
     rc = encode_tmap_2d_sw(&tmm, packed, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)sig_pad,
                            (uint64_t)n, (uint64_t)sig_pad * 4, K6_KS, (uint32_t)n,
                            CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
-    switch (n) {
-        case 16: rc = k6_launch<16>(tmd, tmm, p, grid, st); break;
-        case 32: rc = k6_launch<32>(tmd, tmm, p, grid, st); break;
-        case 48: rc = k6_launch<48>(tmd, tmm, p, grid, st); break;
-        default: rc = k6_launch<64>(tmd, tmm, p, grid, st); break;
+    if constexpr (sizeof(TIN) == 2) {
+        switch (n) {
+            case 16: rc = k6_launch<16, TIN>(tmd, tmm, p, grid, st); break;
+            default: rc = k6_launch<32, TIN>(tmd, tmm, p, grid, st); break;
+        }
+    } else {
+        switch (n) {
+            case 16: rc = k6_launch<16, TIN>(tmd, tmm, p, grid, st); break;
+            case 32: rc = k6_launch<32, TIN>(tmd, tmm, p, grid, st); break;
+            case 48: rc = k6_launch<48, TIN>(tmd, tmm, p, grid, st); break;
+            default: rc = k6_launch<64, TIN>(tmd, tmm, p, grid, st); break;
+        }
     }
     if (rc != LTB_OK) return rc;
     if (p.ksplit > 1) {
@@ -663,6 +803,11 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
                                                    accumulate);
         count_launch();
     }
+    if (sig_sum != nullptr) {
+        k6_sig_finalize_kernel<<<(unsigned)((sig_size + 255) / 256), 256, 0, st>>>(
+            p.sig_acc, sig_size, sig_sum);
+        count_launch();
+    }
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
 }
@@ -670,14 +815,28 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
 int k6_run(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
            const float* masks, int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
            int accumulate, int chain, void* workspace, cudaStream_t st) {
-    const K6Ws wl = k6_ws(n_frames, sig_size, n_masks);
+    const K6Ws wl = k6_ws(n_frames, sig_size, n_masks, K6_KS, false);
     for (int m0 = 0; m0 < n_masks; m0 += 32) {
         const int nm = (n_masks - m0) > 32 ? 32 : (n_masks - m0);
-        int rc = k6_run_group(tile, n_frames, sig_size, ld_tile, masks + (int64_t)m0 * ld_masks,
-                              nm, ld_masks, out + m0, ld_out, accumulate, chain,
-                              (uint8_t*)workspace, wl, st);
+        int rc = k6_run_group<float>(tile, n_frames, sig_size, ld_tile,
+                                     masks + (int64_t)m0 * ld_masks, nm, ld_masks, out + m0,
+                                     ld_out, accumulate, chain, nullptr, (uint8_t*)workspace, wl,
+                                     st);
         if (rc != LTB_OK) return rc;
     }
+    set_last_kernel(6);
+    return LTB_OK;
+}
+
+// uint16 tiles, <= K6_U16_MAX_COLUMNS columns, optional fused frame sum (sig_sum += sum_f tile)
+int k6_run_u16(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+               const float* masks, int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
+               int accumulate, int chain, float* sig_sum, void* workspace, cudaStream_t st) {
+    const K6Ws wl = k6_ws(n_frames, sig_size, n_masks, 2 * K6_KS, sig_sum != nullptr);
+    int rc = k6_run_group<uint16_t>(tile, n_frames, sig_size, ld_tile, masks, n_masks, ld_masks,
+                                    out, ld_out, accumulate, chain, sig_sum, (uint8_t*)workspace,
+                                    wl, st);
+    if (rc != LTB_OK) return rc;
     set_last_kernel(6);
     return LTB_OK;
 }
@@ -716,4 +875,40 @@ extern "C" int ltb200_masks_dense_tc(const float* tile, int64_t n_frames, int64_
     }
     return k6_run(tile, n_frames, sig_size, ld_tile, masks, n_masks, ld_masks, out, ld_out,
                   accumulate, chain, workspace, (cudaStream_t)stream);
+}
+
+extern "C" size_t ltb200_masks_dense_tc_u16_workspace(int64_t n_frames, int64_t sig_size,
+                                                      int n_masks, int with_sig_sum) {
+    if (n_frames <= 0 || sig_size <= 0 || n_masks <= 0) return 0;
+    return k6_u16_workspace(n_frames, sig_size, n_masks, with_sig_sum);
+}
+
+extern "C" int ltb200_masks_dense_tc_u16(const uint16_t* tile, int64_t n_frames,
+                                         int64_t sig_size, int64_t ld_tile, const float* masks,
+                                         int n_masks, int64_t ld_masks, float* out,
+                                         int64_t ld_out, int accumulate, int chain,
+                                         float* sig_sum, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    LTB_REQUIRE(n_frames >= 0 && sig_size >= 0 && n_masks >= 0,
+                "masks_dense_tc_u16: negative size");
+    if (n_frames == 0 || n_masks == 0) return LTB_OK;
+    LTB_REQUIRE(tile != nullptr && masks != nullptr && out != nullptr,
+                "masks_dense_tc_u16: NULL pointer");
+    LTB_REQUIRE(ld_tile >= sig_size && ld_masks >= sig_size && ld_out >= n_masks,
+                "masks_dense_tc_u16: leading dimension too small");
+    if (!k6_u16_shape_ok(tile, n_frames, sig_size, ld_tile, n_masks)) {
+        set_error("masks_dense_tc_u16: shape not supported by the tensor-core path (sig_size "
+                  "%lld, ld_tile %lld, %d columns; need sig_size %% 8 == 0, >= 256, <= %d "
+                  "columns)", (long long)sig_size, (long long)ld_tile, n_masks,
+                  K6_U16_MAX_COLUMNS);
+        return LTB_ERR_UNSUPPORTED;
+    }
+    const size_t need = k6_u16_workspace(n_frames, sig_size, n_masks, sig_sum != nullptr);
+    if (need > workspace_bytes || workspace == nullptr) {
+        set_error("masks_dense_tc_u16: workspace of %zu B required, %zu B given", need,
+                  workspace_bytes);
+        return LTB_ERR_WORKSPACE;
+    }
+    return k6_run_u16(tile, n_frames, sig_size, ld_tile, masks, n_masks, ld_masks, out, ld_out,
+                      accumulate, chain, sig_sum, workspace, (cudaStream_t)stream);
 }

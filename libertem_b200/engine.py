@@ -137,6 +137,80 @@ def masks_dense_tc(tile, masks, out=None, accumulate=False, chain=0):
     return out
 
 
+def masks_dense_tc_u16(tile, masks, out=None, accumulate=False, chain=0, sig_sum=None):
+    """uint16 form of ``masks_dense_tc`` (1..16 columns) with the optional fused frame sum:
+    ``sig_sum`` (K,) float32 += sum over the frames of the tile (SumUDF)."""
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    _require_cuda(masks, 'masks')
+    if tile.dtype != torch.uint16 or masks.dtype != torch.float32:
+        raise TypeError('masks_dense_tc_u16 takes uint16 tiles and float32 masks')
+    if tile.dim() != 2 or masks.dim() != 2 or tile.shape[1] != masks.shape[1]:
+        raise ValueError(f'shape mismatch: tile {tuple(tile.shape)} masks {tuple(masks.shape)}')
+    if tile.stride(1) != 1:
+        tile = tile.contiguous()
+    if masks.stride(1) != 1:
+        masks = masks.contiguous()
+    F, K = tile.shape
+    M = masks.shape[0]
+    if out is None:
+        out = torch.zeros((F, M), dtype=torch.float32, device=tile.device)
+        accumulate = False
+    if sig_sum is not None:
+        _require_cuda(sig_sum, 'sig_sum')
+        if sig_sum.dtype != torch.float32 or sig_sum.numel() != K or not sig_sum.is_contiguous():
+            raise ValueError('sig_sum must be a contiguous float32 tensor of sig_size elements')
+    ld_tile = tile.stride(0) if F > 1 else max(K, 1)
+    ld_masks = masks.stride(0) if M > 1 else max(K, 1)
+    ld_out = out.stride(0) if F > 1 else max(M, 1)
+    with torch.cuda.device(tile.device):
+        need = lib.ltb200_masks_dense_tc_u16_workspace(F, K, M, int(sig_sum is not None))
+        ws = _workspace(tile.device, need)
+        check(lib.ltb200_masks_dense_tc_u16(
+            tile.data_ptr(), F, K, ld_tile, masks.data_ptr(), M, ld_masks, out.data_ptr(),
+            ld_out, int(bool(accumulate)), int(chain),
+            sig_sum.data_ptr() if sig_sum is not None else None, ws.data_ptr(), ws.numel(),
+            _stream_ptr(tile.device)))
+    return out
+
+
+def masks_dense_i8(tile, masks, out=None, accumulate=False, sig_sum=None):
+    """Integer fast path (K8, int8 tensor cores): uint16 tile (F, K) x int8 masks (M, K),
+    M <= 16 -> float32 out (F, M) of the exact integer sums; ``sig_sum`` (K,) float32 +=
+    the exact frame sum of the tile (SumUDF)."""
+    lib = get_lib()
+    _require_cuda(tile, 'tile')
+    _require_cuda(masks, 'masks')
+    if tile.dtype != torch.uint16 or masks.dtype != torch.int8:
+        raise TypeError('masks_dense_i8 takes uint16 tiles and int8 masks')
+    if tile.dim() != 2 or masks.dim() != 2 or tile.shape[1] != masks.shape[1]:
+        raise ValueError(f'shape mismatch: tile {tuple(tile.shape)} masks {tuple(masks.shape)}')
+    if tile.stride(1) != 1:
+        tile = tile.contiguous()
+    if masks.stride(1) != 1:
+        masks = masks.contiguous()
+    F, K = tile.shape
+    M = masks.shape[0]
+    if out is None:
+        out = torch.zeros((F, M), dtype=torch.float32, device=tile.device)
+        accumulate = False
+    if sig_sum is not None:
+        _require_cuda(sig_sum, 'sig_sum')
+        if sig_sum.dtype != torch.float32 or sig_sum.numel() != K or not sig_sum.is_contiguous():
+            raise ValueError('sig_sum must be a contiguous float32 tensor of sig_size elements')
+    ld_tile = tile.stride(0) if F > 1 else max(K, 1)
+    ld_masks = masks.stride(0) if M > 1 else max(K, 1)
+    ld_out = out.stride(0) if F > 1 else max(M, 1)
+    with torch.cuda.device(tile.device):
+        need = lib.ltb200_masks_dense_i8_workspace(F, K, M, int(sig_sum is not None))
+        ws = _workspace(tile.device, max(need, 256))
+        check(lib.ltb200_masks_dense_i8(
+            tile.data_ptr(), F, K, ld_tile, masks.data_ptr(), M, ld_masks, out.data_ptr(),
+            ld_out, int(bool(accumulate)), sig_sum.data_ptr() if sig_sum is not None else None,
+            ws.data_ptr(), ws.numel(), _stream_ptr(tile.device)))
+    return out
+
+
 def synth_fill(shape, dtype, seed, device, start=0):
     """Device twin of oracle.synth.dataset: counter-based synthetic data."""
     lib = get_lib()

@@ -16,6 +16,8 @@ differences:
   with one all-gather (nav) / all-reduce (sig) at the end; partial results never
   leave the device before that.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,8 @@ from . import engine
 
 MAX_FUSED_COLUMNS = 24
 MAX_FUSED_COLUMNS_F32 = 32
+# uint16 tiles x integer-valued masks -> exact int8 tensor-core kernel (LTB200_INT8=0: off)
+INT8_PATH = os.environ.get('LTB200_INT8', '1') != '0'
 
 
 def _get_dtype(udfs, dtype, corrections=None):
@@ -73,6 +77,7 @@ class UDFRunner:
         self._fuse = fuse
         self.stats = {'tiles': 0, 'fused_launch_groups': 0, 'unfused_calls': 0}
         self._cat_cache = {}
+        self._int8_cache = {}
         self._slab = None
         self._slab_map = {}
         self._corr = None
@@ -404,7 +409,7 @@ class UDFRunner:
             consts = [g[3] for g in grp]
             if direct is not None:
                 rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
-                engine.masks_dense(flat, rows, out=direct, accumulate=True, sig_sum=ss)
+                self._dense(flat, rows, out=direct, accumulate=True, sig_sum=ss)
                 if any(c is not None for c in consts):
                     direct += torch.cat([c if c is not None else
                                          torch.zeros(g[2].shape[0], device=device)
@@ -413,12 +418,12 @@ class UDFRunner:
                 pu, spec, rows, const = grp[0]
                 view = getattr(pu.results, spec['buffer'])
                 out = self._real_view(view, rows.shape[0])
-                engine.masks_dense(flat, rows, out=out, accumulate=True)
+                self._dense(flat, rows, out=out, accumulate=True)
                 if const is not None:
                     out += const
             else:
                 rows = self._cat_rows([g[2] for g in grp], flat.shape[1], device)
-                res = engine.masks_dense(flat, rows, sig_sum=ss)
+                res = self._dense(flat, rows, sig_sum=ss)
                 c0 = 0
                 for pu, spec, r, const in grp:
                     c = r.shape[0]
@@ -429,6 +434,34 @@ class UDFRunner:
                         out += const
                     c0 += c
             self.stats['fused_launch_groups'] += 1
+
+    def _dense(self, flat, rows, out=None, accumulate=False, sig_sum=None):
+        """One fused pass.  uint16 tiles against integer-valued mask rows (binary virtual
+        detectors, the all-ones row of SumSigUDF, ...) take the exact int8 tensor-core kernel
+        (K8); everything else the float kernels behind ``masks_dense``."""
+        i8 = self._int8_rows(flat, rows)
+        if i8 is not None:
+            self.stats['int8_passes'] = self.stats.get('int8_passes', 0) + 1
+            return engine.masks_dense_i8(flat, i8, out=out, accumulate=accumulate,
+                                         sig_sum=sig_sum)
+        return engine.masks_dense(flat, rows, out=out, accumulate=accumulate, sig_sum=sig_sum)
+
+    def _int8_rows(self, flat, rows):
+        """int8 copy of the mask rows when K8 applies to this tile (cached per row stack)"""
+        F, K = flat.shape
+        M = rows.shape[0]
+        if (flat.dtype != torch.uint16 or not INT8_PATH or not 1 <= M <= 16 or F < 256
+                or K % 8 or not 256 <= K <= 65536 or flat.stride(1) != 1
+                or (F > 1 and flat.stride(0) % 8) or flat.data_ptr() % 16
+                or rows.dtype != torch.float32):
+            return None
+        key = (rows.data_ptr(), tuple(rows.shape))
+        hit = self._int8_cache.get(key)
+        if hit is None:
+            ok = bool(((rows == rows.round()) & (rows.abs() <= 127)).all().item())
+            hit = (rows.to(torch.int8).contiguous() if ok else None, rows)   # keep source alive
+            self._int8_cache[key] = hit
+        return hit[0]
 
     def _cat_rows(self, row_tensors, k, device):
         """stacked mask rows of one fused group, cached across tiles / partitions / runs"""

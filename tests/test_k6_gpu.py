@@ -162,7 +162,7 @@ def test_tc_routing(eng):
     eng.masks_dense(data, wide, sig_sum=sig)
     assert eng.last_kernel() == 6
     np.testing.assert_allclose(sig.cpu().numpy(), data.double().sum(0).cpu().numpy(), rtol=2e-6)
-    # uint16 tiles never go to K6
+    # uint16 tiles with more than 16 columns stay on the FFMA2 kernel
     t16 = eng.synth_fill((F, K), np.uint16, 13, 'cuda')
     eng.set_k1_variant(3)
     try:
@@ -218,3 +218,145 @@ def test_tc_full_size_properties(eng):
     # nor any float32 kernel holds 1e-5 of the value itself: compare on the column scale)
     np.testing.assert_allclose(out[5:6].cpu().numpy(), ref1, rtol=RTOL,
                                atol=RTOL * float(scale.max()) * 0.3)
+
+
+# ---- uint16 tiles on the tensor cores (ltb200_masks_dense_tc_u16) + fused frame sum ----------
+
+def dev_u16(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).cuda().view(torch.uint16)
+
+
+def as_f64(t16):
+    """uint16 CUDA tensor -> float64 (through int16 views: torch has few uint16 kernels)"""
+    return (t16.view(torch.int16).to(torch.int64) & 0xFFFF).double()
+
+
+def full_range_u16(F, K, seed):
+    return (synth.hash_u32(0, F * K, seed) & 0xFFFF).astype(np.uint16).reshape(F, K)
+
+
+@pytest.mark.parametrize('n_masks', [1, 5, 8, 9, 16])
+def test_tcu16_mask_counts(eng, n_masks):
+    # all 16-bit values (hi and lo parts both in use), float weights, a signal size that is
+    # not a multiple of the 64-pixel stage
+    F, K = 600, 4096 + 8 * 5
+    data = full_range_u16(F, K, 31)
+    masks = synth.uniform_f32(0, n_masks * K, 32).reshape(n_masks, K) - 0.25
+    sig = torch.zeros(K, dtype=torch.float32, device='cuda')
+    out = eng.masks_dense_tc_u16(dev_u16(data), dev(masks), sig_sum=sig).cpu().numpy()
+    assert eng.last_kernel() == 6
+    f = data.astype(np.float32)
+    assert_close_rel(out, f64_truth(f, masks), TIGHT, abs_scale(f, masks))
+    assert np.array_equal(sig.cpu().numpy(), data.astype(np.int64).sum(0).astype(np.float32))
+
+
+@pytest.mark.parametrize('F,K', [(1, 256), (8, 256), (255, 264), (257, 4104), (1000, 520),
+                                 (300, 16384), (40960, 1024), (5000, 65536)])
+def test_tcu16_shapes_exact(eng, F, K):
+    # Poisson counts with a few large outliers x small-integer masks: bit-exact results and an
+    # exact fused frame sum, for ragged frame counts, several items per CTA and split-K shapes
+    data = synth.poisson3_u16(0, F * K, 33).reshape(F, K).copy()
+    data[:, ::1013] += 40000
+    masks = (synth.hash_u32(0, 5 * K, 34) % 3).astype(np.float32).reshape(5, K)
+    masks[4] = 1
+    t = dev_u16(data)
+    sig = torch.zeros(K, dtype=torch.float32, device='cuda')
+    out = eng.masks_dense_tc_u16(t, dev(masks), sig_sum=sig)
+    tt = as_f64(t)
+    exact = tt @ dev(masks).double().T          # integers < 2^24: exact in every precision
+    assert exact.max().item() < 2 ** 24
+    assert torch.equal(out.double(), exact)
+    assert torch.equal(sig, tt.sum(0).float())
+    # without the frame sum (no summing warps on the stage barrier)
+    out2 = eng.masks_dense_tc_u16(t, dev(masks))
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize('chain', [0, 1, 2, 3, 5, 8])
+def test_tcu16_chain_lengths(eng, chain):
+    F, K, M = 700, 8192 + 64 * 3 + 8, 11
+    data = full_range_u16(F, K, 35)
+    masks = synth.uniform_f32(0, M * K, 36).reshape(M, K)
+    out = eng.masks_dense_tc_u16(dev_u16(data), dev(masks), chain=chain).cpu().numpy()
+    assert_close_rel(out, f64_truth(data.astype(np.float32), masks), 5e-6)
+
+
+def test_tcu16_strided_accumulate(eng):
+    F, K, M = 530, 1024, 6
+    big = full_range_u16(F, K + 128, 37)
+    masks = synth.uniform_f32(0, M * K, 38).reshape(M, K)
+    tile = dev_u16(big)[:, 64:64 + K]          # row stride K+128, 128 B aligned offset
+    out = torch.full((F, M + 2), 1.5, dtype=torch.float32, device='cuda')
+    view = out[:, 1:1 + M]
+    eng.masks_dense_tc_u16(tile, dev(masks), out=view, accumulate=True)
+    res = out.cpu().numpy()
+    truth = f64_truth(big[:, 64:64 + K].astype(np.float32), masks)
+    assert np.all(res[:, 0] == 1.5) and np.all(res[:, -1] == 1.5)
+    assert_close_rel(res[:, 1:1 + M] - 1.5, truth, TIGHT)
+    eng.masks_dense_tc_u16(tile, dev(masks), out=view, accumulate=False)
+    assert_close_rel(out.cpu().numpy()[:, 1:1 + M], truth, TIGHT)
+
+
+def test_tcu16_frame_sum_beyond_32_bits(eng):
+    # 70 000 frames of 65535 at some pixels: the per-pixel sum (4.6e9) exceeds 32 bits
+    F, K = 70000, 256
+    data = np.zeros((F, K), dtype=np.uint16)
+    data[:, 3] = 65535
+    data[:, 200] = 65535
+    data[::2, 77] = 1
+    sig = torch.zeros(K, dtype=torch.float32, device='cuda')
+    ones = torch.ones((1, K), dtype=torch.float32, device='cuda')
+    out = eng.masks_dense_tc_u16(dev_u16(data), ones, sig_sum=sig).cpu().numpy()
+    assert np.array_equal(out[:, 0], data.astype(np.int64).sum(1).astype(np.float32))
+    want = data.astype(np.int64).sum(0)
+    assert want[3] == 65535 * F > 2 ** 32
+    assert np.array_equal(sig.cpu().numpy(), want.astype(np.float32))
+
+
+def test_tcu16_routing(eng):
+    """ltb200_masks_dense sends uint16 tiles of >= 1024 frames and 7..16 columns to the
+    tensor-core kernel, frame sum included; results are identical to the FFMA2 kernel's.
+    Narrower stacks stay on the FFMA2 kernel (faster there) unless variant 3 forces K6."""
+    F, K = 4096, 128 * 128
+    t = eng.synth_fill((F, K), np.uint16, 39, 'cuda')
+    rings = ring_stack((128, 128), [(8, 16), (20, 28), (32, 40), (44, 52), (4, 60), (0, 9),
+                                    (50, 64), (30, 31)], 64, 64)
+    masks = dev(np.concatenate([np.ones((1, K), np.float32),
+                                rings.reshape(8, -1).astype(np.float32)]))
+    sig = torch.zeros(K, dtype=torch.float32, device='cuda')
+    out = eng.masks_dense(t, masks, sig_sum=sig)
+    assert eng.last_kernel() == 6
+    eng.set_k1_variant(2)
+    try:
+        sig2 = torch.zeros(K, dtype=torch.float32, device='cuda')
+        ref = eng.masks_dense(t, masks, sig_sum=sig2)
+        assert eng.last_kernel() == 3
+    finally:
+        eng.set_k1_variant(0)
+    assert torch.equal(out, ref) and torch.equal(sig, sig2)
+    tt = as_f64(t)
+    assert torch.equal(out.double(), tt @ masks.double().T)
+    assert torch.equal(sig.double(), tt.sum(0))
+    # <= 6 columns and small tiles stay on the FFMA2 kernel
+    eng.masks_dense(t, masks[:5], sig_sum=sig)
+    assert eng.last_kernel() == 3
+    eng.masks_dense(t[:512], masks)
+    assert eng.last_kernel() == 3
+    eng.set_k1_variant(3)
+    try:
+        out5 = eng.masks_dense(t, masks[:5])
+        assert eng.last_kernel() == 6
+    finally:
+        eng.set_k1_variant(0)
+    assert torch.equal(out5, out[:, :5])
+
+
+def test_tcu16_unsupported(eng):
+    from libertem_b200._lib import LTB200Error
+    t = torch.zeros((300, 1024), dtype=torch.uint16, device='cuda')
+    with pytest.raises(LTB200Error):
+        eng.masks_dense_tc_u16(t, torch.ones((17, 1024), device='cuda'))
+    with pytest.raises(LTB200Error):
+        eng.masks_dense_tc_u16(t[:, :128], torch.ones((2, 128), device='cuda'))
+    with pytest.raises(TypeError):
+        eng.masks_dense_tc_u16(t.float(), torch.ones((2, 1024), device='cuda'))

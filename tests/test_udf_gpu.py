@@ -111,6 +111,52 @@ def test_cfg3_small_bit_exact(lt):
         assert np.array_equal(res[2]['intensity'].raw_data, g['intensity'])
 
 
+def test_cfg3_int8_tensor_path(lt):
+    """cfg3 at a tile size that takes the integer fast path (uint16 tiles x binary masks on
+    the int8 tensor cores, K8): SumUDF + SumSigUDF + 4 sparse ring masks in one pass, bit-exact
+    against the oracle's restatement of the reference loops, with and without a ROI, and
+    identical to the float kernels' results"""
+    from libertem_b200 import masks as M, runner as R, engine
+    shape = (48, 64, 128, 128)
+    rings = [(8, 16), (20, 28), (32, 40), (44, 52)]
+    data = synth.dataset(shape, np.uint16, 107)
+    stack = ring_stack((128, 128), rings, 64, 64)
+    facs = [lambda ri=ri, ro=ro: M.ring(64, 64, 128, 128, ro, ri) for ri, ro in rings]
+    src = torch.from_numpy(data.view(np.int16)).cuda().view(torch.uint16)
+
+    def run(roi=None):
+        ds = lt.MemoryDataSet(data=src, num_partitions=2, sig_dims=2)
+        runner = lt.UDFRunner([lt.udf.SumUDF(), lt.udf.SumSigUDF(),
+                               lt.udf.ApplyMasksUDF(mask_factories=facs, use_sparse=True,
+                                                    mask_dtype=np.float32)])
+        res = runner.run_for_dataset(ds, roi=roi).buffers
+        return runner, res
+
+    runner, res = run()
+    assert runner.stats.get('int8_passes', 0) == 2 and runner.stats['unfused_calls'] == 0
+    assert engine.last_kernel() == 8
+    assert np.array_equal(res[0]['intensity'].data, O.sum_udf(data, num_partitions=2))
+    assert np.array_equal(res[1]['intensity'].raw_data, O.sumsig_udf(data, num_partitions=2))
+    assert np.array_equal(res[2]['intensity'].raw_data,
+                          O.apply_masks(data, stack, num_partitions=2, use_sparse=True,
+                                        mask_dtype=np.float32))
+    old = R.INT8_PATH
+    R.INT8_PATH = False
+    try:
+        runner2, res2 = run()
+    finally:
+        R.INT8_PATH = old
+    assert runner2.stats.get('int8_passes', 0) == 0
+    for a, b in zip(res, res2):
+        assert np.array_equal(a['intensity'].raw_data, b['intensity'].raw_data)
+    roi = roi_from_seed(shape[:2], 108)
+    _, res3 = run(roi)
+    assert np.array_equal(res3[0]['intensity'].data, O.sum_udf(data, num_partitions=2, roi=roi))
+    assert np.array_equal(res3[2]['intensity'].raw_data,
+                          O.apply_masks(data, stack, num_partitions=2, use_sparse=True,
+                                        mask_dtype=np.float32, roi=roi))
+
+
 @pytest.mark.parametrize('kind', ['sparse', 'dense'])
 def test_cfg4_small_radial_fourier(lt, kind):
     meta, g = load_golden('cfg4_small_' + kind)
