@@ -437,17 +437,36 @@ class UDFRunner:
 
     def _dense(self, flat, rows, out=None, accumulate=False, sig_sum=None):
         """One fused pass.  uint16 tiles against integer-valued mask rows (binary virtual
-        detectors, the all-ones row of SumSigUDF, ...) take the exact int8 tensor-core kernel
-        (K8); everything else the float kernels behind ``masks_dense``."""
-        i8 = self._int8_rows(flat, rows)
-        if i8 is not None:
-            self.stats['int8_passes'] = self.stats.get('int8_passes', 0) + 1
+        detectors, the all-ones row of SumSigUDF, the CoM coordinate masks, ...) take the exact
+        int8 tensor-core kernel (K8); everything else the float kernels behind
+        ``masks_dense``."""
+        plan = self._int8_rows(flat, rows)
+        if plan is None:
+            return engine.masks_dense(flat, rows, out=out, accumulate=accumulate,
+                                      sig_sum=sig_sum)
+        i8, hi_src, hi_rows = plan
+        self.stats['int8_passes'] = self.stats.get('int8_passes', 0) + 1
+        if hi_src is None:
             return engine.masks_dense_i8(flat, i8, out=out, accumulate=accumulate,
                                          sig_sum=sig_sum)
-        return engine.masks_dense(flat, rows, out=out, accumulate=accumulate, sig_sum=sig_sum)
+        # rows with weights beyond int8 were split into two base-128 digits: recombine
+        res = engine.masks_dense_i8(flat, i8, sig_sum=sig_sum)
+        M = rows.shape[0]
+        val = res[:, :M]
+        val[:, hi_src] += 128.0 * res[:, hi_rows]
+        if out is None:
+            return val.contiguous()
+        if accumulate:
+            out += val
+        else:
+            out.copy_(val)
+        return out
 
     def _int8_rows(self, flat, rows):
-        """int8 copy of the mask rows when K8 applies to this tile (cached per row stack)"""
+        """int8 form of the mask rows when K8 applies to this tile, cached per row stack:
+        ``(int8 rows, None, None)`` when every weight is an integer in [-127, 127], else
+        ``(int8 rows incl. appended high digits, source row indices, their positions)`` for
+        integer weights up to 127 * 129 (m = d0 + 128 d1, both digits int8), else None."""
         F, K = flat.shape
         M = rows.shape[0]
         if (flat.dtype != torch.uint16 or not INT8_PATH or not 1 <= M <= 16 or F < 256
@@ -458,8 +477,19 @@ class UDFRunner:
         key = (rows.data_ptr(), tuple(rows.shape))
         hit = self._int8_cache.get(key)
         if hit is None:
-            ok = bool(((rows == rows.round()) & (rows.abs() <= 127)).all().item())
-            hit = (rows.to(torch.int8).contiguous() if ok else None, rows)   # keep source alive
+            plan = None
+            amax = rows.abs().amax(dim=1)
+            if bool((rows == rows.round()).all().item()) and float(amax.max()) <= 127 * 129:
+                wide = torch.nonzero(amax > 127).reshape(-1)
+                if len(wide) == 0:
+                    plan = (rows.to(torch.int8).contiguous(), None, None)
+                elif M + len(wide) <= 16:
+                    d1 = torch.trunc(rows[wide] / 128.0)
+                    d0 = rows.clone()
+                    d0[wide] -= 128.0 * d1
+                    i8 = torch.cat([d0, d1]).to(torch.int8).contiguous()
+                    plan = (i8, wide, torch.arange(M, M + len(wide), device=rows.device))
+            hit = (plan, rows)                      # keep the source alive (cache key)
             self._int8_cache[key] = hit
         return hit[0]
 

@@ -157,6 +157,33 @@ def test_cfg3_int8_tensor_path(lt):
                                         mask_dtype=np.float32, roi=roi))
 
 
+def test_com_u16_int8_tensor_path(lt):
+    """CoMUDF + binary ApplyMasksUDF + SumSigUDF + SumUDF on a uint16 detector (256x256): the
+    coordinate masks (weights up to 255) are split into two base-128 int8 digits and the whole
+    group runs on the int8 tensor cores; sums below 2^24 are bit-exact, the rest within 1e-5"""
+    from libertem_b200 import masks as M
+    shape = (16, 64, 256, 256)
+    data = synth.dataset(shape, np.uint16, 109)
+    stack = np.stack([M.circular(128, 128, 256, 256, 40), M.ring(128, 128, 256, 256, 90, 60)])
+    src = torch.from_numpy(data.view(np.int16)).cuda().view(torch.uint16)
+    ds = lt.MemoryDataSet(data=src, num_partitions=2, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.CoMUDF.with_params(cy=120, cx=131, r=100), lt.udf.SumSigUDF(),
+                           lt.udf.ApplyMasksUDF(mask_factories=lambda: stack.astype(np.float32)),
+                           lt.udf.SumUDF()])
+    res = runner.run_for_dataset(ds).buffers
+    assert runner.stats.get('int8_passes', 0) == 2 and runner.stats['unfused_calls'] == 0
+    com = O.com_udf(data, cy=120, cx=131, r=100, num_partitions=2)
+    raw = runner._udfs[0].results.get_buffer('raw_mask_result').raw_data
+    assert np.array_equal(raw[:, 0], com['raw_mask_result'][:, 0])      # m00 < 2^24: exact
+    np.testing.assert_allclose(raw, com['raw_mask_result'], rtol=1e-6)
+    np.testing.assert_allclose(res[0]['raw_com'].raw_data, com['raw_com'], rtol=RTOL)
+    np.testing.assert_allclose(res[0]['field'].raw_data, com['field'], rtol=RTOL, atol=2e-4)
+    assert np.array_equal(res[1]['intensity'].raw_data, O.sumsig_udf(data, num_partitions=2))
+    assert np.array_equal(res[2]['intensity'].raw_data,
+                          O.apply_masks(data, stack.astype(np.float32), num_partitions=2))
+    assert np.array_equal(res[3]['intensity'].data, O.sum_udf(data, num_partitions=2))
+
+
 @pytest.mark.parametrize('kind', ['sparse', 'dense'])
 def test_cfg4_small_radial_fourier(lt, kind):
     meta, g = load_golden('cfg4_small_' + kind)
