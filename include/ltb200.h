@@ -218,6 +218,27 @@ LTB_API int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_t s
                                   float* out, int64_t ld_out, int accumulate, int chain,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Quad / banded plan (the default for 16-byte aligned frame rows): entry_px lists QUADS -- the
+ * first pixel (a multiple of 4) of 4 consecutive pixels that are gathered with one 16-byte
+ * copy per frame; the weight table has 4 entries per quad, zero for pixels outside the ring.
+ * The n_groups = n_bands x n_rings groups are (pixel band, ring) pairs, band-major (group
+ * b * n_rings + r = the quads of ring r inside band b of the flattened signal; n_bands >= 1).
+ * Work is scheduled band by band over a few frame blocks at a time, so the 128-byte lines that
+ * several rings share are fetched from DRAM once and served from L2 (a ring crosses an image
+ * row in runs of ~18 pixels; ring-by-ring gathering moves 2.2-2.7x the bytes it uses).  For
+ * n_bands > 1 the band partial sums go to `workspace` (ltb200_group_masks_tc_workspace bytes)
+ * and are added in fixed band order into out (n_frames, >= n_rings * n_pairs * 2). */
+LTB_API size_t ltb200_group_masks_tc_workspace(int64_t n_frames, int n_groups, int n_pairs,
+                                               int n_bands);
+LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, int64_t sig_size,
+                                         int64_t ld_tile, const int32_t* entry_px,
+                                         const float* table_split,
+                                         const int32_t* group_off_host,
+                                         const int32_t* group_off_dev, int n_groups, int n_pairs,
+                                         int n_bands, float* out, int64_t ld_out, int accumulate,
+                                         int chain, void* workspace, size_t workspace_bytes,
+                                         void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Synthetic data (twin of oracle/synth.py): fills dst[0..count) with value(start + i).
  *   LTB_F32: uniform [0,1) (24-bit);  LTB_U16: Poisson(3) counts.

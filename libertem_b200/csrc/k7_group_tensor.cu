@@ -40,11 +40,13 @@ namespace ltb {
 
 constexpr int K7_FB = 128;            // frames per item (TMEM lanes)
 constexpr int K7_KT = 64;             // ring entries per stage (2 sub-tiles of 32)
-constexpr int K7_STAGES = 3;
+constexpr int K7_DSTAGES = 3;          // gathered data stages (ring size; p.dstages in use)
+constexpr int K7_TSTAGES = 3;          // weight-table stages (ring size; p.tstages in use)
+constexpr int K7_QLEN = 8;             // items queued from the gather producers to the table warp
 constexpr int K7_AS = 4;              // TMEM operand ring (sub-tiles)
 constexpr int K7_PWARPS = 4;
 constexpr int K7_CWARPS = 8;
-constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + 1) * 32;
+constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + 2) * 32;   // + MMA warp + table warp
 constexpr uint32_t K7_SUB_BYTES = K7_FB * 32 * 4;          // 16 KiB per sub-tile
 constexpr uint32_t K7_DATA_BYTES = 2 * K7_SUB_BYTES;
 constexpr int K7_TMEM_COLS = 512;
@@ -64,7 +66,25 @@ struct K7Params {
     int* counter;
     int chain;                     // sub-tiles per TMEM accumulation chain
     int rgroup;                    // adjacent rings scheduled back to back (L2 sharing)
+    int fbgroup;                   // > 0: banded plan, frame blocks per scheduling group
+    int n_bands;                   // banded plan: groups = n_bands x n_rings, band-major
+    int prefetch;                  // banded plan: dense L2 prefetch of the next band
+    int quad;                      // entry_px lists QUADS (4 consecutive, 16-byte aligned pixels)
+    int dstages;                   // data stages in use (<= K7_DSTAGES)
+    int tstages;                   // table stages in use (<= K7_TSTAGES)
+    int late_release;              // converters free a data stage after converting it (A/B)
+    int64_t sig_size;
 };
+
+constexpr int K7_PF_PX = 256;         // pixels per L2-prefetch box (x 128 frames = 128 KiB)
+
+// DRAM -> L2 only: the gathers that follow hit L2 (UTMAPF in SASS)
+__device__ __forceinline__ void k7_tma_prefetch_2d(const CUtensorMap* map, int32_t c0,
+                                                   int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 
 // Item order: ring groups of `rgroup` adjacent rings outermost, frame blocks next, the rings of
 // the group innermost.  CTAs that fetch consecutive items therefore gather ADJACENT rings of the
@@ -73,6 +93,23 @@ struct K7Params {
 // weight-table slices in use at any time stay at rgroup x 4 MB.
 __device__ __forceinline__ void k7_decode_item(const K7Params& p, int64_t item, int& g,
                                                int64_t& fb) {
+    if (p.fbgroup > 0) {
+        // banded plan (groups = (pixel band, ring), band-major): `fbgroup` frame blocks
+        // outermost, groups next, the frame blocks of the group innermost.  All CTAs then work
+        // on the SAME pixel band of the same few frame blocks at the same time: a 128-byte line
+        // of a frame row is fetched from DRAM by the first ring that touches it and served by
+        // L2 to the other rings crossing it, and the weight-table slices of the band in use
+        // stay L2-resident.
+        const int64_t per = (int64_t)p.fbgroup * p.n_groups;
+        const int64_t j = item / per;
+        const int64_t rem = item - j * per;
+        int64_t f_here = p.n_fb - j * p.fbgroup;
+        if (f_here > p.fbgroup) f_here = p.fbgroup;
+        const int64_t gg = rem / f_here;
+        g = (int)gg;
+        fb = j * p.fbgroup + (rem - gg * f_here);
+        return;
+    }
     const int64_t per_group = p.n_fb * p.rgroup;
     const int64_t j = item / per_group;
     const int64_t rem = item - j * per_group;
@@ -166,22 +203,38 @@ __device__ __forceinline__ void k7_cp_async_4(uint32_t smem_dst, const void* gsr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc)
                  : "memory");
 }
+__device__ __forceinline__ void k7_cp_async_16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc)
+                 : "memory");
+}
 __device__ __forceinline__ void k7_cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
 
+// Shared memory: a ring of K7_DSTAGES gathered data stages and a separate, shorter ring of
+// K7_TSTAGES weight-table stages.  The gathers are latency-bound (every stage is thousands of
+// small copies through L1), so what matters is the number of data stages in flight; the table
+// slices arrive by TMA from L2 and need no depth.
 template <int N>
 struct K7Smem {
     static constexpr uint32_t TABLE_BYTES = 2u * N * 128u;                 // two [N x 32] slices
-    static constexpr uint32_t STAGE_BYTES = K7_DATA_BYTES + TABLE_BYTES;
-    static constexpr uint32_t BAR_OFF = K7_STAGES * STAGE_BYTES;
-    static constexpr uint32_t TOTAL = BAR_OFF + 512 + 1024;                // + alignment slack
+    static constexpr uint32_t TABLE_OFF = K7_DSTAGES * K7_DATA_BYTES;
+    static constexpr uint32_t BAR_OFF = TABLE_OFF + K7_TSTAGES * TABLE_BYTES;
+    static constexpr uint32_t TOTAL = BAR_OFF + 1024 + 1024;               // + alignment slack
+};
+
+struct K7QItem {
+    int item;      // < 0: no more work
+    int e0;        // first entry of the item's group
+    int nchunks;
+    int pad;
 };
 
 template <int N>
 __global__ void __launch_bounds__(K7_THREADS, 1)
-k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Params p) {
+k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
+                       const __grid_constant__ CUtensorMap tm_tile, const K7Params p) {
     using SM = K7Smem<N>;
     constexpr int NHALF = N / 2;          // accumulator columns drained per converter warp
     constexpr int NQ = N / 4;             // real columns per half
@@ -192,29 +245,45 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);   // [STAGES]
-    uint64_t* free_bar = full_bar + K7_STAGES;                              // [STAGES]
-    uint64_t* a_full = free_bar + K7_STAGES;                                // [AS]
+    uint64_t* data_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);  // [DSTAGES]
+    uint64_t* data_free = data_full + K7_DSTAGES;                           // [DSTAGES]
+    uint64_t* tab_full = data_free + K7_DSTAGES;                            // [TSTAGES]
+    uint64_t* tab_free = tab_full + K7_TSTAGES;                             // [TSTAGES]
+    uint64_t* a_full = tab_free + K7_TSTAGES;                               // [AS]
     uint64_t* mma_done = a_full + K7_AS;                                    // [AS]
-    K7Meta* meta = reinterpret_cast<K7Meta*>(mma_done + K7_AS);             // [STAGES]
-    int* cur_item = reinterpret_cast<int*>(meta + K7_STAGES);
+    uint64_t* q_full = mma_done + K7_AS;                                    // [QLEN]
+    uint64_t* q_free = q_full + K7_QLEN;                                    // [QLEN]
+    K7Meta* meta = reinterpret_cast<K7Meta*>(q_free + K7_QLEN);             // [DSTAGES]
+    K7Meta* tmeta = meta + K7_DSTAGES;                                      // [TSTAGES]
+    K7QItem* queue = reinterpret_cast<K7QItem*>(tmeta + K7_TSTAGES);        // [QLEN]
+    int* cur_item = reinterpret_cast<int*>(queue + K7_QLEN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cur_item + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    constexpr int MMA_WARP = K7_PWARPS + K7_CWARPS;
+    constexpr int TABLE_WARP = MMA_WARP + 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < K7_STAGES; s++) {
-            mbar_init(&full_bar[s], 1 + K7_PWARPS * 32);
-            mbar_init(&free_bar[s], K7_CWARPS + 1);
+        for (int s = 0; s < K7_DSTAGES; s++) {
+            mbar_init(&data_full[s], 1 + K7_PWARPS * 32);
+            mbar_init(&data_free[s], K7_CWARPS);
+        }
+        for (int s = 0; s < K7_TSTAGES; s++) {
+            mbar_init(&tab_full[s], 1);
+            mbar_init(&tab_free[s], 1);
         }
         for (int s = 0; s < K7_AS; s++) {
             mbar_init(&a_full[s], K7_CWARPS);
             mbar_init(&mma_done[s], 1);
         }
+        for (int s = 0; s < K7_QLEN; s++) {
+            mbar_init(&q_full[s], 1);
+            mbar_init(&q_free[s], 1);
+        }
         fence_mbar_init();
     }
-    if (warp == K7_PWARPS + K7_CWARPS) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "n"(K7_TMEM_COLS)
@@ -228,14 +297,12 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
     const int chain = p.chain;
 
     if (warp < K7_PWARPS) {
-        // ===== producers =====
-        const int pt = threadIdx.x;                       // 0..255
+        // ===== gather producers =====
+        const int pt = threadIdx.x;                       // 0 .. 32 * K7_PWARPS - 1
         const int el = pt & 31;                           // entry inside the sub-tile
         const int sub = (pt >> 5) & 1;                    // sub-tile of the stage
-        constexpr int FPT = K7_FB / (K7_PWARPS / 2);      // frames per thread (32)
+        constexpr int FPT = K7_FB / (K7_PWARPS / 2);      // frames per thread
         const int fq = pt >> 6;                           // rows fq*FPT .. +FPT-1
-        const uint64_t pol_keep = l2_policy_evict_last();
-        if (pt == 0) prefetch_tmap(&tm_table);
         // 128-byte swizzle: 16-byte chunk (el / 4) of row r lands at chunk ^ (r & 7).  The rows
         // of a thread start at a multiple of 8, so the offset pattern repeats every 8 rows:
         // eight precomputed offsets + an immediate per copy.
@@ -244,7 +311,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
         for (int c = 0; c < 8; c++)
             sw[c] = (uint32_t)sub * K7_SUB_BYTES + (uint32_t)(fq * FPT + c) * 128u +
                     ((((uint32_t)(el >> 2)) ^ (uint32_t)c) << 4) + (uint32_t)(el & 3) * 4u;
-        uint32_t it = 0;
+        // quad plan: 16 quads per stage; thread = (quad qd of sub-tile qsub, rows rg + 8 j)
+        const int qd = pt & 7, qsub = (pt >> 3) & 1, rg = pt >> 4;
+        uint32_t it = 0, qn = 0;
+        const uint32_t nd = (uint32_t)p.dstages;
         while (true) {
             if (pt == 0) *cur_item = atomicAdd(p.counter, 1);
             named_bar_sync(2, K7_PWARPS * 32);
@@ -256,41 +326,91 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
             if (!done) {
                 int g;
                 k7_decode_item(p, item, g, fb);
+                if (p.prefetch && pt == 0) {
+                    // Optional dense DRAM -> L2 prefetch of the NEXT pixel band of this frame
+                    // block (LTB200_K7_PF=1; measured slower: it competes with the gathers)
+                    const int n_rings = p.n_groups / p.n_bands;
+                    int nb = g / n_rings + 1;
+                    const int r = g % n_rings;
+                    int64_t pfb = fb;
+                    if (nb == p.n_bands) {
+                        nb = 0;
+                        pfb = fb + p.fbgroup;
+                    }
+                    if (pfb < p.n_fb) {
+                        const int64_t b0 = (p.sig_size * nb) / p.n_bands;
+                        const int64_t b1 = (p.sig_size * (nb + 1)) / p.n_bands;
+                        for (int64_t x = b0 + (int64_t)r * K7_PF_PX; x < b1;
+                             x += (int64_t)n_rings * K7_PF_PX)
+                            k7_tma_prefetch_2d(&tm_tile, (int32_t)x, (int32_t)(pfb * K7_FB));
+                    }
+                }
                 e0 = p.group_off[g];
                 nchunks = (p.group_off[g + 1] - e0) / K7_KT;
                 if (nchunks == 0) continue;   // empty ring: nothing to add
             }
+            if (pt == 0) {
+                // hand the item to the weight-table warp
+                const int q = qn % K7_QLEN;
+                mbar_wait(&q_free[q], ((qn / K7_QLEN) & 1) ^ 1);
+                queue[q] = K7QItem{done ? -1 : item, e0, nchunks, 0};
+                mbar_arrive(&q_full[q]);
+            }
+            qn++;
             const int64_t f_first = fb * K7_FB + fq * FPT;
             const bool ragged = fb * K7_FB + K7_FB > p.n_frames;
             // the pixel index of this thread's entry is loaded one stage ahead (an L2 round
             // trip that would otherwise sit between the stage becoming free and its copies)
-            int px_next = done ? 0 : p.entry_px[e0 + sub * 32 + el];
+            int px_next = done ? 0
+                               : (p.quad ? p.entry_px[(e0 >> 2) + qsub * 8 + qd]
+                                         : p.entry_px[e0 + sub * 32 + el]);
             for (int c = 0; c < nchunks; c++, it++) {
-                const int stage = it % K7_STAGES;
-                mbar_wait(&free_bar[stage], ((it / K7_STAGES) & 1) ^ 1);
-                uint8_t* dst = smem + (size_t)stage * SM::STAGE_BYTES;
+                const int stage = (int)(it % nd);
+                mbar_wait(&data_free[stage], ((it / nd) & 1) ^ 1);
+                uint8_t* dst = smem + (size_t)stage * K7_DATA_BYTES;
                 if (done) {
-                    // sentinel stage: tells the consumers to stop (all arrivals, no data)
+                    // sentinel stage: tells the converters to stop (all arrivals, no data)
                     if (pt == 0) {
                         meta[stage] = K7Meta{-1, 0, 0, 0};
-                        mbar_arrive(&full_bar[stage]);
+                        mbar_arrive(&data_full[stage]);
                     }
-                    mbar_arrive(&full_bar[stage]);
+                    mbar_arrive(&data_full[stage]);
                     continue;
                 }
                 const int ebase = e0 + c * K7_KT;
                 if (pt == 0) {
                     meta[stage] = K7Meta{item, c, nchunks, 0};
-                    mbar_arrive_expect_tx(&full_bar[stage], SM::TABLE_BYTES);
-                    tma_load_2d(dst + K7_DATA_BYTES, &tm_table, ebase, 0, &full_bar[stage],
-                                pol_keep);
-                    tma_load_2d(dst + K7_DATA_BYTES + N * 128, &tm_table, ebase + 32, 0,
-                                &full_bar[stage], pol_keep);
+                    mbar_arrive(&data_full[stage]);
                 }
                 const int px = px_next;
-                if (c + 1 < nchunks) px_next = p.entry_px[ebase + K7_KT + sub * 32 + el];
+                if (c + 1 < nchunks)
+                    px_next = p.quad ? p.entry_px[((ebase + K7_KT) >> 2) + qsub * 8 + qd]
+                                     : p.entry_px[ebase + K7_KT + sub * 32 + el];
                 const uint32_t sdst = smem_u32(dst);
-                if (!ragged) {
+                if (p.quad) {
+                    // one 16-byte copy moves 4 consecutive pixels of a frame into one swizzled
+                    // chunk: a quarter of the copy instructions and of the shared-memory write
+                    // wavefronts of the 4-byte gather
+                    const uint32_t d0 = sdst + (uint32_t)qsub * K7_SUB_BYTES + (uint32_t)rg * 128u +
+                                        ((uint32_t)(qd ^ rg) << 4);
+                    const int64_t fr0 = fb * K7_FB + rg;
+                    if (!ragged) {
+                        const float* src = p.tile + px + fr0 * p.ld_tile;
+                        const int64_t step = 8 * p.ld_tile;
+#pragma unroll 4
+                        for (int j = 0; j < K7_FB / 8; j++) {
+                            k7_cp_async_16(d0 + (uint32_t)j * 1024u, src);
+                            src += step;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int j = 0; j < K7_FB / 8; j++) {
+                            int64_t fr = fr0 + 8 * j;
+                            if (fr >= p.n_frames) fr = p.n_frames - 1;
+                            k7_cp_async_16(d0 + (uint32_t)j * 1024u, p.tile + px + fr * p.ld_tile);
+                        }
+                    }
+                } else if (!ragged) {
                     const float* src = p.tile + px + f_first * p.ld_tile;
 #pragma unroll 1
                     for (int f8 = 0; f8 < FPT / 8; f8++) {
@@ -314,25 +434,57 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                         }
                     }
                 }
-                k7_cp_async_mbar_arrive_noinc(&full_bar[stage]);
+                k7_cp_async_mbar_arrive_noinc(&data_full[stage]);
             }
             if (done) break;
         }
-    } else if (warp == K7_PWARPS + K7_CWARPS) {
+    } else if (warp == TABLE_WARP) {
+        // ===== weight-table producer: TMA of the [N x 32] table slices of every stage =====
+        if (lane == 0) {
+            prefetch_tmap(&tm_table);
+            const uint64_t pol_keep = l2_policy_evict_last();
+            uint32_t tit = 0;
+            const uint32_t nt = (uint32_t)p.tstages;
+            for (uint32_t qn = 0;; qn++) {
+                const int q = qn % K7_QLEN;
+                mbar_wait(&q_full[q], (qn / K7_QLEN) & 1);
+                const K7QItem qi = queue[q];
+                mbar_arrive(&q_free[q]);
+                const int nch = qi.item < 0 ? 1 : qi.nchunks;
+                for (int c = 0; c < nch; c++, tit++) {
+                    const int ts = (int)(tit % nt);
+                    mbar_wait(&tab_free[ts], ((tit / nt) & 1) ^ 1);
+                    uint8_t* dst = smem + SM::TABLE_OFF + (size_t)ts * SM::TABLE_BYTES;
+                    if (qi.item < 0) {
+                        tmeta[ts] = K7Meta{-1, 0, 0, 0};
+                        mbar_arrive(&tab_full[ts]);
+                        continue;
+                    }
+                    const int ebase = qi.e0 + c * K7_KT;
+                    tmeta[ts] = K7Meta{qi.item, c, qi.nchunks, 0};
+                    mbar_arrive_expect_tx(&tab_full[ts], SM::TABLE_BYTES);
+                    tma_load_2d(dst, &tm_table, ebase, 0, &tab_full[ts], pol_keep);
+                    tma_load_2d(dst + N * 128, &tm_table, ebase + 32, 0, &tab_full[ts], pol_keep);
+                }
+                if (qi.item < 0) break;
+            }
+        }
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
-        uint32_t it = 0;       // stages
+        uint32_t tit = 0;      // table stages
         uint32_t st = 0;       // sub-tiles (TMEM slots)
         int in_chain = 0, cbuf = 0;
-        for (;; it++) {
-            const int stage = it % K7_STAGES;
-            mbar_wait(&full_bar[stage], (it / K7_STAGES) & 1);
-            const K7Meta m = meta[stage];
+        const uint32_t nt = (uint32_t)p.tstages;
+        for (;; tit++) {
+            const int ts = (int)(tit % nt);
+            mbar_wait(&tab_full[ts], (tit / nt) & 1);
+            const K7Meta m = tmeta[ts];
             if (m.item < 0) break;
             if (m.chunk == 0) {
                 in_chain = 0;
                 cbuf = 0;
             }
-            const uint32_t tbl = smem_u32(smem + (size_t)stage * SM::STAGE_BYTES + K7_DATA_BYTES);
+            const uint32_t tbl = smem_u32(smem + SM::TABLE_OFF + (size_t)ts * SM::TABLE_BYTES);
 #pragma unroll
             for (int s = 0; s < 2; s++, st++) {
                 const int as = st % K7_AS;
@@ -349,7 +501,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                         k7_mma_tf32_ts(d0, a0 + 32 + kk * 8, bdesc, IDESC, 1u);
                     }
                     k7_commit(&mma_done[as]);
-                    if (s == 1) k7_commit(&free_bar[stage]);
+                    if (s == 1) k7_commit(&tab_free[ts]);
                 }
                 __syncwarp();
                 if (++in_chain == chain) {
@@ -392,9 +544,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
             next_chain++;
         };
 
+        const uint32_t nd = (uint32_t)p.dstages;
         for (;; it++) {
-            const int stage = it % K7_STAGES;
-            mbar_wait(&full_bar[stage], (it / K7_STAGES) & 1);
+            const int stage = (int)(it % nd);
+            mbar_wait(&data_full[stage], (it / nd) & 1);
             const K7Meta m = meta[stage];
             if (m.item < 0) break;
             if (m.chunk == 0) {
@@ -404,7 +557,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                 n_sub = 2 * m.nchunks;
                 next_chain = 0;
             }
-            const uint8_t* dbase = smem + (size_t)stage * SM::STAGE_BYTES + row_off;
+            const uint8_t* dbase = smem + (size_t)stage * K7_DATA_BYTES + row_off;
             float4 x[2][4];
 #pragma unroll
             for (int s = 0; s < 2; s++)
@@ -412,6 +565,16 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                 for (int j = 0; j < 4; j++)
                     x[s][j] = *reinterpret_cast<const float4*>(
                         dbase + s * K7_SUB_BYTES + (((uint32_t)(hh * 4 + j) ^ swz) << 4));
+            // the stage is in registers (the empty asm pins the loaded values in front of the
+            // arrive): hand it back to the gather producers right away
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    asm volatile("" : "+f"(x[s][j].x), "+f"(x[s][j].y), "+f"(x[s][j].z),
+                                      "+f"(x[s][j].w)::"memory");
+            __syncwarp();
+            if (lane == 0 && !p.late_release) mbar_arrive(&data_free[stage]);
 #pragma unroll
             for (int s = 0; s < 2; s++, st++, i++) {
                 const int as = st % K7_AS;
@@ -448,7 +611,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&a_full[as]);
-                    if (s == 1) mbar_arrive(&free_bar[stage]);
+                    if (s == 1 && p.late_release) mbar_arrive(&data_free[stage]);
                 }
             }
             if (m.chunk == m.nchunks - 1) {
@@ -475,7 +638,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
 
     k7_fence_before();
     __syncthreads();
-    if (warp == K7_PWARPS + K7_CWARPS) {
+    if (warp == MMA_WARP) {
         k7_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "n"(K7_TMEM_COLS)
@@ -484,7 +647,8 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table, const K7Par
 }
 
 template <int N>
-static int k7_launch(const CUtensorMap& tm, const K7Params& p, int grid, cudaStream_t st) {
+static int k7_launch(const CUtensorMap& tm, const CUtensorMap& tmt, const K7Params& p, int grid,
+                     cudaStream_t st) {
     auto kern = k7_group_tensor_kernel<N>;
     const size_t smem = K7Smem<N>::TOTAL;
     int dev = 0;
@@ -495,7 +659,7 @@ static int k7_launch(const CUtensorMap& tm, const K7Params& p, int grid, cudaStr
                                             (int)smem));
         configured_dev = dev;
     }
-    kern<<<grid, K7_THREADS, smem, st>>>(tm, p);
+    kern<<<grid, K7_THREADS, smem, st>>>(tm, tmt, p);
     count_launch();
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
@@ -515,20 +679,55 @@ extern "C" int ltb200_group_masks_tc_columns(int n_pairs) {
     return 112;
 }
 
-extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_t sig_size,
-                                     int64_t ld_tile, const int32_t* entry_px,
-                                     const float* table_split, const int32_t* group_off_host,
-                                     const int32_t* group_off_dev, int n_groups, int n_pairs,
-                                     float* out, int64_t ld_out, int accumulate, int chain,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+// out[f, ring, c] (+)= sum over the non-empty bands of part[f, band * n_rings + ring, c]
+// (fixed order: deterministic)
+__global__ void k7_band_reduce_kernel(const float* __restrict__ part, const int32_t* group_off,
+                                      int64_t n_frames, int n_rings, int n_bands, int cols,
+                                      float* __restrict__ out, int64_t ld_out, int accumulate) {
+    const int64_t row = (int64_t)n_rings * cols;
+    const int64_t total = n_frames * row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / row;
+        const int rc = (int)(i - f * row);
+        const int ring = rc / cols;
+        const float* src = part + f * row * n_bands + rc;
+        float s = 0.f;
+        for (int b = 0; b < n_bands; b++) {
+            const int g = b * n_rings + ring;
+            if (group_off[g + 1] > group_off[g]) s += src[(int64_t)b * row];
+        }
+        float* o = out + f * ld_out + rc;
+        *o = accumulate ? (*o + s) : s;
+    }
+}
+
+extern "C" size_t ltb200_group_masks_tc_workspace(int64_t n_frames, int n_groups, int n_pairs,
+                                                  int n_bands) {
+    if (n_bands <= 1) return 256;
+    return 256 + (size_t)n_frames * (size_t)n_groups * (size_t)n_pairs * 2 * sizeof(float);
+}
+
+static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
+                  const int32_t* entry_px, const float* table_split,
+                  const int32_t* group_off_host, const int32_t* group_off_dev, int n_groups,
+                  int n_pairs, int n_bands, int quad_plan, float* out, int64_t ld_out,
+                  int accumulate, int chain, void* workspace, size_t workspace_bytes,
+                  void* stream) {
     LTB_REQUIRE(n_frames >= 0 && sig_size > 0 && n_groups > 0, "group_masks_tc: bad sizes");
+    LTB_REQUIRE(n_bands >= 1 && n_groups % n_bands == 0,
+                "group_masks_tc: n_groups must be n_bands x rings");
     const int n = ltb200_group_masks_tc_columns(n_pairs);
     LTB_REQUIRE(n > 0, "group_masks_tc: 1..28 complex columns per group, got %d", n_pairs);
     if (n_frames == 0) return LTB_OK;
     LTB_REQUIRE(tile && entry_px && table_split && group_off_host && group_off_dev && out,
                 "group_masks_tc: NULL pointer");
-    LTB_REQUIRE(workspace != nullptr && workspace_bytes >= 256, "group_masks_tc: workspace");
-    LTB_REQUIRE(ld_out >= (int64_t)n_groups * n_pairs * 2, "group_masks_tc: ld_out too small");
+    const size_t need = ltb200_group_masks_tc_workspace(n_frames, n_groups, n_pairs, n_bands);
+    LTB_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+                "group_masks_tc: workspace of %zu B required, %zu B given", need,
+                workspace_bytes);
+    const int n_rings = n_groups / n_bands;
+    LTB_REQUIRE(ld_out >= (int64_t)n_rings * n_pairs * 2, "group_masks_tc: ld_out too small");
     LTB_REQUIRE((uintptr_t)table_split % 16 == 0, "group_masks_tc: table must be 16 B aligned");
     LTB_REQUIRE((uintptr_t)tile % 4 == 0, "group_masks_tc: tile must be 4 B aligned");
     const int64_t n_entries = group_off_host[n_groups];
@@ -542,6 +741,10 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
                                (uint64_t)n_entries, (uint64_t)n, (uint64_t)n_entries * 4, 32,
                                (uint32_t)n, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
+    const bool banded = n_bands > 1;     // band partial sums + reduction
+    const bool quad = quad_plan != 0;    // entry_px lists quads (16-byte gathers)
+    LTB_REQUIRE(quad || !banded, "group_masks_tc: banded plans are quad plans");
+    float* part = (float*)((uint8_t*)workspace + 256);
     K7Params p;
     p.tile = tile;
     p.n_frames = n_frames;
@@ -550,9 +753,9 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
     p.group_off = group_off_dev;
     p.n_groups = n_groups;
     p.n_pairs = n_pairs;
-    p.out = out;
-    p.ld_out = ld_out;
-    p.accumulate = accumulate;
+    p.out = banded ? part : out;
+    p.ld_out = banded ? (int64_t)n_groups * n_pairs * 2 : ld_out;
+    p.accumulate = banded ? 0 : accumulate;
     p.n_fb = (n_frames + K7_FB - 1) / K7_FB;
     p.n_items = p.n_fb * n_groups;
     p.counter = (int*)workspace;
@@ -564,9 +767,42 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
     if (const char* e = getenv("LTB200_K7_RGROUP"))
         if (atoi(e) > 0) p.rgroup = atoi(e);
     if (p.rgroup > n_groups) p.rgroup = n_groups;
+    p.fbgroup = 0;
+    p.quad = quad ? 1 : 0;
+    // pipeline depths in use (rings: K7_DSTAGES data, K7_TSTAGES table stages)
+    p.dstages = K7_DSTAGES;
+    p.tstages = K7_TSTAGES;
+    if (const char* e = getenv("LTB200_K7_DS"))
+        if (atoi(e) >= 1 && atoi(e) <= K7_DSTAGES) p.dstages = atoi(e);
+    p.late_release = 0;
+    if (const char* e = getenv("LTB200_K7_LATE")) p.late_release = atoi(e);
+    if (const char* e = getenv("LTB200_K7_TS"))
+        if (atoi(e) >= 1 && atoi(e) <= K7_TSTAGES) p.tstages = atoi(e);
+    if (quad)
+        LTB_REQUIRE((uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0,
+                    "group_masks_tc: the quad plan needs 16-byte aligned frame rows");
+    p.n_bands = n_bands;
+    p.prefetch = 0;
+    p.sig_size = sig_size;
+    CUtensorMap tmt = tm;
+    if (quad) {
+        p.fbgroup = 8;
+        if (const char* e = getenv("LTB200_K7_FBG"))
+            if (atoi(e) > 0) p.fbgroup = atoi(e);
+        int want_pf = 0;   // measured: the dense prefetch competes with the gathers (slower)
+        if (const char* e = getenv("LTB200_K7_PF")) want_pf = atoi(e);
+        if (want_pf && (uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0 && sig_size >= K7_PF_PX &&
+            sig_size < (1ll << 31)) {
+            rc = encode_tmap_2d_sw(&tmt, tile, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)sig_size,
+                                   (uint64_t)n_frames, (uint64_t)ld_tile * 4, K7_PF_PX, K7_FB,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc != LTB_OK) return rc;
+            p.prefetch = 1;
+        }
+    }
     LTB_REQUIRE(p.n_items < (1ll << 31), "group_masks_tc: too many work items");
     LTB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 4, st));
-    if (!accumulate) {
+    if (!accumulate && !banded) {
         // rings without entries leave their columns untouched: define them as zero
         LTB_CUDA_CHECK(cudaMemset2DAsync(out, ld_out * sizeof(float), 0,
                                          (size_t)n_groups * n_pairs * 2 * sizeof(float), n_frames,
@@ -575,9 +811,45 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
     int grid = sm_count();
     if (p.n_items < grid) grid = (int)p.n_items;
     switch (n) {
-        case 16: return k7_launch<16>(tm, p, grid, st);
-        case 32: return k7_launch<32>(tm, p, grid, st);
-        case 64: return k7_launch<64>(tm, p, grid, st);
-        default: return k7_launch<112>(tm, p, grid, st);
+        case 16: rc = k7_launch<16>(tm, tmt, p, grid, st); break;
+        case 32: rc = k7_launch<32>(tm, tmt, p, grid, st); break;
+        case 64: rc = k7_launch<64>(tm, tmt, p, grid, st); break;
+        default: rc = k7_launch<112>(tm, tmt, p, grid, st); break;
     }
+    if (rc != LTB_OK) return rc;
+    if (banded) {
+        const int64_t total = n_frames * (int64_t)n_rings * n_pairs * 2;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        k7_band_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, group_off_dev, n_frames, n_rings,
+                                                           n_bands, n_pairs * 2, out, ld_out,
+                                                           accumulate);
+        count_launch();
+        LTB_CUDA_CHECK(cudaGetLastError());
+    }
+    return LTB_OK;
+}
+
+extern "C" int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, int64_t sig_size,
+                                            int64_t ld_tile, const int32_t* entry_px,
+                                            const float* table_split,
+                                            const int32_t* group_off_host,
+                                            const int32_t* group_off_dev, int n_groups,
+                                            int n_pairs, int n_bands, float* out, int64_t ld_out,
+                                            int accumulate, int chain, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    return k7_run(tile, n_frames, sig_size, ld_tile, entry_px, table_split, group_off_host,
+                  group_off_dev, n_groups, n_pairs, n_bands, 1, out, ld_out, accumulate, chain,
+                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_t sig_size,
+                                     int64_t ld_tile, const int32_t* entry_px,
+                                     const float* table_split, const int32_t* group_off_host,
+                                     const int32_t* group_off_dev, int n_groups, int n_pairs,
+                                     float* out, int64_t ld_out, int accumulate, int chain,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    return k7_run(tile, n_frames, sig_size, ld_tile, entry_px, table_split, group_off_host,
+                  group_off_dev, n_groups, n_pairs, 1, 0, out, ld_out, accumulate, chain,
+                  workspace, workspace_bytes, stream);
 }

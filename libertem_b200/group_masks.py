@@ -11,6 +11,8 @@ within every block of 32 entries the 64 floats of a row are ordered
 ``(c // 2) * 32 + q * 4 + (c % 2) * 2 + which`` for entry ``4*q + c`` and component ``which``
 (0 = real, 1 = imag), which makes the two LDS.128 of a pixel lane bank-conflict free.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -46,7 +48,7 @@ def split_table(table, n_cols):
 
 class GroupPlan:
     def __init__(self, entry_px, table_packed, group_off, n_groups, n_pairs, n_masks, device,
-                 table_split=None, n_cols=0):
+                 table_split=None, n_cols=0, banded=None):
         self.entry_px = torch.from_numpy(entry_px).to(device)
         self.table = torch.from_numpy(table_packed).to(device)
         #: (N, n_entries) hi/lo weight table of the tensor-core kernel (None: FFMA2 kernel only)
@@ -59,6 +61,17 @@ class GroupPlan:
         self.n_masks = n_masks
         self.n_entries = int(group_off[-1])
         self.workspace = torch.zeros(64, dtype=torch.int32, device=device)
+        #: banded twin of the entry list for the tensor-core kernel on large signals:
+        #: dict(n_bands, entry_px, table_split, group_off_host, group_off_dev, n_groups)
+        self.banded = banded
+        self._band_ws = None
+
+    def band_workspace(self, n_frames):
+        need = get_lib().ltb200_group_masks_tc_workspace(
+            n_frames, self.banded['n_groups'], self.n_pairs, self.banded['n_bands'])
+        if self._band_ws is None or self._band_ws.numel() < need:
+            self._band_ws = torch.zeros(need, dtype=torch.uint8, device=self.entry_px.device)
+        return self._band_ws
 
 
 def find_groups(stack2d, max_pairs=MAX_PAIRS):
@@ -89,7 +102,60 @@ def pack_rows(table):
     return np.ascontiguousarray(t.reshape(rows, 2 * n))
 
 
-def build_plan(stack, group_size, device):
+TC_KT = 64                        # entries per stage of the tensor-core kernel (K7_KT)
+#: frame-stream bytes of one band of one 128-frame block aimed at by the band count (a handful
+#: of frame blocks x this must stay L2-resident together with the band's weight-table slices)
+BAND_TARGET_BYTES = 32 << 20
+
+
+def default_bands(sig_size):
+    n = int(round(sig_size * 4 * 128 / BAND_TARGET_BYTES))
+    return max(1, min(32, n))
+
+
+def build_banded(flat, group_size, n_bands, n_cols):
+    """(band, ring) groups of QUADS for the tensor-core kernel: band b holds the pixels
+    [b * K / n_bands, (b + 1) * K / n_bands) of the flattened signal (row bands; K % (4 n_bands)
+    == 0).  A ring's pixels inside a band are covered by quads = 4 consecutive pixels starting at
+    a multiple of 4 (one 16-byte copy per frame); the pixels of a quad outside the ring carry
+    weight 0.  Every group is padded to a multiple of TC_KT entries.  Returns quad_px (first
+    pixel of every quad), the split weight table over the entries (4 per quad) and offsets."""
+    M, K = flat.shape
+    n_rings = M // group_size
+    if K % (4 * n_bands):
+        return None
+    edges = [(b * K) // n_bands for b in range(n_bands + 1)]
+    quad_list, tabs, offs = [], [], [0]
+    supports = []
+    for g in range(n_rings):
+        rows = flat[g * group_size:(g + 1) * group_size]
+        px = np.nonzero(np.any(rows != 0, axis=0))[0]
+        supports.append((rows, np.unique(px >> 2).astype(np.int64)))
+    for b in range(n_bands):
+        for rows, quads_all in supports:
+            q = quads_all[(quads_all * 4 >= edges[b]) & (quads_all * 4 < edges[b + 1])]
+            nq = len(q)
+            nq_pad = ((4 * nq + TC_KT - 1) // TC_KT) * (TC_KT // 4)
+            qpx = np.zeros(nq_pad, dtype=np.int32)
+            qpx[:nq] = 4 * q
+            if nq:
+                qpx[nq:] = 4 * q[-1]          # padding re-reads the last quad (weight 0)
+            px = (4 * q[:, None] + np.arange(4)[None, :]).reshape(-1)
+            tab = np.zeros((group_size, 4 * nq_pad, 2), dtype=np.float32)
+            vals = rows[:, px]
+            tab[:, :4 * nq, 0] = vals.real
+            tab[:, :4 * nq, 1] = vals.imag
+            quad_list.append(qpx)
+            tabs.append(tab)
+            offs.append(offs[-1] + 4 * nq_pad)
+    if offs[-1] == 0:
+        return None
+    return dict(n_bands=n_bands, n_groups=n_bands * n_rings, entry_px=np.concatenate(quad_list),
+                table_split=split_table(np.concatenate(tabs, axis=1), n_cols),
+                group_off=np.array(offs, dtype=np.int32))
+
+
+def build_plan(stack, group_size, device, n_bands=None):
     """stack: complex (M, *sig) dense array with M = n_groups * group_size"""
     M = stack.shape[0]
     flat = np.asarray(stack).reshape(M, -1).astype(np.complex64)
@@ -119,8 +185,21 @@ def build_plan(stack, group_size, device):
         table = np.zeros((MAX_PAIRS, KT, 2), dtype=np.float32)
     n_cols = get_lib().ltb200_group_masks_tc_columns(group_size)
     split = split_table(table[:group_size], n_cols) if n_cols else None
+    if n_bands is None:
+        n_bands = int(os.environ.get('LTB200_K7_BANDS', 0)) or default_bands(flat.shape[1])
+    banded = None
+    while n_bands > 1 and flat.shape[1] % (4 * n_bands):
+        n_bands -= 1
+    if n_cols and n_groups > 0 and flat.shape[1] % 4 == 0:
+        b = build_banded(flat, group_size, n_bands, n_cols)
+        if b is not None:
+            banded = dict(n_bands=b['n_bands'], n_groups=b['n_groups'],
+                          entry_px=torch.from_numpy(b['entry_px']).to(device),
+                          table_split=torch.from_numpy(b['table_split']).to(device),
+                          group_off_host=b['group_off'],
+                          group_off_dev=torch.from_numpy(b['group_off']).to(device))
     return GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
-                     group_size, M, device, table_split=split, n_cols=n_cols)
+                     group_size, M, device, table_split=split, n_cols=n_cols, banded=banded)
 
 
 #: frames from which the tensor-core kernel (128-frame items) is preferred over the FFMA2 one
@@ -130,7 +209,9 @@ TC_MIN_FRAMES = 96
 def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     """out (F, n_masks) complex64 (+)= group-sparse contraction of the float32 tile.
 
-    kernel: 'auto' (tensor cores, K7, from TC_MIN_FRAMES frames), 'tc' (K7) or 'ffma' (K4)"""
+    kernel: 'auto' (tensor cores, K7, from TC_MIN_FRAMES frames: the quad / banded plan for
+    16-byte aligned frame rows, else the 4-byte ring-major gather), 'tc' (K7, 4-byte gather,
+    ring-major), 'banded' (K7, quad gather, banded schedule) or 'ffma' (K4)"""
     lib = get_lib()
     if not tile.is_cuda:
         raise _lib.LTB200Error('tile must be a CUDA tensor (no CPU fallback)')
@@ -145,11 +226,27 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     real = torch.view_as_real(out).reshape(F, 2 * plan.n_masks)
     ld_tile = tile.stride(0) if F > 1 else max(K, 1)
     ld_out = real.stride(0) if F > 1 else max(2 * plan.n_masks, 1)
-    use_tc = kernel == 'tc' or (kernel == 'auto' and F >= TC_MIN_FRAMES)
+    use_tc = kernel in ('tc', 'banded') or (kernel == 'auto' and F >= TC_MIN_FRAMES)
     if use_tc and plan.table_split is None:
-        if kernel == 'tc':
+        if kernel in ('tc', 'banded'):
             raise _lib.LTB200Error('no tensor-core table for this plan')
         use_tc = False
+    if kernel == 'banded' and plan.banded is None:
+        raise _lib.LTB200Error('no quad plan (sig_size not a multiple of 4)')
+    aligned = tile.data_ptr() % 16 == 0 and ld_tile % 4 == 0
+    if kernel == 'banded' and not aligned:
+        raise _lib.LTB200Error('the banded plan needs 16-byte aligned frame rows')
+    if use_tc and plan.banded is not None and aligned and kernel in ('banded', 'auto'):
+        b = plan.banded
+        ws = plan.band_workspace(F)
+        with torch.cuda.device(tile.device):
+            check(lib.ltb200_group_masks_tc_banded(
+                tile.data_ptr(), F, K, ld_tile, b['entry_px'].data_ptr(),
+                b['table_split'].data_ptr(), b['group_off_host'].ctypes.data,
+                b['group_off_dev'].data_ptr(), b['n_groups'], plan.n_pairs, b['n_bands'],
+                real.data_ptr(), ld_out, int(bool(accumulate)), int(chain), ws.data_ptr(),
+                ws.numel(), torch.cuda.current_stream(tile.device).cuda_stream))
+        return out
     if use_tc:
         with torch.cuda.device(tile.device):
             check(lib.ltb200_group_masks_tc(

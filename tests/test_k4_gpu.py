@@ -23,7 +23,7 @@ def make_stack(n_groups, size, K, seed, empty_group=None):
     return stack
 
 
-@pytest.mark.parametrize('kernel', ['ffma', 'tc'])
+@pytest.mark.parametrize('kernel', ['ffma', 'tc', 'banded', 'auto'])
 @pytest.mark.parametrize('F,K,n_groups,size', [(64, 512, 3, 25), (100, 1000, 5, 7), (7, 300, 2, 28),
                                                (200, 4096, 32, 25), (65, 640, 4, 1),
                                                (129, 1000, 5, 4), (300, 2048, 6, 16),
@@ -66,6 +66,43 @@ def test_group_masks_tc_chains(chain):
     assert np.abs(out - ref).max() / scale <= 3e-6
     ffma = gm.group_masks(t, plan, kernel='ffma').cpu().numpy()
     assert np.abs(out - ffma).max() / scale <= 3e-6
+
+
+@pytest.mark.parametrize('F,K,n_groups,size,n_bands', [(300, 4096, 6, 25, 4), (1000, 3000, 5, 7, 3),
+                                                       (129, 2048, 4, 25, 16), (2000, 8192, 8, 25, 2),
+                                                       (64, 1000, 3, 9, 5)])
+def test_group_masks_banded(F, K, n_groups, size, n_bands):
+    """banded plan of K7 ((pixel band, ring) groups, band-major schedule, fixed-order band
+    reduction): same result as the ring-major schedule and as numpy float64; empty (band, ring)
+    groups, an empty ring, accumulate and strided tiles"""
+    from libertem_b200 import group_masks as gm
+    stack = make_stack(n_groups, size, K, seed=F + K + 1, empty_group=1 if n_groups > 3 else None)
+    stack[:size, K // 2:] = 0                     # ring 0 lives in the first bands only
+    plan = gm.build_plan(stack, size, torch.device('cuda'), n_bands=n_bands)
+    assert plan.banded is not None and plan.banded['n_groups'] == n_bands * n_groups
+    data = synth.uniform_f32(0, F * K, 9).reshape(F, K)
+    t = torch.from_numpy(data).cuda()
+    out = gm.group_masks(t, plan, kernel='banded').cpu().numpy()
+    ref = data.astype(np.float64) @ stack.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(stack).astype(np.float64).T).max() + 1e-30
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    tc = gm.group_masks(t, plan, kernel='tc').cpu().numpy()
+    assert np.abs(out - tc).max() / scale <= 2e-6
+    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True,
+                          kernel='banded').cpu().numpy()
+    assert np.abs(out2 - 2 * ref).max() / scale <= 4e-6
+    big = torch.zeros((F, K + 24), device='cuda')
+    big[:, 8:8 + K] = t
+    out3 = gm.group_masks(big[:, 8:8 + K], plan, kernel='banded').cpu().numpy()
+    assert np.array_equal(out3, out)              # deterministic
+    import os
+    os.environ['LTB200_K7_FBG'] = '2'
+    try:
+        out4 = gm.group_masks(t, plan, kernel='banded').cpu().numpy()
+    finally:
+        del os.environ['LTB200_K7_FBG']
+    assert np.array_equal(out4, out)              # schedule does not change the arithmetic
 
 
 def test_split_table_layout():
