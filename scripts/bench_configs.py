@@ -15,7 +15,7 @@ from libertem_b200.udf import ApplyMasksUDF, CoMUDF, SumUDF, SumSigUDF
 from libertem_b200.api import Context
 from bench import bench_masks
 
-PEAK = 6549.4
+PEAK = 6551.0
 dev = torch.device('cuda')
 
 
@@ -47,7 +47,8 @@ def report(name, ds, udfs, note='', steps=10):
     line = dict(config=name, frames=frames, ms_per_pass=round(ms, 4),
                 frames_per_s=round(frames / ms * 1e3), GBps=round(gbs, 1),
                 roofline_frac=round(gbs / PEAK, 4), launches_per_pass=launches, note=note,
-                unfused_calls=runner.stats['unfused_calls'])
+                unfused_calls=runner.stats['unfused_calls'],
+                int8_passes=runner.stats.get('int8_passes', 0), last_kernel=engine.last_kernel())
     print(json.dumps(line), flush=True)
     return line
 
@@ -68,7 +69,7 @@ if 'cfg3' in which:
                       ds, [SumUDF(), SumSigUDF(),
                            ApplyMasksUDF(mask_factories=facs, use_sparse=True,
                                          mask_dtype=np.float32)],
-                      'one fused pass: u16 TMA ingest, 5 columns + frame sum'))
+                      'one fused pass on the int8 tensor cores (K8): u16 TMA ingest, 5 columns + frame sum as MMAs'))
     del ds
     torch.cuda.empty_cache()
 if 'cfg5' in which:
@@ -87,6 +88,6 @@ if 'cfg4' in which:
     ctx = Context()
     a = ctx.create_radial_fourier_analysis(ds, n_bins=32)
     out.append(report('cfg4 (nav %dx64 sub-sample): 512x512 sig f32, radial Fourier 32 bins x 25 orders' % ds.shape[0],
-                      ds, [a.get_udf()], 'K7 group-sparse tensor-core kernel, %d complex masks' % a.parameters['mask_count'], steps=3))
+                      ds, [a.get_udf()], 'K7 group-sparse tensor-core kernel (quad gather, banded schedule), %d complex masks' % a.parameters['mask_count'], steps=3))
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(out, open('gpurun_out/configs.json', 'w'), indent=1)
