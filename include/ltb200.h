@@ -134,22 +134,22 @@ LTB_API int ltb200_masks_dense_tc_u16(const uint16_t* tile, int64_t n_frames, in
                                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * Integer fast path (K8): uint16 tiles x int8 masks (binary virtual-detector masks, all-ones
+ * Integer fast path (K8): uint16 (LTB_U16) or uint8 (LTB_U8) tiles x int8 masks (binary virtual-detector masks, all-ones
  * for SumSigUDF, small integer weights) on the int8 tensor cores (tcgen05.mma kind::i8).  For
  * integer data and integer masks the reference's float32 sums (udf/masks.py:59-77) are exact,
  * so exact int32 accumulation reproduces them bit for bit; the bytes of the TMA-staged tile
  * are the MMA operand as they land in shared memory -- no per-pixel instruction runs.
  * out = float32 of the exact integer result.  `sig_sum` (nullable) fuses SumUDF
- * (udf/sum.py:44-49) as a second MMA over the same stage.  1..16 columns, sig_size % 8 == 0,
- * 256 <= sig_size <= 65536; LTB_ERR_UNSUPPORTED otherwise.
+ * (udf/sum.py:44-49) as a second MMA over the same stage.  1..16 columns, 16-byte aligned rows,
+ * 256 (uint16) / 512 (uint8) <= sig_size <= 65536; LTB_ERR_UNSUPPORTED otherwise.
  * ------------------------------------------------------------------------------------- */
-LTB_API size_t ltb200_masks_dense_i8_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
-                                               int with_sig_sum);
-LTB_API int ltb200_masks_dense_i8(const uint16_t* tile, int64_t n_frames, int64_t sig_size,
-                                  int64_t ld_tile, const int8_t* masks, int n_masks,
-                                  int64_t ld_masks, float* out, int64_t ld_out, int accumulate,
-                                  float* sig_sum, void* workspace, size_t workspace_bytes,
-                                  void* stream);
+LTB_API size_t ltb200_masks_dense_i8_workspace(int tile_dtype, int64_t n_frames, int64_t sig_size,
+                                               int n_masks, int with_sig_sum);
+LTB_API int ltb200_masks_dense_i8(const void* tile, int tile_dtype, int64_t n_frames,
+                                  int64_t sig_size, int64_t ld_tile, const int8_t* masks,
+                                  int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
+                                  int accumulate, float* sig_sum, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 
 /* tuning / test knob: which dense kernel ltb200_masks_dense uses for float32 tiles.
  * 0 = auto (default), 1 = FFMA2 even/odd-pixel accumulator pairs, 2 = FFMA2 mask-pair

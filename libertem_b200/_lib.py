@@ -27,9 +27,9 @@ SIGNATURES = {
     'ltb200_masks_dense_tc_u16_workspace': (_sz, [_i64, _i64, _int, _int]),
     'ltb200_masks_dense_tc_u16': (_int, [_vp, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _int,
                                          _int, _vp, _vp, _sz, _vp]),
-    'ltb200_masks_dense_i8_workspace': (_sz, [_i64, _i64, _int, _int]),
-    'ltb200_masks_dense_i8': (_int, [_vp, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _int,
-                                     _vp, _vp, _sz, _vp]),
+    'ltb200_masks_dense_i8_workspace': (_sz, [_int, _i64, _i64, _int, _int]),
+    'ltb200_masks_dense_i8': (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64,
+                                     _int, _vp, _vp, _sz, _vp]),
     'ltb200_set_k1_variant': (_int, [_int]),
     'ltb200_last_kernel': (_int, []),
     'ltb200_launch_count': (_i64, [_int]),

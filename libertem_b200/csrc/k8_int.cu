@@ -19,6 +19,9 @@
 //     with the stage read as an MN-major [K = 256 frames x N = 128 bytes] B operand and an
 //     all-ones A operand held in TMEM; every row of D2 is the per-byte column sum.
 //
+// uint8 tiles (BPP = 1) are the same kernel with one byte per pixel: 128 pixels per stage, one
+// int8 mask row per column, out = L.
+//
 // So the SM only moves data: TMA -> shared memory -> tensor core.  Warps: 0 frame-stream TMA,
 // 1 mask-tile TMA, 2 MMA issuer (warp-uniform loop, one elected lane), 3 TMEM allocation,
 // 4..7 drain (per stage: the 128 byte sums -> 64 pixel sums -> 64-bit RED into the frame-sum
@@ -30,7 +33,6 @@
 namespace ltb {
 
 constexpr int K8_FB = 256;             // frames per item (2 groups of 128 TMEM lanes)
-constexpr int K8_PX = 64;              // pixels per stage (128 bytes per frame row)
 constexpr int K8_DS = 5;               // data ring depth
 constexpr int K8_MS = 4;               // mask ring depth
 constexpr int K8_THREADS = 256;
@@ -46,7 +48,7 @@ struct K8Params {
     int64_t sig_size;
     int n_masks;
     int ksplit;
-    int64_t k_per_split;   // pixels, multiple of K8_PX
+    int64_t k_per_split;   // pixels, multiple of the stage width (128 / BPP)
     int64_t n_items;
     float* out;
     int64_t ld_out;
@@ -159,8 +161,8 @@ __host__ __device__ constexpr uint32_t k8_idesc(int a_signed, int b_signed, int 
            ((uint32_t)(128 >> 4) << 24);
 }
 
-// packed[r, 2p + b] (int8, (2 NC) x (2 sig_pad)): r < NC -> mask r weights the low bytes,
-// r >= NC -> mask r - NC weights the high bytes; zero padded
+// uint16 tiles: packed[r, 2p + b] (int8, (2 NC) x (2 sig_pad)): r < NC -> mask r weights the low
+// bytes, r >= NC -> mask r - NC weights the high bytes; zero padded.
 __global__ void k8_pack_masks_kernel(const int8_t* __restrict__ masks, int n_masks,
                                      int64_t ld_masks, int64_t sig_size, int64_t sig_pad, int nc,
                                      uint16_t* __restrict__ packed) {
@@ -173,6 +175,19 @@ __global__ void k8_pack_masks_kernel(const int8_t* __restrict__ masks, int n_mas
         if (r < n_masks && k < sig_size) m = (uint8_t)masks[(int64_t)r * ld_masks + k];
         packed[(int64_t)r * sig_pad + k] = m;
         packed[(int64_t)(r + nc) * sig_pad + k] = (uint16_t)(m << 8);
+    }
+}
+
+// uint8 tiles: packed[r, p] (int8, N x sig_pad) = mask r, zero padded
+__global__ void k8_pack_masks_u8_kernel(const int8_t* __restrict__ masks, int n_masks,
+                                        int64_t ld_masks, int64_t sig_size, int64_t sig_pad,
+                                        int n, int8_t* __restrict__ packed) {
+    const int64_t total = (int64_t)n * sig_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / sig_pad);
+        const int64_t k = i % sig_pad;
+        packed[i] = (r < n_masks && k < sig_size) ? masks[(int64_t)r * ld_masks + k] : (int8_t)0;
     }
 }
 
@@ -206,12 +221,14 @@ struct K8Smem {
     static constexpr uint32_t total(int n) { return bar_off(n) + 256 + 1024; }
 };
 
-// N = 2 NC accumulator columns per frame group (NC = 8 or 16 mask columns)
-template <int N>
+// N accumulator columns per frame group: BPP = 2 (uint16): N = 2 NC, NC = 8 or 16 mask columns
+// (low-byte and high-byte sums); BPP = 1 (uint8): N = 16 mask columns
+template <int N, int BPP>
 __global__ void __launch_bounds__(K8_THREADS, 1)
 k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
               const __grid_constant__ CUtensorMap tm_mask, const K8Params p) {
-    constexpr int NC = N / 2;
+    constexpr int NC = N / BPP;
+    constexpr int K8_PX = 128 / BPP;                            // pixels per stage
     constexpr uint32_t MASK_BYTES = (uint32_t)N * 128u;
     constexpr uint32_t IDESC_MASK = k8_idesc(0, 1, 0, N);       // u8 data x s8 masks
     constexpr uint32_t IDESC_SUM = k8_idesc(0, 0, 1, 128);      // u8 ones x u8 data (MN-major)
@@ -318,7 +335,7 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
                     mbar_wait(&mask_empty[ms], ((it / K8_MS) & 1) ^ 1);
                     mbar_arrive_expect_tx(&mask_full[ms], MASK_BYTES);
                     tma_load_2d(smem + K8Smem::mask_off(ms, N), &tm_mask,
-                                (int32_t)(2 * (k0 + i * K8_PX)), 0, &mask_full[ms], pol);
+                                (int32_t)(BPP * (k0 + i * K8_PX)), 0, &mask_full[ms], pol);
                 }
             }
         }
@@ -397,14 +414,23 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&sum_free[sb]);
-                        const int64_t px0 = k0 + (int64_t)i * K8_PX + w * 16;
+                        if constexpr (BPP == 2) {
+                            const int64_t px0 = k0 + (int64_t)i * K8_PX + w * 16;
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const uint32_t lo = r[j >> 3][(2 * j) & 15];
-                            const uint32_t hi = r[j >> 3][(2 * j + 1) & 15];
-                            if (px0 + j < p.sig_size)
-                                atomicAdd(p.sig_acc + px0 + j,
-                                          (unsigned long long)(lo + (hi << 8)));
+                            for (int j = 0; j < 16; j++) {
+                                const uint32_t lo = r[j >> 3][(2 * j) & 15];
+                                const uint32_t hi = r[j >> 3][(2 * j + 1) & 15];
+                                if (px0 + j < p.sig_size)
+                                    atomicAdd(p.sig_acc + px0 + j,
+                                              (unsigned long long)(lo + (hi << 8)));
+                            }
+                        } else {
+                            const int64_t px0 = k0 + (int64_t)i * K8_PX + w * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (px0 + j < p.sig_size)
+                                    atomicAdd(p.sig_acc + px0 + j,
+                                              (unsigned long long)r[j >> 4][j & 15]);
                         }
                     }
                 }
@@ -436,8 +462,9 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     if (c >= p.n_masks) break;
-                    const long long tot = (long long)(int32_t)v[g][c / 16][c % 16] +
-                                          256ll * (int32_t)v[g][(NC + c) / 16][(NC + c) % 16];
+                    long long tot = (long long)(int32_t)v[g][c / 16][c % 16];
+                    if constexpr (BPP == 2)
+                        tot += 256ll * (int32_t)v[g][(NC + c) / 16][(NC + c) % 16];
                     if (p.ksplit == 1) {
                         const float val = (float)tot;
                         o[c] = p.accumulate ? (o[c] + val) : val;
@@ -462,11 +489,11 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms) {
+static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms, int px) {
     int best = 1;
     double best_eff = 0.0;
     for (int ks = 1; ks <= 64; ks *= 2) {
-        if (ks > 1 && sig_size / ks < 16 * K8_PX) break;
+        if (ks > 1 && sig_size / ks < 16 * px) break;
         const int64_t items = n_fb * ks;
         const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
         if (eff > best_eff + 1e-9) {
@@ -480,29 +507,32 @@ static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms) {
 
 static size_t k8_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// accumulator columns N of the kernel instantiation
+static int k8_n(int n_masks, int bpp) { return bpp == 2 ? (n_masks <= 8 ? 16 : 32) : 16; }
+
 struct K8Ws {
     size_t pack_off, part_off, sig_off, total;
 };
 
-static K8Ws k8_ws(int64_t n_frames, int64_t sig_size, int n_masks, bool with_sig) {
+static K8Ws k8_ws(int64_t n_frames, int64_t sig_size, int n_masks, int bpp, bool with_sig) {
     K8Ws w;
-    const int nc = n_masks <= 8 ? 8 : 16;
-    const int64_t sig_pad = ((sig_size + K8_PX - 1) / K8_PX) * K8_PX;
+    const int px = 128 / bpp;
+    const int64_t sig_pad = ((sig_size + px - 1) / px) * px;
     w.pack_off = 0;
-    const size_t pack = (size_t)2 * nc * sig_pad * 2;
+    const size_t pack = (size_t)k8_n(n_masks, bpp) * sig_pad * bpp;
     w.part_off = k8_align256(pack);
     const int64_t n_fb = (n_frames + K8_FB - 1) / K8_FB;
-    const int ks = k8_choose_ksplit(n_fb, sig_size, sm_count());
+    const int ks = k8_choose_ksplit(n_fb, sig_size, sm_count(), px);
     const size_t part = ks > 1 ? (size_t)ks * n_frames * n_masks * sizeof(long long) : 0;
     w.sig_off = w.part_off + k8_align256(part);
     w.total = w.sig_off + (with_sig ? k8_align256((size_t)sig_size * 8) : 0);
     return w;
 }
 
-template <int N>
+template <int N, int BPP>
 static int k8_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K8Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k8_int_kernel<N>;
+    auto kern = k8_int_kernel<N, BPP>;
     const size_t smem = K8Smem::total(N);
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -519,10 +549,12 @@ static int k8_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K8Par
 }
 
 static bool k8_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
-                        int n_masks) {
-    // 255 * 127 * sig_size < 2^31 keeps the int32 accumulators exact
-    return sig_size % 8 == 0 && ld_tile % 8 == 0 && (uintptr_t)tile % 16 == 0 &&
-           sig_size >= 4 * K8_PX && sig_size <= 65536 && n_frames >= 1 &&
+                        int n_masks, int bpp) {
+    // 16-byte aligned rows for the TMA; 255 * 127 * sig_size < 2^31 keeps the int32
+    // accumulators exact
+    const int align = 16 / bpp;
+    return sig_size % align == 0 && ld_tile % align == 0 && (uintptr_t)tile % 16 == 0 &&
+           sig_size >= 4 * (128 / bpp) && sig_size <= 65536 && n_frames >= 1 &&
            n_frames < (1ll << 31) && n_masks >= 1 && n_masks <= K8_MAX_COLUMNS;
 }
 
@@ -530,31 +562,37 @@ static bool k8_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, in
 
 using namespace ltb;
 
-extern "C" size_t ltb200_masks_dense_i8_workspace(int64_t n_frames, int64_t sig_size, int n_masks,
+extern "C" size_t ltb200_masks_dense_i8_workspace(int tile_dtype, int64_t n_frames,
+                                                  int64_t sig_size, int n_masks,
                                                   int with_sig_sum) {
     if (n_frames <= 0 || sig_size <= 0 || n_masks <= 0 || n_masks > K8_MAX_COLUMNS) return 0;
-    return k8_ws(n_frames, sig_size, n_masks, with_sig_sum != 0).total;
+    const int bpp = tile_dtype == LTB_U8 ? 1 : 2;
+    return k8_ws(n_frames, sig_size, n_masks, bpp, with_sig_sum != 0).total;
 }
 
-extern "C" int ltb200_masks_dense_i8(const uint16_t* tile, int64_t n_frames, int64_t sig_size,
-                                     int64_t ld_tile, const int8_t* masks, int n_masks,
-                                     int64_t ld_masks, float* out, int64_t ld_out, int accumulate,
-                                     float* sig_sum, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+extern "C" int ltb200_masks_dense_i8(const void* tile, int tile_dtype, int64_t n_frames,
+                                     int64_t sig_size, int64_t ld_tile, const int8_t* masks,
+                                     int n_masks, int64_t ld_masks, float* out, int64_t ld_out,
+                                     int accumulate, float* sig_sum, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
     LTB_REQUIRE(n_frames >= 0 && sig_size >= 0 && n_masks >= 0, "masks_dense_i8: negative size");
+    LTB_REQUIRE(tile_dtype == LTB_U16 || tile_dtype == LTB_U8,
+                "masks_dense_i8: uint16 or uint8 tiles, got dtype %d", tile_dtype);
     if (n_frames == 0 || n_masks == 0) return LTB_OK;
     LTB_REQUIRE(tile != nullptr && masks != nullptr && out != nullptr,
                 "masks_dense_i8: NULL pointer");
     LTB_REQUIRE(ld_tile >= sig_size && ld_masks >= sig_size && ld_out >= n_masks,
                 "masks_dense_i8: leading dimension too small");
-    if (!k8_shape_ok(tile, n_frames, sig_size, ld_tile, n_masks)) {
+    const int bpp = tile_dtype == LTB_U8 ? 1 : 2;
+    const int px = 128 / bpp;
+    if (!k8_shape_ok(tile, n_frames, sig_size, ld_tile, n_masks, bpp)) {
         set_error("masks_dense_i8: shape not supported by the int8 tensor-core path (sig_size "
-                  "%lld, ld_tile %lld, %d columns; need sig_size %% 8 == 0 in [256, 65536], "
-                  "1..%d columns)", (long long)sig_size, (long long)ld_tile, n_masks,
-                  K8_MAX_COLUMNS);
+                  "%lld, ld_tile %lld, %d columns; need 16-byte aligned rows, %d <= sig_size <= "
+                  "65536, 1..%d columns)", (long long)sig_size, (long long)ld_tile, n_masks,
+                  4 * px, K8_MAX_COLUMNS);
         return LTB_ERR_UNSUPPORTED;
     }
-    const K8Ws wl = k8_ws(n_frames, sig_size, n_masks, sig_sum != nullptr);
+    const K8Ws wl = k8_ws(n_frames, sig_size, n_masks, bpp, sig_sum != nullptr);
     if (wl.total > workspace_bytes || workspace == nullptr) {
         set_error("masks_dense_i8: workspace of %zu B required, %zu B given", wl.total,
                   workspace_bytes);
@@ -563,18 +601,17 @@ extern "C" int ltb200_masks_dense_i8(const uint16_t* tile, int64_t n_frames, int
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)workspace;
     const int sms = sm_count();
-    const int nc = n_masks <= 8 ? 8 : 16;
-    const int n = 2 * nc;
-    const int64_t sig_pad = ((sig_size + K8_PX - 1) / K8_PX) * K8_PX;
+    const int n = k8_n(n_masks, bpp);
+    const int64_t sig_pad = ((sig_size + px - 1) / px) * px;
     const int64_t n_fb = (n_frames + K8_FB - 1) / K8_FB;
 
     K8Params p;
     p.n_frames = n_frames;
     p.sig_size = sig_size;
     p.n_masks = n_masks;
-    p.ksplit = k8_choose_ksplit(n_fb, sig_size, sms);
-    const int64_t subs = (sig_size + K8_PX - 1) / K8_PX;
-    p.k_per_split = ((subs + p.ksplit - 1) / p.ksplit) * K8_PX;
+    p.ksplit = k8_choose_ksplit(n_fb, sig_size, sms, px);
+    const int64_t subs = (sig_size + px - 1) / px;
+    p.k_per_split = ((subs + p.ksplit - 1) / p.ksplit) * px;
     p.n_items = n_fb * p.ksplit;
     p.out = out;
     p.ld_out = ld_out;
@@ -588,25 +625,36 @@ extern "C" int ltb200_masks_dense_i8(const uint16_t* tile, int64_t n_frames, int
         p.sig_acc = (unsigned long long*)(ws + wl.sig_off);
         LTB_CUDA_CHECK(cudaMemsetAsync(p.sig_acc, 0, (size_t)sig_size * 8, st));
     }
-    uint16_t* packed = (uint16_t*)(ws + wl.pack_off);
     {
-        const int64_t total = (int64_t)nc * sig_pad;
+        const int64_t total = (int64_t)(bpp == 2 ? n / 2 : n) * sig_pad;
         int blocks = (int)((total + 255) / 256);
         if (blocks > sms * 8) blocks = sms * 8;
-        k8_pack_masks_kernel<<<blocks, 256, 0, st>>>(masks, n_masks, ld_masks, sig_size, sig_pad,
-                                                     nc, packed);
+        if (bpp == 2)
+            k8_pack_masks_kernel<<<blocks, 256, 0, st>>>(masks, n_masks, ld_masks, sig_size,
+                                                         sig_pad, n / 2,
+                                                         (uint16_t*)(ws + wl.pack_off));
+        else
+            k8_pack_masks_u8_kernel<<<blocks, 256, 0, st>>>(masks, n_masks, ld_masks, sig_size,
+                                                            sig_pad, n,
+                                                            (int8_t*)(ws + wl.pack_off));
         count_launch();
     }
     CUtensorMap tmd, tmm;
-    int rc = encode_tmap_2d_sw(&tmd, tile, CU_TENSOR_MAP_DATA_TYPE_UINT16, (uint64_t)sig_size,
-                               (uint64_t)n_frames, (uint64_t)ld_tile * 2, K8_PX, K8_FB,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap_2d_sw(&tmd, tile,
+                               bpp == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                        : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                               (uint64_t)sig_size, (uint64_t)n_frames, (uint64_t)ld_tile * bpp,
+                               (uint32_t)px, K8_FB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
-    rc = encode_tmap_2d_sw(&tmm, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)sig_pad * 2,
-                           (uint64_t)n, (uint64_t)sig_pad * 2, 128, (uint32_t)n,
-                           CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap_2d_sw(&tmm, ws + wl.pack_off, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                           (uint64_t)sig_pad * bpp, (uint64_t)n, (uint64_t)sig_pad * bpp, 128,
+                           (uint32_t)n, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
-    rc = n == 16 ? k8_launch<16>(tmd, tmm, p, grid, st) : k8_launch<32>(tmd, tmm, p, grid, st);
+    if (bpp == 1)
+        rc = k8_launch<16, 1>(tmd, tmm, p, grid, st);
+    else
+        rc = n == 16 ? k8_launch<16, 2>(tmd, tmm, p, grid, st)
+                     : k8_launch<32, 2>(tmd, tmm, p, grid, st);
     if (rc != LTB_OK) return rc;
     if (p.ksplit > 1) {
         const int64_t total = n_frames * n_masks;

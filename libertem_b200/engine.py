@@ -175,14 +175,15 @@ def masks_dense_tc_u16(tile, masks, out=None, accumulate=False, chain=0, sig_sum
 
 
 def masks_dense_i8(tile, masks, out=None, accumulate=False, sig_sum=None):
-    """Integer fast path (K8, int8 tensor cores): uint16 tile (F, K) x int8 masks (M, K),
+    """Integer fast path (K8, int8 tensor cores): uint16 / uint8 tile (F, K) x int8 masks (M, K),
     M <= 16 -> float32 out (F, M) of the exact integer sums; ``sig_sum`` (K,) float32 +=
     the exact frame sum of the tile (SumUDF)."""
     lib = get_lib()
     _require_cuda(tile, 'tile')
     _require_cuda(masks, 'masks')
-    if tile.dtype != torch.uint16 or masks.dtype != torch.int8:
-        raise TypeError('masks_dense_i8 takes uint16 tiles and int8 masks')
+    if tile.dtype not in (torch.uint16, torch.uint8) or masks.dtype != torch.int8:
+        raise TypeError('masks_dense_i8 takes uint16 / uint8 tiles and int8 masks')
+    tdt = _TORCH_DTYPES[tile.dtype]
     if tile.dim() != 2 or masks.dim() != 2 or tile.shape[1] != masks.shape[1]:
         raise ValueError(f'shape mismatch: tile {tuple(tile.shape)} masks {tuple(masks.shape)}')
     if tile.stride(1) != 1:
@@ -202,10 +203,10 @@ def masks_dense_i8(tile, masks, out=None, accumulate=False, sig_sum=None):
     ld_masks = masks.stride(0) if M > 1 else max(K, 1)
     ld_out = out.stride(0) if F > 1 else max(M, 1)
     with torch.cuda.device(tile.device):
-        need = lib.ltb200_masks_dense_i8_workspace(F, K, M, int(sig_sum is not None))
+        need = lib.ltb200_masks_dense_i8_workspace(tdt, F, K, M, int(sig_sum is not None))
         ws = _workspace(tile.device, max(need, 256))
         check(lib.ltb200_masks_dense_i8(
-            tile.data_ptr(), F, K, ld_tile, masks.data_ptr(), M, ld_masks, out.data_ptr(),
+            tile.data_ptr(), tdt, F, K, ld_tile, masks.data_ptr(), M, ld_masks, out.data_ptr(),
             ld_out, int(bool(accumulate)), sig_sum.data_ptr() if sig_sum is not None else None,
             ws.data_ptr(), ws.numel(), _stream_ptr(tile.device)))
     return out

@@ -436,7 +436,7 @@ class UDFRunner:
             self.stats['fused_launch_groups'] += 1
 
     def _dense(self, flat, rows, out=None, accumulate=False, sig_sum=None):
-        """One fused pass.  uint16 tiles against integer-valued mask rows (binary virtual
+        """One fused pass.  uint16 / uint8 tiles against integer-valued mask rows (binary virtual
         detectors, the all-ones row of SumSigUDF, the CoM coordinate masks, ...) take the exact
         int8 tensor-core kernel (K8); everything else the float kernels behind
         ``masks_dense``."""
@@ -469,9 +469,12 @@ class UDFRunner:
         integer weights up to 127 * 129 (m = d0 + 128 d1, both digits int8), else None."""
         F, K = flat.shape
         M = rows.shape[0]
-        if (flat.dtype != torch.uint16 or not INT8_PATH or not 1 <= M <= 16 or F < 256
-                or K % 8 or not 256 <= K <= 65536 or flat.stride(1) != 1
-                or (F > 1 and flat.stride(0) % 8) or flat.data_ptr() % 16
+        if flat.dtype not in (torch.uint16, torch.uint8):
+            return None
+        align = 16 // flat.element_size()            # pixels per 16 bytes
+        if (not INT8_PATH or not 1 <= M <= 16 or F < 256 or K % align
+                or not 64 * align // 2 <= K <= 65536 or flat.stride(1) != 1
+                or (F > 1 and flat.stride(0) % align) or flat.data_ptr() % 16
                 or rows.dtype != torch.float32):
             return None
         key = (rows.data_ptr(), tuple(rows.shape))

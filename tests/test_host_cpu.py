@@ -293,3 +293,38 @@ def _cpu_tiles(ds):
     for f0 in range(part.start, part.stop, depth):
         f1 = min(f0 + depth, part.stop)
         yield from ds._emit(flat[f0:f1], f0, f1, None, None, ds.tileshape)
+
+
+def test_banded_quad_plan_reconstructs_the_masks():
+    """host plan of the tensor-core group-sparse kernel (group_masks.build_banded): quads are 4
+    consecutive pixels at a multiple of 4 inside their band, groups are (band, ring) pairs
+    padded to 64 entries, and hi + lo of the split weight table reproduce every mask value"""
+    from libertem_b200 import group_masks as gm
+    rng = np.random.default_rng(0)
+    K, size, n_rings, n_bands = 4096, 5, 3, 4
+    stack = np.zeros((n_rings * size, K), np.complex64)
+    for g in range(n_rings):
+        px = np.sort(rng.choice(K, 300, replace=False))
+        stack[g * size:(g + 1) * size, px] = (rng.random((size, 300)) - 0.5
+                                              + 1j * rng.random((size, 300))).astype(np.complex64)
+    n_cols = 32                                   # 4 * size = 20 -> 32 accumulator columns
+    b = gm.build_banded(stack, size, n_bands, n_cols)
+    off, quad_px, table = b['group_off'], b['entry_px'], b['table_split']
+    assert b['n_groups'] == n_bands * n_rings and len(off) == b['n_groups'] + 1
+    assert np.all(off % gm.TC_KT == 0) and off[-1] == 4 * len(quad_px) == table.shape[1]
+    assert np.all(quad_px % 4 == 0)
+    nq = n_cols // 4
+    dense = np.zeros_like(stack, dtype=np.complex128)
+    for gidx in range(b['n_groups']):
+        band, ring = divmod(gidx, n_rings)
+        for e in range(off[gidx], off[gidx + 1]):
+            px = quad_px[e // 4] + e % 4
+            in_band = band * K // n_bands <= px < (band + 1) * K // n_bands
+            assert in_band or not table[:, e].any()
+            for r in range(2 * size):
+                h, j = divmod(r, nq)
+                val = float(table[h * 2 * nq + j, e]) + float(table[h * 2 * nq + nq + j, e])
+                dense[ring * size + r // 2, px] += val * (1j if r % 2 else 1.0)
+    assert np.abs(dense - stack).max() <= 2.0 ** -21
+    assert gm.default_bands(512 * 512) == 4 and gm.default_bands(64 * 64) == 1
+    assert gm.build_banded(stack[:, :4090], size, 4, n_cols) is None     # K % 16 != 0

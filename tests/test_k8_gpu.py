@@ -142,3 +142,57 @@ def test_i8_unsupported(eng):
     big = torch.zeros((4, 65536 + 64), dtype=torch.uint16, device='cuda')
     with pytest.raises(LTB200Error):
         eng.masks_dense_i8(big, torch.ones((1, 65536 + 64), dtype=torch.int8, device='cuda'))
+
+
+# ---- uint8 tiles (one byte per pixel) -----------------------------------------------------------
+
+def check_exact_u8(eng, data, masks, with_sum=True):
+    t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+    m = torch.from_numpy(masks).cuda()
+    K = data.shape[1]
+    sig = torch.zeros(K, dtype=torch.float32, device='cuda') if with_sum else None
+    out = eng.masks_dense_i8(t, m, sig_sum=sig)
+    assert eng.last_kernel() == 8
+    tt = t.double()
+    exact = tt @ m.double().T
+    assert torch.equal(out, exact.float()), (out.double() - exact).abs().max().item()
+    if with_sum:
+        assert torch.equal(sig, tt.sum(0).float())
+    return out
+
+
+@pytest.mark.parametrize('n_masks', [1, 5, 8, 9, 16])
+def test_i8_u8_mask_counts(eng, n_masks):
+    F, K = 600, 4096 + 16 * 3
+    data = (synth.hash_u32(0, F * K, 51) & 0xFF).astype(np.uint8).reshape(F, K)
+    masks = int_masks(n_masks, K, 52, -128, 127)
+    masks[0] = 1
+    check_exact_u8(eng, data, masks)
+
+
+@pytest.mark.parametrize('F,K', [(1, 512), (255, 528), (257, 4112), (1000, 1040), (300, 16384),
+                                 (40960, 1024), (3000, 65536)])
+def test_i8_u8_shapes(eng, F, K):
+    data = (synth.hash_u32(0, F * K, 53) % 7).astype(np.uint8).reshape(F, K)
+    data[:, ::1013] = 255
+    masks = int_masks(5, K, 54, 0, 2)
+    masks[4] = 1
+    out = check_exact_u8(eng, data, masks)
+    out2 = check_exact_u8(eng, data, masks, with_sum=False)
+    assert torch.equal(out, out2)
+    # the float kernels of this library agree (uint8 ingest of the generic path)
+    f = eng.masks_dense(torch.from_numpy(data).cuda(),
+                        torch.from_numpy(masks.astype(np.float32)).cuda())
+    assert torch.equal(out, f)
+
+
+def test_i8_u8_unsupported(eng):
+    from libertem_b200._lib import LTB200Error
+    t = torch.zeros((300, 1024), dtype=torch.uint8, device='cuda')
+    with pytest.raises(LTB200Error):
+        eng.masks_dense_i8(t[:, :256], torch.ones((2, 256), dtype=torch.int8, device='cuda'))
+    with pytest.raises(LTB200Error):
+        eng.masks_dense_i8(t[:, :1000], torch.ones((2, 1000), dtype=torch.int8, device='cuda'))
+    with pytest.raises(TypeError):
+        eng.masks_dense_i8(t.to(torch.int16), torch.ones((2, 1024), dtype=torch.int8,
+                                                          device='cuda'))

@@ -184,6 +184,28 @@ def test_com_u16_int8_tensor_path(lt):
     assert np.array_equal(res[3]['intensity'].data, O.sum_udf(data, num_partitions=2))
 
 
+def test_u8_int8_tensor_path(lt):
+    """uint8 detector data: SumUDF + SumSigUDF + binary masks + CoM in one pass on the int8
+    tensor cores, bit-exact against the oracle"""
+    from libertem_b200 import masks as M
+    shape = (16, 32, 64, 64)
+    data = (synth.hash_u32(0, int(np.prod(shape)), 111) % 23).astype(np.uint8).reshape(shape)
+    stack = np.stack([M.circular(32, 32, 64, 64, 10), M.ring(32, 32, 64, 64, 30, 20)])
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=2, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.SumUDF(), lt.udf.SumSigUDF(), lt.udf.CoMUDF(),
+                           lt.udf.ApplyMasksUDF(mask_factories=lambda: stack.astype(np.float32))])
+    res = runner.run_for_dataset(ds).buffers
+    assert runner.stats.get('int8_passes', 0) == 2 and runner.stats['unfused_calls'] == 0
+    assert np.array_equal(res[0]['intensity'].data, O.sum_udf(data, num_partitions=2))
+    assert np.array_equal(res[1]['intensity'].raw_data, O.sumsig_udf(data, num_partitions=2))
+    com = O.com_udf(data, num_partitions=2)
+    raw = runner._udfs[2].results.get_buffer('raw_mask_result').raw_data
+    assert np.array_equal(raw, com['raw_mask_result'])             # all sums < 2^24: exact
+    np.testing.assert_allclose(res[2]['raw_com'].raw_data, com['raw_com'], rtol=RTOL)
+    assert np.array_equal(res[3]['intensity'].raw_data,
+                          O.apply_masks(data, stack.astype(np.float32), num_partitions=2))
+
+
 @pytest.mark.parametrize('kind', ['sparse', 'dense'])
 def test_cfg4_small_radial_fourier(lt, kind):
     meta, g = load_golden('cfg4_small_' + kind)
