@@ -49,6 +49,31 @@ def _get_dtype(udfs, dtype, corrections=None):
     return tmp
 
 
+def int8_digit_plan(rows, max_rows=16):
+    """int8 form of a float32 mask stack (M, K) for the integer tensor-core kernel K8, or None.
+
+    Every weight must be an integer.  ``|m| <= 127``: ``(rows as int8, None, None)``.  Up to
+    ``127 * 129``: the wide rows are split into two base-128 digits ``m = d0 + 128 d1`` (both in
+    [-127, 127], ``d1 = trunc(m / 128)``); the high digits are appended as extra rows and the
+    caller adds ``128 x`` their results to the source rows: ``(int8 rows, source row indices,
+    positions of the appended rows)``.  None when the weights are not integers, too large, or
+    the digits do not fit in ``max_rows`` rows."""
+    M = rows.shape[0]
+    amax = rows.abs().amax(dim=1)
+    if not bool((rows == rows.round()).all().item()) or float(amax.max()) > 127 * 129:
+        return None
+    wide = torch.nonzero(amax > 127).reshape(-1)
+    if len(wide) == 0:
+        return (rows.to(torch.int8).contiguous(), None, None)
+    if M + len(wide) > max_rows:
+        return None
+    d1 = torch.trunc(rows[wide] / 128.0)
+    d0 = rows.clone()
+    d0[wide] -= 128.0 * d1
+    i8 = torch.cat([d0, d1]).to(torch.int8).contiguous()
+    return (i8, wide, torch.arange(M, M + len(wide), device=rows.device))
+
+
 class UDFResults:
     def __init__(self, buffers, damage):
         self.buffers = buffers
@@ -480,19 +505,7 @@ class UDFRunner:
         key = (rows.data_ptr(), tuple(rows.shape))
         hit = self._int8_cache.get(key)
         if hit is None:
-            plan = None
-            amax = rows.abs().amax(dim=1)
-            if bool((rows == rows.round()).all().item()) and float(amax.max()) <= 127 * 129:
-                wide = torch.nonzero(amax > 127).reshape(-1)
-                if len(wide) == 0:
-                    plan = (rows.to(torch.int8).contiguous(), None, None)
-                elif M + len(wide) <= 16:
-                    d1 = torch.trunc(rows[wide] / 128.0)
-                    d0 = rows.clone()
-                    d0[wide] -= 128.0 * d1
-                    i8 = torch.cat([d0, d1]).to(torch.int8).contiguous()
-                    plan = (i8, wide, torch.arange(M, M + len(wide), device=rows.device))
-            hit = (plan, rows)                      # keep the source alive (cache key)
+            hit = (int8_digit_plan(rows), rows)      # keep the source alive (cache key)
             self._int8_cache[key] = hit
         return hit[0]
 

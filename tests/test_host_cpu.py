@@ -328,3 +328,32 @@ def test_banded_quad_plan_reconstructs_the_masks():
     assert np.abs(dense - stack).max() <= 2.0 ** -21
     assert gm.default_bands(512 * 512) == 4 and gm.default_bands(64 * 64) == 1
     assert gm.build_banded(stack[:, :4090], size, 4, n_cols) is None     # K % 16 != 0
+
+
+def test_int8_digit_plan():
+    """host side of the integer fast path: which mask stacks K8 takes and how wide integer
+    weights are split into base-128 int8 digits"""
+    from libertem_b200.runner import int8_digit_plan
+    K = 64
+    binary = torch.zeros((3, K))
+    binary[0] = 1
+    binary[1, ::3] = 1
+    binary[2, 5:9] = -127
+    i8, src, pos = int8_digit_plan(binary)
+    assert src is None and pos is None and i8.dtype == torch.int8
+    assert torch.equal(i8.float(), binary)
+    # CoM coordinate rows of a 256-wide detector: 0..255 needs a second digit
+    grad = torch.arange(K, dtype=torch.float32).repeat(2, 1) * 4.0          # 0 .. 252
+    grad[1] = -grad[1] - 16000 + 3                                          # down to -16249
+    stack = torch.cat([binary[:1], grad])
+    i8, src, pos = int8_digit_plan(stack)
+    assert i8.shape == (5, K) and src.tolist() == [1, 2] and pos.tolist() == [3, 4]
+    assert int(i8.abs().max()) <= 127
+    rebuilt = i8[:3].float()
+    rebuilt[src] += 128.0 * i8[pos].float()
+    assert torch.equal(rebuilt, stack)
+    # not representable: fractional weights, too large, too many rows
+    assert int8_digit_plan(stack * 0.5 + 0.25) is None
+    assert int8_digit_plan(stack * 2) is None
+    assert int8_digit_plan(grad[:1].repeat(9, 1)) is None                   # 9 + 9 rows > 16
+    assert int8_digit_plan(grad[:1].repeat(8, 1)) is not None
