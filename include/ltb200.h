@@ -239,6 +239,25 @@ LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, in
                                          int chain, void* workspace, size_t workspace_bytes,
                                          void* stream);
 
+/* Mirror-symmetric plan (EXPERIMENTAL, not yet validated on hardware; off unless the host
+ * sets LTB200_K7_SYM=1): for stacks whose masks obey m(sy - y, x) = conj(m(y, x)) -- the
+ * radial_mask_factory stacks about the default centre -- a stage holds 32 ORBITS: 8 quads of
+ * rows y < sy/2 followed by the 8 mirrored quads (same columns, row sy - y).  The kernel forms
+ * I(p) + I(p') and I(p) - I(p'); the sums meet the real parts of the weights, the differences
+ * the imaginary parts: two MMAs of 64 columns per pixel PAIR instead of two of 112 per pixel,
+ * and a weight table of 128 rows per orbit instead of 112 per pixel.  table_sym is
+ * (128, n_entries / 2) float32: rows [0, 32) hi(Re w_c), [32, 64) lo(Re w_c), [64, 96)
+ * hi(Im w_c), [96, 128) lo(Im w_c) for complex column c, w = the orbit-averaged weight of the
+ * upper pixel.  Same group / band / workspace conventions as ltb200_group_masks_tc_banded; the
+ * rows without a mirror partner (0 and sy/2) go through that entry point with accumulate = 1. */
+LTB_API int ltb200_group_masks_tc_sym(const float* tile, int64_t n_frames, int64_t sig_size,
+                                      int64_t ld_tile, const int32_t* entry_px,
+                                      const float* table_sym, const int32_t* group_off_host,
+                                      const int32_t* group_off_dev, int n_groups, int n_pairs,
+                                      int n_bands, float* out, int64_t ld_out, int accumulate,
+                                      int chain, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Synthetic data (twin of oracle/synth.py): fills dst[0..count) with value(start + i).
  *   LTB_F32: uniform [0,1) (24-bit);  LTB_U16: Poisson(3) counts.

@@ -216,9 +216,9 @@ __device__ __forceinline__ void k7_cp_async_mbar_arrive_noinc(uint64_t* bar) {
 // K7_TSTAGES weight-table stages.  The gathers are latency-bound (every stage is thousands of
 // small copies through L1), so what matters is the number of data stages in flight; the table
 // slices arrive by TMA from L2 and need no depth.
-template <int N>
+template <int NMMA>
 struct K7Smem {
-    static constexpr uint32_t TABLE_BYTES = 2u * N * 128u;                 // two [N x 32] slices
+    static constexpr uint32_t TABLE_BYTES = 2u * NMMA * 128u;              // two [NMMA x 32] slices
     static constexpr uint32_t TABLE_OFF = K7_DSTAGES * K7_DATA_BYTES;
     static constexpr uint32_t BAR_OFF = TABLE_OFF + K7_TSTAGES * TABLE_BYTES;
     static constexpr uint32_t TOTAL = BAR_OFF + 1024 + 1024;               // + alignment slack
@@ -231,15 +231,23 @@ struct K7QItem {
     int pad;
 };
 
-template <int N>
+// SYM (mirror-symmetric plan, N = 128): a stage holds 32 ORBITS -- sub-tile 0 the pixels p,
+// sub-tile 1 their mirror images p' (same columns, row sy - y) -- whose masks obey
+// m(p') = conj(m(p)).  The converters form I(p) + I(p') and I(p) - I(p'); the sums meet the REAL
+// parts of the weights in accumulator columns [0, 64), the differences the IMAGINARY parts in
+// [64, 128): two MMAs of N = 64 per k-step instead of two of N = 112 per pixel pair, and a
+// weight table of 128 rows per orbit instead of 112 per pixel.
+template <int N, bool SYM>
 __global__ void __launch_bounds__(K7_THREADS, 1)
 k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                        const __grid_constant__ CUtensorMap tm_tile, const K7Params p) {
-    using SM = K7Smem<N>;
+    constexpr int NMMA = SYM ? 64 : N;    // columns of one MMA
+    using SM = K7Smem<NMMA>;
     constexpr int NHALF = N / 2;          // accumulator columns drained per converter warp
     constexpr int NQ = N / 4;             // real columns per half
-    constexpr uint32_t IDESC = k7_idesc_tf32(N);
-    static_assert(N % 16 == 0 && N >= 16 && N <= 112, "K7: N in 16..112 step 16");
+    constexpr uint32_t IDESC = k7_idesc_tf32(NMMA);
+    static_assert(N % 16 == 0 && N >= 16 && N <= 128, "K7: N in 16..128 step 16");
+    static_assert(!SYM || N == 128, "K7: the symmetric plan uses 2 x 64 accumulator columns");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -463,8 +471,16 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     const int ebase = qi.e0 + c * K7_KT;
                     tmeta[ts] = K7Meta{qi.item, c, qi.nchunks, 0};
                     mbar_arrive_expect_tx(&tab_full[ts], SM::TABLE_BYTES);
-                    tma_load_2d(dst, &tm_table, ebase, 0, &tab_full[ts], pol_keep);
-                    tma_load_2d(dst + N * 128, &tm_table, ebase + 32, 0, &tab_full[ts], pol_keep);
+                    if constexpr (SYM) {
+                        // 32 orbits: rows [0, 64) = real parts (hi | lo), [64, 128) = imaginary
+                        tma_load_2d(dst, &tm_table, ebase >> 1, 0, &tab_full[ts], pol_keep);
+                        tma_load_2d(dst + NMMA * 128, &tm_table, ebase >> 1, 64, &tab_full[ts],
+                                    pol_keep);
+                    } else {
+                        tma_load_2d(dst, &tm_table, ebase, 0, &tab_full[ts], pol_keep);
+                        tma_load_2d(dst + N * 128, &tm_table, ebase + 32, 0, &tab_full[ts],
+                                    pol_keep);
+                    }
                 }
                 if (qi.item < 0) break;
             }
@@ -490,14 +506,17 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 const int as = st % K7_AS;
                 mbar_wait(&a_full[as], (st / K7_AS) & 1);
                 k7_fence_after();
-                const uint64_t bdesc0 = k7_desc_k_sw128(tbl + (uint32_t)s * N * 128u);
+                const uint64_t bdesc0 = k7_desc_k_sw128(tbl + (uint32_t)s * NMMA * 128u);
                 const uint32_t a0 = tmem_base + (uint32_t)(K7_A_BASE + as * 64);
-                const uint32_t d0 = tmem_base + (uint32_t)(cbuf * N);
+                // SYM: sub-tile 0 (sums) -> columns [0, 64), sub-tile 1 (differences) -> [64, 128);
+                // a chain starts with the first STAGE (both sub-tiles zero-initialise)
+                const uint32_t d0 = tmem_base + (uint32_t)(cbuf * N + (SYM ? s * 64 : 0));
+                const int first = SYM ? (in_chain < 2 ? 0 : 1) : in_chain;
                 if (k7_elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {
                         const uint64_t bdesc = bdesc0 + (uint64_t)(kk * 2);
-                        k7_mma_tf32_ts(d0, a0 + kk * 8, bdesc, IDESC, (in_chain | kk) != 0 ? 1u : 0u);
+                        k7_mma_tf32_ts(d0, a0 + kk * 8, bdesc, IDESC, (first | kk) != 0 ? 1u : 0u);
                         k7_mma_tf32_ts(d0, a0 + 32 + kk * 8, bdesc, IDESC, 1u);
                     }
                     k7_commit(&mma_done[as]);
@@ -573,6 +592,15 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 for (int j = 0; j < 4; j++)
                     asm volatile("" : "+f"(x[s][j].x), "+f"(x[s][j].y), "+f"(x[s][j].z),
                                       "+f"(x[s][j].w)::"memory");
+            if constexpr (SYM) {
+                // butterflies of the mirror pairs: sub-tile 0 <- I(p) + I(p'), 1 <- I(p) - I(p')
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float4 u = x[0][j], v = x[1][j];
+                    x[0][j] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+                    x[1][j] = make_float4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w);
+                }
+            }
             __syncwarp();
             if (lane == 0 && !p.late_release) mbar_arrive(&data_free[stage]);
 #pragma unroll
@@ -626,11 +654,20 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 k7_decode_item(p, m.item, g, fb);
                 const int64_t f = fb * K7_FB + row;
                 if (f < p.n_frames) {
-                    float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2 + hh * NQ;
+                    if constexpr (SYM) {
+                        // warp half hh = 0 holds the real parts, 1 the imaginary parts
+                        float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2 + hh;
 #pragma unroll
-                    for (int c = 0; c < NQ; c++)
-                        if (hh * NQ + c < 2 * p.n_pairs)
-                            o[c] = p.accumulate ? (o[c] + acc[c]) : acc[c];
+                        for (int c = 0; c < NQ; c++)
+                            if (c < p.n_pairs)
+                                o[2 * c] = p.accumulate ? (o[2 * c] + acc[c]) : acc[c];
+                    } else {
+                        float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2 + hh * NQ;
+#pragma unroll
+                        for (int c = 0; c < NQ; c++)
+                            if (hh * NQ + c < 2 * p.n_pairs)
+                                o[c] = p.accumulate ? (o[c] + acc[c]) : acc[c];
+                    }
                 }
             }
         }
@@ -646,11 +683,11 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
     }
 }
 
-template <int N>
+template <int N, bool SYM>
 static int k7_launch(const CUtensorMap& tm, const CUtensorMap& tmt, const K7Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k7_group_tensor_kernel<N>;
-    const size_t smem = K7Smem<N>::TOTAL;
+    auto kern = k7_group_tensor_kernel<N, SYM>;
+    const size_t smem = K7Smem<SYM ? 64 : N>::TOTAL;
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
     static thread_local int configured_dev = -1;
@@ -711,13 +748,16 @@ extern "C" size_t ltb200_group_masks_tc_workspace(int64_t n_frames, int n_groups
 static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
                   const int32_t* entry_px, const float* table_split,
                   const int32_t* group_off_host, const int32_t* group_off_dev, int n_groups,
-                  int n_pairs, int n_bands, int quad_plan, float* out, int64_t ld_out,
+                  int n_pairs, int n_bands, int quad_plan, int sym, float* out, int64_t ld_out,
                   int accumulate, int chain, void* workspace, size_t workspace_bytes,
                   void* stream) {
     LTB_REQUIRE(n_frames >= 0 && sig_size > 0 && n_groups > 0, "group_masks_tc: bad sizes");
     LTB_REQUIRE(n_bands >= 1 && n_groups % n_bands == 0,
                 "group_masks_tc: n_groups must be n_bands x rings");
-    const int n = ltb200_group_masks_tc_columns(n_pairs);
+    LTB_REQUIRE(!sym || quad_plan, "group_masks_tc: the symmetric plan is a quad plan");
+    // symmetric plan: 2 x (hi 32 | lo 32) accumulator columns, table of 128 rows per orbit
+    const int n = sym ? (n_pairs >= 1 && n_pairs <= 28 ? 128 : 0)
+                      : ltb200_group_masks_tc_columns(n_pairs);
     LTB_REQUIRE(n > 0, "group_masks_tc: 1..28 complex columns per group, got %d", n_pairs);
     if (n_frames == 0) return LTB_OK;
     LTB_REQUIRE(tile && entry_px && table_split && group_off_host && group_off_dev && out,
@@ -737,9 +777,12 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     LTB_REQUIRE(n_entries > 0 && n_entries % 4 == 0, "group_masks_tc: empty entry list");
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tm;
-    int rc = encode_tmap_2d_sw(&tm, table_split, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                               (uint64_t)n_entries, (uint64_t)n, (uint64_t)n_entries * 4, 32,
-                               (uint32_t)n, CU_TENSOR_MAP_SWIZZLE_128B);
+    // table: (n, n_entries) floats; symmetric plan: (128, n_entries / 2) -- one column per orbit,
+    // fetched as two [64 x 32] boxes (real rows, imaginary rows) per stage
+    const uint64_t tcols = sym ? (uint64_t)n_entries / 2 : (uint64_t)n_entries;
+    int rc = encode_tmap_2d_sw(&tm, table_split, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tcols,
+                               (uint64_t)n, tcols * 4, 32, (uint32_t)(sym ? 64 : n),
+                               CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
     const bool banded = n_bands > 1;     // band partial sums + reduction
     const bool quad = quad_plan != 0;    // entry_px lists quads (16-byte gathers)
@@ -763,6 +806,7 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     if (chain <= 0)
         if (const char* e = getenv("LTB200_K7_CHAIN"))
             if (atoi(e) > 0) p.chain = atoi(e);
+    if (sym) p.chain = ((p.chain + 1) / 2) * 2;     // whole stages per chain
     p.rgroup = 4;
     if (const char* e = getenv("LTB200_K7_RGROUP"))
         if (atoi(e) > 0) p.rgroup = atoi(e);
@@ -810,11 +854,12 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     }
     int grid = sm_count();
     if (p.n_items < grid) grid = (int)p.n_items;
-    switch (n) {
-        case 16: rc = k7_launch<16>(tm, tmt, p, grid, st); break;
-        case 32: rc = k7_launch<32>(tm, tmt, p, grid, st); break;
-        case 64: rc = k7_launch<64>(tm, tmt, p, grid, st); break;
-        default: rc = k7_launch<112>(tm, tmt, p, grid, st); break;
+    switch (sym ? 128 : n) {
+        case 16: rc = k7_launch<16, false>(tm, tmt, p, grid, st); break;
+        case 32: rc = k7_launch<32, false>(tm, tmt, p, grid, st); break;
+        case 64: rc = k7_launch<64, false>(tm, tmt, p, grid, st); break;
+        case 128: rc = k7_launch<128, true>(tm, tmt, p, grid, st); break;
+        default: rc = k7_launch<112, false>(tm, tmt, p, grid, st); break;
     }
     if (rc != LTB_OK) return rc;
     if (banded) {
@@ -839,7 +884,19 @@ extern "C" int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames,
                                             int accumulate, int chain, void* workspace,
                                             size_t workspace_bytes, void* stream) {
     return k7_run(tile, n_frames, sig_size, ld_tile, entry_px, table_split, group_off_host,
-                  group_off_dev, n_groups, n_pairs, n_bands, 1, out, ld_out, accumulate, chain,
+                  group_off_dev, n_groups, n_pairs, n_bands, 1, 0, out, ld_out, accumulate, chain,
+                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int ltb200_group_masks_tc_sym(const float* tile, int64_t n_frames, int64_t sig_size,
+                                         int64_t ld_tile, const int32_t* entry_px,
+                                         const float* table_sym, const int32_t* group_off_host,
+                                         const int32_t* group_off_dev, int n_groups, int n_pairs,
+                                         int n_bands, float* out, int64_t ld_out, int accumulate,
+                                         int chain, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    return k7_run(tile, n_frames, sig_size, ld_tile, entry_px, table_sym, group_off_host,
+                  group_off_dev, n_groups, n_pairs, n_bands, 1, 1, out, ld_out, accumulate, chain,
                   workspace, workspace_bytes, stream);
 }
 
@@ -850,6 +907,6 @@ extern "C" int ltb200_group_masks_tc(const float* tile, int64_t n_frames, int64_
                                      float* out, int64_t ld_out, int accumulate, int chain,
                                      void* workspace, size_t workspace_bytes, void* stream) {
     return k7_run(tile, n_frames, sig_size, ld_tile, entry_px, table_split, group_off_host,
-                  group_off_dev, n_groups, n_pairs, 1, 0, out, ld_out, accumulate, chain,
+                  group_off_dev, n_groups, n_pairs, 1, 0, 0, out, ld_out, accumulate, chain,
                   workspace, workspace_bytes, stream);
 }

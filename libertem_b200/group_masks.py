@@ -65,10 +65,13 @@ class GroupPlan:
         #: dict(n_bands, entry_px, table_split, group_off_host, group_off_dev, n_groups)
         self.banded = banded
         self._band_ws = None
+        #: experimental mirror-symmetric plan (dict(main=..., rest=...)) or None
+        self.sym = None
 
-    def band_workspace(self, n_frames):
+    def band_workspace(self, n_frames, which=None):
+        which = self.banded if which is None else which
         need = get_lib().ltb200_group_masks_tc_workspace(
-            n_frames, self.banded['n_groups'], self.n_pairs, self.banded['n_bands'])
+            n_frames, which['n_groups'], self.n_pairs, which['n_bands'])
         if self._band_ws is None or self._band_ws.numel() < need:
             self._band_ws = torch.zeros(need, dtype=torch.uint8, device=self.entry_px.device)
         return self._band_ws
@@ -103,6 +106,10 @@ def pack_rows(table):
 
 
 TC_KT = 64                        # entries per stage of the tensor-core kernel (K7_KT)
+#: EXPERIMENTAL mirror-symmetric plan (ltb200_group_masks_tc_sym): written without access to
+#: the hardware, validated only through its CPU emulation (tests/test_host_cpu.py); off by
+#: default until it has passed tests/test_k4_gpu.py::test_group_masks_sym on a B200
+SYM_PATH = os.environ.get('LTB200_K7_SYM', '0') == '1'
 #: frame-stream bytes of one band of one 128-frame block aimed at by the band count (a handful
 #: of frame blocks x this must stay L2-resident together with the band's weight-table slices)
 BAND_TARGET_BYTES = 32 << 20
@@ -155,9 +162,91 @@ def build_banded(flat, group_size, n_bands, n_cols):
                 group_off=np.array(offs, dtype=np.int32))
 
 
+def split_table_sym(avg):
+    """(pairs <= 28, n_orbits) complex orbit-averaged weights -> the (128, n_orbits) table of the
+    symmetric kernel: rows [0, 32) hi(Re), [32, 64) lo(Re), [64, 96) hi(Im), [96, 128) lo(Im)"""
+    pairs, n = avg.shape
+    out = np.zeros((128, n), dtype=np.float32)
+    for part, base in ((np.ascontiguousarray(avg.real, dtype=np.float32), 0),
+                       (np.ascontiguousarray(avg.imag, dtype=np.float32), 64)):
+        hi = tf32_round(part)
+        out[base:base + pairs] = hi
+        out[base + 32:base + 32 + pairs] = tf32_round(part - hi)
+    return out
+
+
+#: largest |m(sy - y, x) - conj(m(y, x))| for which a stack counts as mirror-symmetric (the
+#: reference's complex64 radial masks: 1.1e-5, mean 7e-11)
+SYM_TOL = 2e-5
+
+
+def build_sym(stack3, group_size, n_bands):
+    """Mirror-symmetric plan of the tensor-core kernel (EXPERIMENTAL, ltb200_group_masks_tc_sym)
+    for a (M, sy, sx) complex stack with m(sy - y, x) = conj(m(y, x)), or None.
+
+    Orbits are pixel pairs {(y, x), (sy - y, x)}, 1 <= y < sy/2.  Groups are (row band of the
+    upper half, ring) pairs, band-major.  Per stage of 64 entries the quad list holds 8 upper
+    quads followed by their 8 mirrored quads; the weight table has one column per orbit (32 per
+    stage) with the orbit-averaged weight (m(p) + conj(m(p'))) / 2 of the upper pixel.  Rows 0
+    and sy/2 have no partner: ``residual`` is a boolean (sy, sx) map of the pixels the caller
+    must still run through the ordinary quad plan."""
+    M, sy, sx = stack3.shape
+    if sy % 2 or sx % 4 or sy < 4 or group_size > 28:
+        return None
+    cy = sy // 2
+    n_rings = M // group_size
+    up = stack3[:, 1:cy, :]
+    dn = stack3[:, sy - 1:cy:-1, :]                # row sy - y for y = 1 .. cy - 1
+    if np.abs(dn - np.conj(up)).max() > SYM_TOL:
+        return None
+    avg = ((up.astype(np.complex128) + np.conj(dn.astype(np.complex128))) / 2)
+    rows_up = cy - 1
+    n_bands = max(1, min(n_bands, rows_up))
+    edges = [1 + (b * rows_up) // n_bands for b in range(n_bands + 1)]     # rows of band b
+    quad_list, tabs, offs = [], [], [0]
+    supports = []
+    for g in range(n_rings):
+        rows = avg[g * group_size:(g + 1) * group_size]                    # (size, cy-1, sx)
+        yy, xx = np.nonzero(np.any(rows != 0, axis=0))
+        q = np.unique((yy + 1) * (sx // 4) + xx // 4)                      # quad id = y * sx/4 + x/4
+        supports.append((rows, q))
+    for b in range(n_bands):
+        for rows, q_all in supports:
+            qy = q_all // (sx // 4)
+            q = q_all[(qy >= edges[b]) & (qy < edges[b + 1])]
+            nq = len(q)
+            nq_pad = ((nq + 7) // 8) * 8
+            qp = np.zeros(nq_pad, dtype=np.int64)
+            qp[:nq] = q
+            if nq:
+                qp[nq:] = q[-1]
+            y, x0 = qp // (sx // 4), (qp % (sx // 4)) * 4
+            upper = (y * sx + x0).astype(np.int32)
+            lower = ((sy - y) * sx + x0).astype(np.int32)
+            # per stage: 8 upper quads, then their 8 mirror images
+            quads = np.concatenate([upper.reshape(-1, 8), lower.reshape(-1, 8)], axis=1)
+            quad_list.append(quads.reshape(-1))
+            tab = np.zeros((rows.shape[0], 4 * nq_pad), dtype=np.complex128)
+            if nq:
+                px_y = np.repeat(y[:nq], 4) - 1                            # row index into avg
+                px_x = (x0[:nq, None] + np.arange(4)[None, :]).reshape(-1)
+                tab[:, :4 * nq] = rows[:, px_y, px_x]
+            tabs.append(tab)
+            offs.append(offs[-1] + 8 * nq_pad)                             # entries: 2 x 4 per quad
+    if offs[-1] == 0:
+        return None
+    residual = np.zeros((sy, sx), dtype=bool)
+    residual[[0, cy], :] = True
+    return dict(n_bands=n_bands, n_groups=n_bands * n_rings,
+                entry_px=np.concatenate(quad_list).astype(np.int32),
+                table_sym=split_table_sym(np.concatenate(tabs, axis=1)),
+                group_off=np.array(offs, dtype=np.int32), residual=residual)
+
+
 def build_plan(stack, group_size, device, n_bands=None):
     """stack: complex (M, *sig) dense array with M = n_groups * group_size"""
     M = stack.shape[0]
+    sig_shape = tuple(np.asarray(stack).shape[1:])
     flat = np.asarray(stack).reshape(M, -1).astype(np.complex64)
     n_groups = M // group_size
     assert n_groups * group_size == M and group_size <= MAX_PAIRS
@@ -198,8 +287,30 @@ def build_plan(stack, group_size, device, n_bands=None):
                           table_split=torch.from_numpy(b['table_split']).to(device),
                           group_off_host=b['group_off'],
                           group_off_dev=torch.from_numpy(b['group_off']).to(device))
-    return GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
+    plan = GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
                      group_size, M, device, table_split=split, n_cols=n_cols, banded=banded)
+    if SYM_PATH and banded is not None and len(sig_shape) == 2:
+        plan.sym = _sym_to_device(flat, sig_shape, group_size, max(1, n_bands // 2), n_cols,
+                                  device)
+    return plan
+
+
+def _sym_to_device(flat, sig_shape, group_size, n_bands, n_cols, device):
+    """device form of build_sym + the ordinary quad plan of the rows without a mirror partner"""
+    sy, sx = sig_shape
+    b = build_sym(flat.reshape(-1, sy, sx), group_size, n_bands)
+    if b is None:
+        return None
+    keep = b['residual'].reshape(-1)
+    rest = build_banded(np.where(keep[None, :], flat, 0), group_size, 1, n_cols)
+
+    def dev(d, table_key):
+        return dict(n_bands=d['n_bands'], n_groups=d['n_groups'],
+                    entry_px=torch.from_numpy(d['entry_px']).to(device),
+                    table=torch.from_numpy(d[table_key]).to(device),
+                    group_off_host=d['group_off'],
+                    group_off_dev=torch.from_numpy(d['group_off']).to(device))
+    return dict(main=dev(b, 'table_sym'), rest=None if rest is None else dev(rest, 'table_split'))
 
 
 #: frames from which the tensor-core kernel (128-frame items) is preferred over the FFMA2 one
@@ -226,9 +337,9 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     real = torch.view_as_real(out).reshape(F, 2 * plan.n_masks)
     ld_tile = tile.stride(0) if F > 1 else max(K, 1)
     ld_out = real.stride(0) if F > 1 else max(2 * plan.n_masks, 1)
-    use_tc = kernel in ('tc', 'banded') or (kernel == 'auto' and F >= TC_MIN_FRAMES)
+    use_tc = kernel in ('tc', 'banded', 'sym') or (kernel == 'auto' and F >= TC_MIN_FRAMES)
     if use_tc and plan.table_split is None:
-        if kernel in ('tc', 'banded'):
+        if kernel in ('tc', 'banded', 'sym'):
             raise _lib.LTB200Error('no tensor-core table for this plan')
         use_tc = False
     if kernel == 'banded' and plan.banded is None:
@@ -236,6 +347,27 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     aligned = tile.data_ptr() % 16 == 0 and ld_tile % 4 == 0
     if kernel == 'banded' and not aligned:
         raise _lib.LTB200Error('the banded plan needs 16-byte aligned frame rows')
+    if kernel == 'sym' and plan.sym is None:
+        raise _lib.LTB200Error('no mirror-symmetric plan (LTB200_K7_SYM=1 and a symmetric stack)')
+    if use_tc and plan.sym is not None and aligned and kernel in ('sym', 'auto'):
+        stream = torch.cuda.current_stream(tile.device).cuda_stream
+        with torch.cuda.device(tile.device):
+            m = plan.sym['main']
+            ws = plan.band_workspace(F, m)
+            check(lib.ltb200_group_masks_tc_sym(
+                tile.data_ptr(), F, K, ld_tile, m['entry_px'].data_ptr(), m['table'].data_ptr(),
+                m['group_off_host'].ctypes.data, m['group_off_dev'].data_ptr(), m['n_groups'],
+                plan.n_pairs, m['n_bands'], real.data_ptr(), ld_out, int(bool(accumulate)),
+                int(chain), ws.data_ptr(), ws.numel(), stream))
+            r = plan.sym['rest']
+            if r is not None:
+                ws = plan.band_workspace(F, r)
+                check(lib.ltb200_group_masks_tc_banded(
+                    tile.data_ptr(), F, K, ld_tile, r['entry_px'].data_ptr(),
+                    r['table'].data_ptr(), r['group_off_host'].ctypes.data,
+                    r['group_off_dev'].data_ptr(), r['n_groups'], plan.n_pairs, r['n_bands'],
+                    real.data_ptr(), ld_out, 1, int(chain), ws.data_ptr(), ws.numel(), stream))
+        return out
     if use_tc and plan.banded is not None and aligned and kernel in ('banded', 'auto'):
         b = plan.banded
         ws = plan.band_workspace(F)

@@ -357,3 +357,68 @@ def test_int8_digit_plan():
     assert int8_digit_plan(stack * 2) is None
     assert int8_digit_plan(grad[:1].repeat(9, 1)) is None                   # 9 + 9 rows > 16
     assert int8_digit_plan(grad[:1].repeat(8, 1)) is not None
+
+
+def _emulate_quad_plan(b, data, n_rings, size, n_cols):
+    """what K7 computes from a banded quad plan (gather 4 px per quad, weights = hi + lo)"""
+    off, quad_px, table = b['group_off'], b['entry_px'], b['table_split']
+    nq = n_cols // 4
+    out = np.zeros((data.shape[0], n_rings * size), dtype=np.complex128)
+    for gidx in range(b['n_groups']):
+        ring = gidx % n_rings
+        for e in range(off[gidx], off[gidx + 1]):
+            x = data[:, quad_px[e // 4] + e % 4].astype(np.float64)
+            for r in range(2 * size):
+                h, j = divmod(r, nq)
+                w = float(table[h * 2 * nq + j, e]) + float(table[h * 2 * nq + nq + j, e])
+                out[:, ring * size + r // 2] += x * w * (1j if r % 2 else 1.0)
+    return out
+
+
+def test_mirror_symmetric_plan_emulation():
+    """host plan of the experimental mirror-symmetric kernel (group_masks.build_sym), emulated
+    stage by stage exactly as the kernel walks it: 8 upper quads + their 8 mirror images per
+    stage, float32 butterflies, real weights on the sums and imaginary weights on the
+    differences, one table column per orbit; plus the rows without a partner through the
+    ordinary quad plan.  Must reproduce the direct sum over the reference's radial masks."""
+    from libertem_b200 import group_masks as gm
+    from libertem_b200.analysis.radialfourier import radial_mask_factory
+    S, n_bins, max_order = 32, 4, 6
+    size = max_order + 1
+    ro = M.bounding_radius(S / 2, S / 2, S, S)
+    stack = np.asarray(radial_mask_factory(S, S, S / 2, S / 2, 0, ro, n_bins, max_order,
+                                           use_sparse=False)()).astype(np.complex64)
+    assert stack.shape == (n_bins * size, S, S)
+    b = gm.build_sym(stack, size, n_bands=3)
+    assert b is not None and b['n_groups'] == 3 * n_bins
+    off, quads, T = b['group_off'], b['entry_px'], b['table_sym']
+    assert np.all(off % gm.TC_KT == 0) and off[-1] == 4 * len(quads) and T.shape == (128, off[-1] // 2)
+    assert np.all(quads % 4 == 0)
+    F = 5
+    data = np.random.default_rng(3).random((F, S * S), dtype=np.float32)
+    out = np.zeros((F, n_bins * size), dtype=np.complex128)
+    for gidx in range(b['n_groups']):
+        ring = gidx % n_bins
+        for k in range((off[gidx + 1] - off[gidx]) // 64):
+            q0 = off[gidx] // 4 + 16 * k
+            upper, lower = quads[q0:q0 + 8], quads[q0 + 8:q0 + 16]
+            assert np.all(lower // S == S - upper // S) and np.all(lower % S == upper % S)
+            px_u = (upper[:, None] + np.arange(4)[None, :]).reshape(-1)
+            px_l = (lower[:, None] + np.arange(4)[None, :]).reshape(-1)
+            s = (data[:, px_u] + data[:, px_l]).astype(np.float64)        # float32 butterflies
+            d = (data[:, px_u] - data[:, px_l]).astype(np.float64)
+            col0 = off[gidx] // 2 + 32 * k
+            t = T[:, col0:col0 + 32].astype(np.float64)
+            for c in range(size):
+                out[:, ring * size + c] += s @ (t[c] + t[32 + c]) + 1j * (d @ (t[64 + c] + t[96 + c]))
+    rest = gm.build_banded(np.where(b['residual'].reshape(-1)[None, :], stack.reshape(-1, S * S), 0),
+                           size, 1, 32)
+    out += _emulate_quad_plan(rest, data, n_bins, size, 32)
+    ref = data.astype(np.float64) @ stack.reshape(-1, S * S).astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(stack.reshape(-1, S * S)).astype(np.float64).T).max()
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    # a stack without the symmetry has no such plan
+    broken = stack.copy()
+    broken[3, 5, 7] += 0.5
+    assert gm.build_sym(broken, size, 3) is None
+    assert gm.build_sym(stack[:, :31, :], size, 3) is None

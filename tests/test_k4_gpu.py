@@ -105,6 +105,33 @@ def test_group_masks_banded(F, K, n_groups, size, n_bands):
     assert np.array_equal(out4, out)              # schedule does not change the arithmetic
 
 
+@pytest.mark.skipif(__import__('os').environ.get('LTB200_K7_SYM') != '1',
+                    reason='experimental mirror-symmetric plan: run with LTB200_K7_SYM=1')
+@pytest.mark.parametrize('S,n_bins,max_order,F', [(64, 4, 6, 300), (128, 8, 24, 1000)])
+def test_group_masks_sym(S, n_bins, max_order, F):
+    """mirror-symmetric plan of K7 on the reference's radial masks: same result as the banded
+    quad plan and as numpy float64"""
+    from libertem_b200 import group_masks as gm, masks as M
+    from libertem_b200.analysis.radialfourier import radial_mask_factory
+    ro = M.bounding_radius(S / 2, S / 2, S, S)
+    stack = np.asarray(radial_mask_factory(S, S, S / 2, S / 2, 0, ro, n_bins, max_order,
+                                           use_sparse=False)()).astype(np.complex64)
+    plan = gm.build_plan(stack, max_order + 1, torch.device('cuda'), n_bands=2)
+    assert plan.sym is not None
+    data = synth.uniform_f32(0, F * S * S, 12).reshape(F, S * S)
+    t = torch.from_numpy(data).cuda()
+    out = gm.group_masks(t, plan, kernel='sym').cpu().numpy()
+    flat = stack.reshape(stack.shape[0], -1)
+    ref = data.astype(np.float64) @ flat.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(flat).astype(np.float64).T).max() + 1e-30
+    assert np.abs(out - ref).max() / scale <= 3e-6
+    banded = gm.group_masks(t, plan, kernel='banded').cpu().numpy()
+    assert np.abs(out - banded).max() / scale <= 3e-6
+    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True,
+                          kernel='sym').cpu().numpy()
+    assert np.abs(out2 - 2 * ref).max() / scale <= 6e-6
+
+
 def test_split_table_layout():
     from libertem_b200 import group_masks as gm
     rng = np.random.default_rng(5)
