@@ -216,7 +216,14 @@ class MaskContainer:
             support = np.any(stack.reshape(stack.shape[0] // size, size, -1) != 0, axis=1)
             # worth it when the gathered entries are few compared with columns x pixels
             if np.count_nonzero(support) * size < 0.5 * stack.shape[0] * stack.shape[1]:
-                plan = gm.build_plan(stack, size, device)
+                # (the 2D signal shape lets the builder look for mirror symmetry, full frames only)
+                try:
+                    sig_shape = tuple(int(v) for v in slice_.shape)
+                    if any(int(o) != 0 for o in slice_.origin):
+                        sig_shape = None
+                except (AttributeError, TypeError):
+                    sig_shape = None
+                plan = gm.build_plan(stack, size, device, sig_shape=sig_shape)
         self._device_cache[key] = plan
         return plan
 

@@ -243,11 +243,16 @@ def build_sym(stack3, group_size, n_bands):
                 group_off=np.array(offs, dtype=np.int32), residual=residual)
 
 
-def build_plan(stack, group_size, device, n_bands=None):
-    """stack: complex (M, *sig) dense array with M = n_groups * group_size"""
+def build_plan(stack, group_size, device, n_bands=None, sig_shape=None):
+    """stack: complex (M, *sig) dense array with M = n_groups * group_size (``sig_shape`` gives
+    the 2D signal shape when the stack comes flattened)"""
     M = stack.shape[0]
-    sig_shape = tuple(np.asarray(stack).shape[1:])
+    if sig_shape is None:
+        sig_shape = tuple(np.asarray(stack).shape[1:])
+    sig_shape = tuple(int(v) for v in sig_shape)
     flat = np.asarray(stack).reshape(M, -1).astype(np.complex64)
+    if int(np.prod(sig_shape)) != flat.shape[1]:
+        sig_shape = (flat.shape[1],)
     n_groups = M // group_size
     assert n_groups * group_size == M and group_size <= MAX_PAIRS
     px_list, offs = [], [0]
