@@ -26,7 +26,8 @@
 // 1 mask-tile TMA, 2 MMA issuer (warp-uniform loop, one elected lane), 3 TMEM allocation,
 // 4..7 drain (per stage: the 128 byte sums -> 64 pixel sums -> 64-bit RED into the frame-sum
 // accumulator; per item: the (256 frames x columns) block).  int32 accumulation is exact:
-// |L|, |H| <= 255 * 127 * sig_size < 2^31 for sig_size <= 65536 (checked on the host).
+// |L|, |H| <= 255 * 127 * 65536 < 2^31 per K split of <= 65536 pixels (larger signals are split on
+// the host side of the call and recombined as int64).
 #include "common.cuh"
 #include <cstdlib>
 
@@ -489,11 +490,19 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// K split: enough items for the SMs, and never more than K8_MAX_SPLIT_PX pixels per split so
+// that the int32 accumulators stay exact (255 * 127 * 65536 < 2^31); the splits are recombined
+// as int64 (k8_finalize_kernel)
+constexpr int64_t K8_MAX_SPLIT_PX = 65536;
+constexpr int64_t K8_MAX_SIG = K8_MAX_SPLIT_PX * 64;
+
 static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms, int px) {
-    int best = 1;
+    int ks0 = 1;
+    while ((int64_t)ks0 * K8_MAX_SPLIT_PX < sig_size) ks0 *= 2;      // exactness: forced splits
+    int best = ks0;
     double best_eff = 0.0;
-    for (int ks = 1; ks <= 64; ks *= 2) {
-        if (ks > 1 && sig_size / ks < 16 * px) break;
+    for (int ks = ks0; ks <= 64; ks *= 2) {
+        if (ks > ks0 && sig_size / ks < 16 * px) break;
         const int64_t items = n_fb * ks;
         const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
         if (eff > best_eff + 1e-9) {
@@ -550,11 +559,11 @@ static int k8_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K8Par
 
 static bool k8_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile,
                         int n_masks, int bpp) {
-    // 16-byte aligned rows for the TMA; 255 * 127 * sig_size < 2^31 keeps the int32
-    // accumulators exact
+    // 16-byte aligned rows for the TMA; signals beyond 65536 pixels are K-split so that the
+    // int32 accumulators stay exact
     const int align = 16 / bpp;
     return sig_size % align == 0 && ld_tile % align == 0 && (uintptr_t)tile % 16 == 0 &&
-           sig_size >= 4 * (128 / bpp) && sig_size <= 65536 && n_frames >= 1 &&
+           sig_size >= 4 * (128 / bpp) && sig_size <= K8_MAX_SIG && n_frames >= 1 &&
            n_frames < (1ll << 31) && n_masks >= 1 && n_masks <= K8_MAX_COLUMNS;
 }
 
@@ -588,8 +597,8 @@ extern "C" int ltb200_masks_dense_i8(const void* tile, int tile_dtype, int64_t n
     if (!k8_shape_ok(tile, n_frames, sig_size, ld_tile, n_masks, bpp)) {
         set_error("masks_dense_i8: shape not supported by the int8 tensor-core path (sig_size "
                   "%lld, ld_tile %lld, %d columns; need 16-byte aligned rows, %d <= sig_size <= "
-                  "65536, 1..%d columns)", (long long)sig_size, (long long)ld_tile, n_masks,
-                  4 * px, K8_MAX_COLUMNS);
+                  "%lld, 1..%d columns)", (long long)sig_size, (long long)ld_tile, n_masks,
+                  4 * px, (long long)K8_MAX_SIG, K8_MAX_COLUMNS);
         return LTB_ERR_UNSUPPORTED;
     }
     const K8Ws wl = k8_ws(n_frames, sig_size, n_masks, bpp, sig_sum != nullptr);
