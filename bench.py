@@ -231,6 +231,33 @@ def reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 
+def _bind_near_gpu(torch, local_rank):
+    """Multi-GPU runs: pin this rank to the CPUs NVML names for its GPU, so that the pinned host
+    buffers of the e2e leg (first touch) and the copy threads sit on the GPU's NUMA node
+    instead of wherever torchrun started the process.  Returns the number of CPUs or None."""
+    if os.environ.get('LTB200_NO_AFFINITY') == '1' or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local_rank)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {i for i in range(n_cpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def gpu_arm(args):
     import logging
     logging.getLogger('libertem_b200').setLevel(logging.ERROR)
@@ -249,7 +276,9 @@ def gpu_arm(args):
                            'for the CPU arm)')
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    cpu_affinity = None
     if world > 1:
+        cpu_affinity = _bind_near_gpu(torch, local_rank)
         dist.init_process_group('nccl', device_id=device)
     n_gpus = world
 
@@ -362,7 +391,8 @@ def gpu_arm(args):
                    'l2': 'inputs %.1f GB per GPU >> 126 MB L2, streamed once per step' %
                          (frames_per_rank * k * 4 / 1e9),
                    'merge': 'nccl all_gather of nav buffers inside the step' if world > 1
-                   else 'device-side copy into the nav-shaped buffers'},
+                   else 'device-side copy into the nav-shaped buffers',
+                   'cpu_affinity': cpu_affinity},
         'hbm_gbs': total_frames * k * 4 / (ms_per_step * 1e-3) / 1e9 / n_gpus,
         'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches),
     }
