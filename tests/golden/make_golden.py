@@ -345,6 +345,40 @@ def g_corrections():
                              excluded=[(0, 0), (3, 4), (3, 5), (15, 11), (8, 0), (9, 7)]), **out)
 
 
+def g_int_detector():
+    # integer detectors (the inputs of the int8 tensor-core path of libertem_b200): CoM with a
+    # disk, SumUDF, SumSigUDF and two binary masks on uint16 (256x256) and uint8 (64x64) frames
+    cases = {
+        'u16': dict(shape=(16, 64, 256, 256), dtype=np.uint16, seed=109,
+                    com=dict(cy=120, cx=131, r=100),
+                    masks=lambda: np.stack([M.circular(128, 128, 256, 256, 40),
+                                            M.ring(128, 128, 256, 256, 90, 60)])),
+        'u8': dict(shape=(16, 32, 64, 64), dtype=np.uint8, seed=111, com=dict(),
+                   masks=lambda: np.stack([M.circular(32, 32, 64, 64, 10),
+                                           M.ring(32, 32, 64, 64, 30, 20)])),
+    }
+    for name, c in cases.items():
+        shape = c['shape']
+        if c['dtype'] == np.uint16:
+            data = synth.dataset(shape, np.uint16, seed=c['seed'])
+        else:
+            data = (synth.hash_u32(0, int(np.prod(shape)), c['seed']) % 23).astype(
+                np.uint8).reshape(shape)
+        stack = c['masks']().astype(np.float32)
+        kw = dict(data=data, num_partitions=2, sig_dims=2)
+        _, bufs = run(kw, [CoMUDF.with_params(**c['com']), SumUDF(), SumSigUDF(),
+                           ApplyMasksUDF(mask_factories=lambda: stack, mask_count=2,
+                                         mask_dtype=np.float32, use_sparse=False)])
+        arrays = {'com_' + k: bufs[0][k].raw_data for k in COM_KEYS}
+        arrays['com_raw_mask_result'] = com_raw(kw, cy=c['com'].get('cy'), cx=c['com'].get('cx'),
+                                                r=c['com'].get('r', float('inf')))
+        arrays['sum'] = bufs[1]['intensity'].data
+        arrays['sumsig'] = bufs[2]['intensity'].raw_data
+        arrays['intensity'] = bufs[3]['intensity'].raw_data
+        save('int_detector_' + name, dict(shape=shape, data_seed=c['seed'], com=c['com'],
+                                          num_partitions=2), **arrays)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or None
     for name, fn in list(globals().items()):

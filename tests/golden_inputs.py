@@ -32,3 +32,18 @@ def roi_from_seed(nav_shape, seed):
 def ring_stack(sig_shape, rings, cy, cx):
     sy, sx = sig_shape
     return np.stack([masks_gen.ring(cx, cy, sx, sy, ro, ri) for ri, ro in rings])
+
+
+def int_detector_inputs(name, meta):
+    """data and binary mask stack of the integer-detector goldens (make_golden.g_int_detector)"""
+    shape = tuple(meta['shape'])
+    if name == 'u16':
+        data = synth.dataset(shape, np.uint16, meta['data_seed'])
+        stack = np.stack([masks_gen.circular(128, 128, 256, 256, 40),
+                          masks_gen.ring(128, 128, 256, 256, 90, 60)])
+    else:
+        data = (synth.hash_u32(0, int(np.prod(shape)), meta['data_seed']) % 23).astype(
+            np.uint8).reshape(shape)
+        stack = np.stack([masks_gen.circular(32, 32, 64, 64, 10),
+                          masks_gen.ring(32, 32, 64, 64, 30, 20)])
+    return data, stack.astype(np.float32)

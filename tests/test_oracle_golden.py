@@ -244,3 +244,23 @@ def test_corrections(dt):
         assert (np.abs(folded - g[key + 'intensity']) / scale).max() <= 1e-6
         fs = cs.correct_frame_sum(data.reshape(20, -1).astype(np.float64).sum(0), 20)
         np.testing.assert_allclose(fs.reshape(16, 12), g[key + 'sum'], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('name', ['u16', 'u8'])
+def test_int_detector(name):
+    """integer detectors (uint16 / uint8 frames, binary masks, CoM with a disk): the oracle
+    reproduces the unmodified reference bit for bit -- every sum is an exact integer in
+    float32 -- which is what the int8 tensor-core path of the product is held to"""
+    from golden_inputs import int_detector_inputs
+    meta, g = load_golden('int_detector_' + name)
+    data, stack = int_detector_inputs(name, meta)
+    P = meta['num_partitions']
+    assert np.array_equal(O.sum_udf(data, num_partitions=P), g['sum'])
+    assert np.array_equal(O.sumsig_udf(data, num_partitions=P), g['sumsig'])
+    assert np.array_equal(O.apply_masks(data, stack, num_partitions=P), g['intensity'])
+    com = O.com_udf(data, num_partitions=P, **meta['com'])
+    assert np.array_equal(com['raw_mask_result'], g['com_raw_mask_result'])
+    for k in ('raw_com', 'raw_shifts', 'field', 'field_y', 'field_x', 'magnitude',
+              'divergence', 'curl', 'regression'):
+        assert com[k].dtype == g['com_' + k].dtype and com[k].shape == g['com_' + k].shape, k
+        np.testing.assert_allclose(com[k], g['com_' + k], rtol=1e-6, atol=1e-6, err_msg=k)

@@ -182,6 +182,15 @@ def test_com_u16_int8_tensor_path(lt):
     assert np.array_equal(res[2]['intensity'].raw_data,
                           O.apply_masks(data, stack.astype(np.float32), num_partitions=2))
     assert np.array_equal(res[3]['intensity'].data, O.sum_udf(data, num_partitions=2))
+    # and against the unmodified reference (tests/golden/int_detector_u16.npz, same inputs)
+    meta, g = load_golden('int_detector_u16')
+    assert tuple(meta['shape']) == shape and meta['com'] == dict(cy=120, cx=131, r=100)
+    assert np.array_equal(raw[:, 0], g['com_raw_mask_result'][:, 0])
+    np.testing.assert_allclose(raw, g['com_raw_mask_result'], rtol=1e-6)
+    np.testing.assert_allclose(res[0]['raw_com'].raw_data, g['com_raw_com'], rtol=RTOL)
+    assert np.array_equal(res[1]['intensity'].raw_data, g['sumsig'])
+    assert np.array_equal(res[2]['intensity'].raw_data, g['intensity'])
+    assert np.array_equal(res[3]['intensity'].data, g['sum'])
 
 
 def test_u8_int8_tensor_path(lt):
@@ -204,6 +213,14 @@ def test_u8_int8_tensor_path(lt):
     np.testing.assert_allclose(res[2]['raw_com'].raw_data, com['raw_com'], rtol=RTOL)
     assert np.array_equal(res[3]['intensity'].raw_data,
                           O.apply_masks(data, stack.astype(np.float32), num_partitions=2))
+    # and against the unmodified reference (tests/golden/int_detector_u8.npz, same inputs)
+    meta, g = load_golden('int_detector_u8')
+    assert tuple(meta['shape']) == shape
+    assert np.array_equal(res[0]['intensity'].data, g['sum'])
+    assert np.array_equal(res[1]['intensity'].raw_data, g['sumsig'])
+    assert np.array_equal(raw, g['com_raw_mask_result'])
+    np.testing.assert_allclose(res[2]['raw_com'].raw_data, g['com_raw_com'], rtol=RTOL)
+    assert np.array_equal(res[3]['intensity'].raw_data, g['intensity'])
 
 
 @pytest.mark.parametrize('kind', ['sparse', 'dense'])
