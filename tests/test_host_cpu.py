@@ -330,6 +330,42 @@ def test_banded_quad_plan_reconstructs_the_masks():
     assert gm.build_banded(stack[:, :4090], size, 4, n_cols) is None     # K % 16 != 0
 
 
+@pytest.mark.parametrize('seed,K,size,n_rings,n_bands', [(1, 1024, 3, 2, 1), (2, 2048, 7, 4, 8),
+                                                        (3, 960, 1, 3, 5), (4, 4096, 25, 2, 16)])
+def test_banded_quad_plan_random(seed, K, size, n_rings, n_bands):
+    """random supports (incl. an empty ring and rings confined to a few bands): every support
+    pixel appears exactly once with its weight, padding carries weight zero"""
+    from libertem_b200 import group_masks as gm
+    rng = np.random.default_rng(seed)
+    stack = np.zeros((n_rings * size, K), np.complex64)
+    for g in range(n_rings):
+        if g == 1:
+            continue                                   # an empty ring
+        lo = int(rng.integers(0, K // 2))
+        px = np.sort(rng.choice(np.arange(lo, min(K, lo + K // 3)), 150, replace=False))
+        stack[g * size:(g + 1) * size, px] = (rng.random((size, 150)) + 0.1
+                                              + 1j * rng.random((size, 150))).astype(np.complex64)
+    n_cols = _lib.get_lib().ltb200_group_masks_tc_columns(size)
+    b = gm.build_banded(stack, size, n_bands, n_cols)
+    assert b['n_groups'] == n_bands * n_rings
+    x = rng.random((2, K)).astype(np.float32)
+    out = _emulate_quad_plan(b, x, n_rings, size, n_cols)
+    ref = x.astype(np.float64) @ stack.astype(np.complex128).T
+    assert np.abs(out - ref).max() <= 2.0 ** -20 * np.abs(ref).max()
+    # every (ring, pixel) of the support is listed exactly once with a non-zero weight
+    off, quad_px, table = b['group_off'], b['entry_px'], b['table_split']
+    for ring in range(n_rings):
+        seen = []
+        for band in range(n_bands):
+            gidx = band * n_rings + ring
+            e = np.arange(off[gidx], off[gidx + 1])
+            px = quad_px[e // 4] + e % 4
+            seen.append(px[np.any(table[:, e] != 0, axis=0)])
+        seen = np.concatenate(seen) if seen else np.zeros(0, int)
+        want = np.nonzero(np.any(stack[ring * size:(ring + 1) * size] != 0, axis=0))[0]
+        assert np.array_equal(np.sort(seen), want)
+
+
 def test_int8_digit_plan():
     """host side of the integer fast path: which mask stacks K8 takes and how wide integer
     weights are split into base-128 int8 digits"""
