@@ -140,7 +140,8 @@ LTB_API int ltb200_masks_dense_tc_u16(const uint16_t* tile, int64_t n_frames, in
  * so exact int32 accumulation reproduces them bit for bit; the bytes of the TMA-staged tile
  * are the MMA operand as they land in shared memory -- no per-pixel instruction runs.
  * out = float32 of the exact integer result.  `sig_sum` (nullable) fuses SumUDF
- * (udf/sum.py:44-49) as a second MMA over the same stage.  1..16 columns, 16-byte aligned rows,
+ * (udf/sum.py:44-49) as a second MMA over the same stage.  1..16 columns (17..32: experimental,
+ * not yet validated on hardware), 16-byte aligned rows,
  * sig_size >= 256 (uint16) / 512 (uint8); signals beyond 65536 pixels are K-split so that the
  * int32 accumulators stay exact (<= 4 Mi pixels); LTB_ERR_UNSUPPORTED otherwise.
  * ------------------------------------------------------------------------------------- */

@@ -42,7 +42,8 @@ constexpr uint32_t K8_STAGE_BYTES = K8_FB * 128;          // 32 KiB
 constexpr int K8_TMEM_COLS = 512;
 constexpr int K8_ONES_COL = 128;       // TMEM columns [128, 136): all-ones A operand (32 int8 / row)
 constexpr int K8_SUM_COL = 256;        // TMEM columns [256, 512): 2 x 128 byte-sum accumulators
-constexpr int K8_MAX_COLUMNS = 16;
+constexpr int K8_MAX_COLUMNS = 32;     // rows 17..32 (N = 64 / uint8 N = 32): EXPERIMENTAL, not yet
+                                       // validated on hardware; the runner stays at <= 16 rows
 
 struct K8Params {
     int64_t n_frames;
@@ -233,7 +234,11 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
     constexpr uint32_t MASK_BYTES = (uint32_t)N * 128u;
     constexpr uint32_t IDESC_MASK = k8_idesc(0, 1, 0, N);       // u8 data x s8 masks
     constexpr uint32_t IDESC_SUM = k8_idesc(0, 0, 1, 128);      // u8 ones x u8 data (MN-major)
-    static_assert(N == 16 || N == 32, "K8: N in {16, 32}");
+    static_assert(N == 16 || N == 32 || N == 64, "K8: N in {16, 32, 64}");
+    // item accumulators: 2 frame groups x N columns, double-buffered across items while they fit
+    // in TMEM columns [0, 128); N = 64 keeps ONE buffer (the MMA warp waits for the drain at the
+    // item boundary, once per >= 64 stages)
+    constexpr bool ONE_ACC = N == 64;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -347,8 +352,8 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
             int64_t fb, k0;
             int ksi, n_sub;
             item_range(item, fb, ksi, k0, n_sub);
-            const uint32_t ab = item_n & 1;
-            mbar_wait(&acc_free[ab], ((item_n >> 1) & 1) ^ 1);
+            const uint32_t ab = ONE_ACC ? 0u : (item_n & 1);
+            mbar_wait(&acc_free[ab], ONE_ACC ? ((item_n & 1) ^ 1) : (((item_n >> 1) & 1) ^ 1));
             for (int i = 0; i < n_sub; i++, it++) {
                 const int ds = it % K8_DS;
                 const int ms = it % K8_MS;
@@ -437,40 +442,79 @@ k8_int_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             }
             // item accumulators
-            const uint32_t ab = item_n & 1;
-            mbar_wait(&acc_full[ab], (item_n >> 1) & 1);
-            k8_fence_after();
-            uint32_t v[2][N / 16][16];
+            if constexpr (!ONE_ACC) {
+                const uint32_t ab = item_n & 1;
+                mbar_wait(&acc_full[ab], (item_n >> 1) & 1);
+                k8_fence_after();
+                uint32_t v[2][N / 16][16];
+    #pragma unroll
+                for (int g = 0; g < 2; g++)
+    #pragma unroll
+                    for (int q = 0; q < N / 16; q++)
+                        k8_ld16(tmem_base + lane_sel + ab * 2 * N + g * N + q * 16, v[g][q]);
+                k8_wait_ld();
+    #pragma unroll
+                for (int g = 0; g < 2; g++)
+    #pragma unroll
+                    for (int q = 0; q < N / 16; q++) k8_ld_fence16(v[g][q]);
+                k8_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_free[ab]);
+    #pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const int64_t f = fb * K8_FB + g * 128 + w * 32 + lane;
+                    if (f >= p.n_frames) continue;
+                    float* o = p.out + f * p.ld_out;
+                    long long* po = p.part + ((int64_t)ksi * p.n_frames + f) * p.n_masks;
+    #pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        if (c >= p.n_masks) break;
+                        long long tot = (long long)(int32_t)v[g][c / 16][c % 16];
+                        if constexpr (BPP == 2)
+                            tot += 256ll * (int32_t)v[g][(NC + c) / 16][(NC + c) % 16];
+                        if (p.ksplit == 1) {
+                            const float val = (float)tot;
+                            o[c] = p.accumulate ? (o[c] + val) : val;
+                        } else {
+                            po[c] = tot;
+                        }
+                    }
+                }
+            } else {
+                // 64 columns per group, one accumulator buffer: one group at a time keeps the
+                // drain at 64 registers; the buffer is handed back after the second load
+                mbar_wait(&acc_full[0], item_n & 1);
+                k8_fence_after();
 #pragma unroll
-            for (int g = 0; g < 2; g++)
+                for (int g = 0; g < 2; g++) {
+                    uint32_t v[N / 16][16];
 #pragma unroll
-                for (int q = 0; q < N / 16; q++)
-                    k8_ld16(tmem_base + lane_sel + ab * 2 * N + g * N + q * 16, v[g][q]);
-            k8_wait_ld();
+                    for (int q = 0; q < N / 16; q++)
+                        k8_ld16(tmem_base + lane_sel + g * N + q * 16, v[q]);
+                    k8_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 2; g++)
+                    for (int q = 0; q < N / 16; q++) k8_ld_fence16(v[q]);
+                    if (g == 1) {
+                        k8_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_free[0]);
+                    }
+                    const int64_t f = fb * K8_FB + g * 128 + w * 32 + lane;
+                    if (f >= p.n_frames) continue;
+                    float* o = p.out + f * p.ld_out;
+                    long long* po = p.part + ((int64_t)ksi * p.n_frames + f) * p.n_masks;
 #pragma unroll
-                for (int q = 0; q < N / 16; q++) k8_ld_fence16(v[g][q]);
-            k8_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[ab]);
-#pragma unroll
-            for (int g = 0; g < 2; g++) {
-                const int64_t f = fb * K8_FB + g * 128 + w * 32 + lane;
-                if (f >= p.n_frames) continue;
-                float* o = p.out + f * p.ld_out;
-                long long* po = p.part + ((int64_t)ksi * p.n_frames + f) * p.n_masks;
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    if (c >= p.n_masks) break;
-                    long long tot = (long long)(int32_t)v[g][c / 16][c % 16];
-                    if constexpr (BPP == 2)
-                        tot += 256ll * (int32_t)v[g][(NC + c) / 16][(NC + c) % 16];
-                    if (p.ksplit == 1) {
-                        const float val = (float)tot;
-                        o[c] = p.accumulate ? (o[c] + val) : val;
-                    } else {
-                        po[c] = tot;
+                    for (int c = 0; c < NC; c++) {
+                        if (c >= p.n_masks) break;
+                        long long tot = (long long)(int32_t)v[c / 16][c % 16];
+                        if constexpr (BPP == 2)
+                            tot += 256ll * (int32_t)v[(NC + c) / 16][(NC + c) % 16];
+                        if (p.ksplit == 1) {
+                            const float val = (float)tot;
+                            o[c] = p.accumulate ? (o[c] + val) : val;
+                        } else {
+                            po[c] = tot;
+                        }
                     }
                 }
             }
@@ -517,7 +561,10 @@ static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms, int px) {
 static size_t k8_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // accumulator columns N of the kernel instantiation
-static int k8_n(int n_masks, int bpp) { return bpp == 2 ? (n_masks <= 8 ? 16 : 32) : 16; }
+static int k8_n(int n_masks, int bpp) {
+    if (bpp == 2) return n_masks <= 8 ? 16 : n_masks <= 16 ? 32 : 64;
+    return n_masks <= 16 ? 16 : 32;
+}
 
 struct K8Ws {
     size_t pack_off, part_off, sig_off, total;
@@ -660,10 +707,12 @@ extern "C" int ltb200_masks_dense_i8(const void* tile, int tile_dtype, int64_t n
                            (uint32_t)n, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != LTB_OK) return rc;
     if (bpp == 1)
-        rc = k8_launch<16, 1>(tmd, tmm, p, grid, st);
+        rc = n == 16 ? k8_launch<16, 1>(tmd, tmm, p, grid, st)
+                     : k8_launch<32, 1>(tmd, tmm, p, grid, st);
     else
         rc = n == 16 ? k8_launch<16, 2>(tmd, tmm, p, grid, st)
-                     : k8_launch<32, 2>(tmd, tmm, p, grid, st);
+             : n == 32 ? k8_launch<32, 2>(tmd, tmm, p, grid, st)
+                       : k8_launch<64, 2>(tmd, tmm, p, grid, st);
     if (rc != LTB_OK) return rc;
     if (p.ksplit > 1) {
         const int64_t total = n_frames * n_masks;

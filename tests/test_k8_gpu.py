@@ -134,7 +134,7 @@ def test_i8_unsupported(eng):
     from libertem_b200._lib import LTB200Error
     t = torch.zeros((300, 1024), dtype=torch.uint16, device='cuda')
     with pytest.raises(LTB200Error):
-        eng.masks_dense_i8(t, torch.ones((17, 1024), dtype=torch.int8, device='cuda'))
+        eng.masks_dense_i8(t, torch.ones((33, 1024), dtype=torch.int8, device='cuda'))
     with pytest.raises(LTB200Error):
         eng.masks_dense_i8(t[:, :128], torch.ones((2, 128), dtype=torch.int8, device='cuda'))
     with pytest.raises(TypeError):
@@ -145,9 +145,31 @@ def test_i8_unsupported(eng):
         eng.masks_dense_i8(big, torch.ones((1, K), dtype=torch.int8, device='cuda'))
 
 
-@pytest.mark.skipif(__import__('os').environ.get('LTB200_TEST_EXPERIMENTAL') != '1',
-                    reason='forced K split for signals > 65536 px: written after the round-1 GPU '
-                           'budget ran out; run with LTB200_TEST_EXPERIMENTAL=1')
+EXPERIMENTAL = pytest.mark.skipif(
+    __import__('os').environ.get('LTB200_TEST_EXPERIMENTAL') != '1',
+    reason='written after the round-1 GPU budget ran out; run with LTB200_TEST_EXPERIMENTAL=1')
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize('n_masks', [17, 24, 32])
+@pytest.mark.parametrize('dt', ['u16', 'u8'])
+def test_i8_wide_stacks(eng, n_masks, dt):
+    """17..32 int8 rows per pass (N = 64 for uint16 tiles with one accumulator buffer, N = 32
+    for uint8 tiles), several items per CTA, with the fused frame sum"""
+    F, K = 40960, 1024
+    masks = int_masks(n_masks, K, 72, -128, 127)
+    masks[0] = 1
+    if dt == 'u16':
+        data = (synth.hash_u32(0, F * K, 71) & 0xFFFF).astype(np.uint16).reshape(F, K)
+        check_exact(eng, data, masks)
+        check_exact(eng, data[:300], masks, with_sum=False)
+    else:
+        data = (synth.hash_u32(0, F * K, 71) & 0xFF).astype(np.uint8).reshape(F, K)
+        check_exact_u8(eng, data, masks)
+        check_exact_u8(eng, data[:300], masks, with_sum=False)
+
+
+@EXPERIMENTAL
 @pytest.mark.parametrize('K', [65536 + 64, 512 * 512, 3 * 65536 + 8 * 5])
 def test_i8_large_signals(eng, K):
     """signals beyond 65536 pixels are K-split so that every int32 accumulator stays exact; the
