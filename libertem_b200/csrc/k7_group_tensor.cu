@@ -207,6 +207,11 @@ __device__ __forceinline__ void k7_cp_async_16(uint32_t smem_dst, const void* gs
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc)
                  : "memory");
 }
+// A/B variant (LTB200_K7_CA=1): the quad gather through L1
+__device__ __forceinline__ void k7_cp_async_16_ca(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc)
+                 : "memory");
+}
 __device__ __forceinline__ void k7_cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -237,7 +242,7 @@ struct K7QItem {
 // parts of the weights in accumulator columns [0, 64), the differences the IMAGINARY parts in
 // [64, 128): two MMAs of N = 64 per k-step instead of two of N = 112 per pixel pair, and a
 // weight table of 128 rows per orbit instead of 112 per pixel.
-template <int N, bool SYM>
+template <int N, bool SYM, bool CA = false>
 __global__ void __launch_bounds__(K7_THREADS, 1)
 k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                        const __grid_constant__ CUtensorMap tm_tile, const K7Params p) {
@@ -407,7 +412,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                         const int64_t step = 8 * p.ld_tile;
 #pragma unroll 4
                         for (int j = 0; j < K7_FB / 8; j++) {
-                            k7_cp_async_16(d0 + (uint32_t)j * 1024u, src);
+                            if constexpr (CA)
+                                k7_cp_async_16_ca(d0 + (uint32_t)j * 1024u, src);
+                            else
+                                k7_cp_async_16(d0 + (uint32_t)j * 1024u, src);
                             src += step;
                         }
                     } else {
@@ -683,10 +691,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
     }
 }
 
-template <int N, bool SYM>
+template <int N, bool SYM, bool CA = false>
 static int k7_launch(const CUtensorMap& tm, const CUtensorMap& tmt, const K7Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k7_group_tensor_kernel<N, SYM>;
+    auto kern = k7_group_tensor_kernel<N, SYM, CA>;
     const size_t smem = K7Smem<SYM ? 64 : N>::TOTAL;
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -854,6 +862,12 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     }
     int grid = sm_count();
     if (p.n_items < grid) grid = (int)p.n_items;
+    bool gather_ca = false;                 // A/B: quad gather through L1 (cp.async.ca)
+    if (const char* e = getenv("LTB200_K7_CA")) gather_ca = atoi(e) != 0;
+    if (gather_ca && quad && (sym || n == 112)) {
+        rc = sym ? k7_launch<128, true, true>(tm, tmt, p, grid, st)
+                 : k7_launch<112, false, true>(tm, tmt, p, grid, st);
+    } else
     switch (sym ? 128 : n) {
         case 16: rc = k7_launch<16, false>(tm, tmt, p, grid, st); break;
         case 32: rc = k7_launch<32, false>(tm, tmt, p, grid, st); break;
