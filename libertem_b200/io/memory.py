@@ -137,6 +137,7 @@ class MemoryDataSet(_DataSetBase):
         self.tile_depth = tile_depth
         self._pin = pin
         self._registered = False
+        self._stage = {}
 
     def _flat(self):
         n = self._shape.nav.size
@@ -193,20 +194,22 @@ class MemoryDataSet(_DataSetBase):
             for f0, f1 in blocks:
                 yield from emit(flat[f0:f1], f0, f1)
             return
-        # host data: double-buffered H2D on a side stream
+        # host data: double-buffered H2D on a side stream.  The staging buffers, the copy
+        # stream and the "buffer free" events live on the dataset (one set per device / depth),
+        # so they persist across partitions and runs: a buffer is never handed back to the
+        # caching allocator while a kernel of an earlier partition may still read it, and
+        # every copy into a buffer waits for the event recorded after its last consumer.
         self._register()
         src = flat if self._is_torch else _np_to_torch(flat)
-        copy_stream = torch.cuda.Stream(device=device)
+        st = self._staging(device, depth, sig, src.dtype)
         main = torch.cuda.current_stream(device)
-        bufs = [None, None]
-        ready = [None, None]
-        free = [None, None]
+        copy_stream = st['stream']
+        bufs, ready, free = st['bufs'], st['ready'], st['free']
 
-        def launch(i, f0, f1):
-            b = i & 1
+        def launch(f0, f1):
+            b = st['next'] & 1
+            st['next'] += 1
             n = f1 - f0
-            if bufs[b] is None or bufs[b].shape[0] < n:
-                bufs[b] = torch.empty((depth,) + sig, dtype=src.dtype, device=device)
             with torch.cuda.stream(copy_stream):
                 if free[b] is not None:
                     copy_stream.wait_event(free[b])
@@ -214,18 +217,41 @@ class MemoryDataSet(_DataSetBase):
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 ready[b] = ev
+            return b
 
-        if blocks:
-            launch(0, *blocks[0])
+        pending = launch(*blocks[0]) if blocks else None
         for i, (f0, f1) in enumerate(blocks):
+            b = pending
             if i + 1 < len(blocks):
-                launch(i + 1, *blocks[i + 1])
-            b = i & 1
+                pending = launch(*blocks[i + 1])
             main.wait_event(ready[b])
-            yield from emit(bufs[b][:f1 - f0], f0, f1)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            free[b] = ev
+            try:
+                yield from emit(bufs[b][:f1 - f0], f0, f1)
+            finally:
+                # also on an abandoned generator: whatever main has queued so far is the
+                # last possible reader of this buffer
+                ev = torch.cuda.Event()
+                ev.record(main)
+                free[b] = ev
+
+    def _staging(self, device, depth, sig, dtype):
+        """persistent double buffer + copy stream for host -> device streaming"""
+        key = (str(device), int(depth), tuple(sig), dtype)
+        st = self._stage.get(key)
+        if st is None:
+            main = torch.cuda.current_stream(device)
+            copy_stream = torch.cuda.Stream(device=device)
+            bufs = [torch.empty((depth,) + tuple(sig), dtype=dtype, device=device)
+                    for _ in range(2)]
+            # the allocator may hand out blocks whose previous users are still queued on the
+            # main stream: order the first copies after everything queued so far
+            copy_stream.wait_stream(main)
+            for b in bufs:
+                b.record_stream(copy_stream)
+            st = {'stream': copy_stream, 'bufs': bufs, 'ready': [None, None],
+                  'free': [None, None], 'next': 0}
+            self._stage[key] = st
+        return st
 
 
 class SyntheticDataSet(_DataSetBase):

@@ -21,7 +21,7 @@ import os
 import numpy as np
 import torch
 
-from .common.buffers import BufferWrapper, torch_dtype, to_numpy
+from .common.buffers import BufferWrapper, torch_dtype, to_numpy, _NP2TORCH
 from .common.shape import Shape
 from .udf.base import UDFMeta, UDFData, MergeAttrMapping, UDFException
 from .udf.base import UDF as _BaseUDF
@@ -129,7 +129,7 @@ class UDFRunner:
     # -- main entry -------------------------------------------------------------------------------
     def run_for_dataset(self, dataset, executor=None, roi=None, progress=False,
                         corrections=None, backends=None, dry=False, device=None,
-                        finalize=True):
+                        finalize=True, use_merge_all=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
@@ -146,6 +146,9 @@ class UDFRunner:
             corrections = None
         input_dtype = _get_dtype(udfs, dataset.dtype, corrections)
         self._corr = corrections
+        # caches derived from the CorrectionSet of a previous run must not leak into this one
+        self._fold_cache = {}
+        self._slice_corr = {}
         # corrections fold into the masks (libertem_b200/corrections.py) when every tile is a
         # full frame; sub-frame tilings get explicitly corrected tiles like in the reference
         self._corr_fold = corrections is not None and getattr(dataset, 'tileshape', None) is None
@@ -190,11 +193,21 @@ class UDFRunner:
         mine = self.my_partitions(partitions, rank, world)
         damage = np.zeros(n_frames if roi_flat is None else int(roi_flat.sum()), dtype=bool)
 
+        self._input_tdtype = torch_dtype(input_dtype) if np.dtype(input_dtype) in _NP2TORCH \
+            else None
         if not dry:
+            collected = [dict() for _ in udfs]       # per UDF: {partition Slice: results}
             for part in mine:
                 part_udfs = self._run_partition(part, dataset, udfs, roi_flat, input_dtype,
                                                 device)
-                self._merge_partition(part, udfs, part_udfs, roi_flat, damage)
+                self._merge_partition(part, udfs, part_udfs, roi_flat, damage,
+                                      collect=collected if use_merge_all else None)
+            if use_merge_all:
+                # the reference's merge_all contract (udf/base.py:944-1002, used by
+                # executor/delayed.py:81-88): all partition results of a UDF at once, in order
+                for ui, (udf, parts_) in enumerate(zip(udfs, collected)):
+                    if parts_:
+                        udf._do_merge_all(parts_)
         if dist:
             self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device)
         if self._corr is not None and self._sig_sum_folded:
@@ -530,6 +543,13 @@ class UDFRunner:
     def _run_unfused(self, pu, tile):
         self.stats['unfused_calls'] += 1
         method = pu.get_method()
+        # the reference guarantees tile.dtype == meta.input_dtype (udf/base.py:106-123,
+        # io/dataset/memory.py:99-108); the built-in UDFs' kernels convert on the fly and keep
+        # the native dtype, everything else gets the converted tile
+        want = getattr(self, '_input_tdtype', None)
+        if (want is not None and tile.dtype != want
+                and getattr(pu, '_fused_spec', None) is None):
+            tile = tile.to(want)
         if method == 'partition':
             part = pu.meta.partition_slice
             if tile.shape[0] != part.shape[0] and pu.meta.roi is None:
@@ -552,7 +572,14 @@ class UDFRunner:
                 pu.results.clear_views()
                 for name, v in views.items():
                     buf = pu.results.get_buffer(name)
-                    pu.results.set_view(name, v[i] if buf.kind == 'nav' else v)
+                    if buf.kind != 'nav':
+                        pu.results.set_view(name, v)
+                    elif buf.extra_shape:
+                        pu.results.set_view(name, v[i])
+                    else:
+                        # (1,) view like get_view_for_frame (common/buffers.py:792-821), so
+                        # ``self.results.x[:] = value`` works
+                        pu.results.set_view(name, v[i:i + 1])
                 if hasattr(shifts, 'for_frames'):
                     arr = shifts.for_frames(pu.meta.dataset_shape, pu.meta.roi)
                     pu._current_shift = arr[tslice.origin[0] + i].astype(int)
@@ -565,26 +592,73 @@ class UDFRunner:
             pu.process_tile(tile)
 
     # -- merging ---------------------------------------------------------------------------------
-    def _merge_partition(self, part, udfs, part_udfs, roi_flat, damage):
+    def _merge_partition(self, part, udfs, part_udfs, roi_flat, damage, collect=None):
         r0, r1 = self._roi_range(part, roi_flat)
-        for udf, pu in zip(udfs, part_udfs):
+        for ui, (udf, pu) in enumerate(zip(udfs, part_udfs)):
             dest, src = {}, {}
             for name, buf in udf.results.items():
                 if buf.use == 'result_only' or not buf.has_data():
                     continue
-                if (udfs.index(udf), name) in self._slab_map:
+                if (ui, name) in self._slab_map:
                     continue        # partition buffer aliases the dataset slab rows already
                 dest[name] = buf.rows(r0, r1)
                 src[name] = pu.results.get_buffer(name).tensor
-            if dest:
+            if not dest:
+                continue
+            can_merge_all = (getattr(udf, 'merge_all', None) is not None
+                             or (type(udf).merge is _BaseUDF.merge
+                                 and not udf.requires_custom_merge_all))
+            if collect is not None and can_merge_all:
+                collect[ui][part.slice] = MergeAttrMapping(src)
+            else:
                 udf.merge(dest=MergeAttrMapping(dest), src=MergeAttrMapping(src))
         damage[r0:r1] = True
 
+    @staticmethod
+    def _gather_rows(dist, comm, bounds, equal):
+        """assemble a nav buffer whose rows [a_r, b_r) are valid on rank r: all-gather of the
+        contiguous row blocks; ragged blocks are padded to the largest one.  bool / complex
+        buffers travel as bytes / real pairs (NCCL has no bool, gloo no complex)."""
+        rank = dist.get_rank()
+        a, b = bounds[rank]
+        orig = comm
+        if comm.dtype == torch.bool:
+            comm = comm.view(torch.uint8)
+        elif comm.is_complex():
+            comm = torch.view_as_real(comm)
+        if not comm.is_contiguous():
+            raise UDFException('nav buffers must be contiguous for the multi-rank merge')
+        if equal:
+            dist.all_gather_into_tensor(comm.view(-1), comm[a:b].contiguous().view(-1))
+            return orig
+        width = max(bb - aa for aa, bb in bounds)
+        if width == 0:
+            return orig
+        block = torch.zeros((width,) + tuple(comm.shape[1:]), dtype=comm.dtype,
+                            device=comm.device)
+        block[:b - a] = comm[a:b]
+        gathered = torch.empty((len(bounds),) + tuple(block.shape), dtype=comm.dtype,
+                               device=comm.device)
+        dist.all_gather_into_tensor(gathered.view(-1), block.view(-1))
+        for r, (aa, bb) in enumerate(bounds):
+            if r != rank and bb > aa:
+                comm[aa:bb] = gathered[r, :bb - aa]
+        return orig
+
     def _merge_ranks(self, dist, udfs, partitions, roi_flat, damage, device):
-        """assemble the dataset-sized buffers across ranks: nav -> all-gather of each rank's
-        contiguous row block (equal blocks) or all-reduce over disjoint zero-padded rows
-        (ragged blocks); sig -> all-reduce(sum) (mirrors SumUDF.merge, udf/sum.py:51-53)"""
+        """assemble the dataset-sized buffers across ranks.
+
+        * the fused slab and every nav buffer of a UDF with the *default* merge: all-gather of
+          each rank's contiguous row block (the default merge is a row copy,
+          udf/base.py:1420-1453);
+        * UDFs that declare ``_additive_merge`` (SumUDF: ``dest += src``, udf/sum.py:51-53):
+          all-reduce(sum);
+        * any other custom ``merge``: every rank's locally merged buffers are gathered and
+          ``udf.merge(dest, src)`` is replayed in rank (= partition) order onto freshly zeroed
+          dataset buffers on every rank -- a rank acts as one large partition, which is what an
+          associative merge (max / min, variance-style, 'single' buffers) needs."""
         world = dist.get_world_size()
+        rank = dist.get_rank()
         backend = dist.get_backend()
         bounds = []
         for r in range(world):
@@ -597,36 +671,68 @@ class UDFRunner:
             bounds.append((a, b))
         sizes = [b - a for a, b in bounds]
         equal = len(set(sizes)) == 1 and sizes[0] > 0
+
+        def on_wire(t):
+            return t if backend == 'nccl' or not t.is_cuda else t.cpu()
+
         if self._slab is not None:
             t = self._slab
-            comm = t if backend == 'nccl' else t.cpu()
-            if equal:
-                a, b = bounds[dist.get_rank()]
-                dist.all_gather_into_tensor(comm.view(-1), comm[a:b].contiguous().view(-1))
-            else:
-                dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            comm = on_wire(t)
+            self._gather_rows(dist, comm, bounds, equal)
             if comm is not t:
                 t.copy_(comm)
         for ui, udf in enumerate(udfs):
-            for name, buf in udf.results.items():
-                if buf.use == 'result_only' or not buf.has_data():
-                    continue
-                if (ui, name) in self._slab_map:
-                    continue
-                t = buf.tensor
-                comm = t if backend == 'nccl' else t.cpu()
-                if buf.kind == 'nav' and equal and not comm.is_complex():
-                    a, b = bounds[dist.get_rank()]
-                    block = comm[a:b].contiguous()
-                    dist.all_gather_into_tensor(comm.view(-1), block.view(-1))
-                else:
-                    if comm.is_complex():
-                        r = torch.view_as_real(comm)
-                        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            names = [name for name, buf in udf.results.items()
+                     if buf.use != 'result_only' and buf.has_data()
+                     and (ui, name) not in self._slab_map]
+            if not names:
+                continue
+            default_merge = type(udf).merge is _BaseUDF.merge
+            if default_merge or getattr(udf, '_additive_merge', False):
+                for name in names:
+                    buf = udf.results.get_buffer(name)
+                    t = buf.tensor
+                    comm = on_wire(t)
+                    if default_merge and buf.kind == 'nav':
+                        self._gather_rows(dist, comm, bounds, equal)
+                    elif default_merge:
+                        raise UDFException(
+                            "buffer '%s' (kind=%s) needs a custom merge" % (name, buf.kind))
+                    elif comm.is_complex():
+                        dist.all_reduce(torch.view_as_real(comm), op=dist.ReduceOp.SUM)
                     else:
                         dist.all_reduce(comm, op=dist.ReduceOp.SUM)
-                if comm is not t:
-                    t.copy_(comm)
+                    if comm is not t:
+                        t.copy_(comm)
+                continue
+            # custom merge: gather every rank's buffers, replay merge in rank order
+            per_rank = {}
+            for name in names:
+                t = udf.results.get_buffer(name).tensor
+                comm = on_wire(t).contiguous()
+                wire = comm.view(torch.uint8) if comm.dtype == torch.bool else (
+                    torch.view_as_real(comm) if comm.is_complex() else comm)
+                gathered = torch.empty((world,) + tuple(wire.shape), dtype=wire.dtype,
+                                       device=wire.device)
+                dist.all_gather_into_tensor(gathered.view(-1), wire.reshape(-1))
+                if comm.dtype == torch.bool:
+                    gathered = gathered.view(torch.bool)
+                elif comm.is_complex():
+                    gathered = torch.view_as_complex(gathered)
+                per_rank[name] = gathered.to(t.device)
+            for name in names:
+                udf.results.get_buffer(name).tensor.zero_()
+            for r in range(world):
+                a, b = bounds[r]
+                if b <= a:
+                    continue
+                dest, src = {}, {}
+                for name in names:
+                    buf = udf.results.get_buffer(name)
+                    dest[name] = buf.rows(a, b)
+                    src[name] = (per_rank[name][r][a:b] if buf.kind == 'nav'
+                                 else per_rank[name][r])
+                udf.merge(dest=MergeAttrMapping(dest), src=MergeAttrMapping(src))
         damage[:] = True
 
     # -- results ---------------------------------------------------------------------------------

@@ -146,6 +146,20 @@ class UDFMeta:
         return valid
 
 
+def _default_merge_all(udf, ordered_results):
+    """concatenate the partitions' nav buffers in partition order (base.py:985-1002)"""
+    import torch
+    if udf.requires_custom_merge_all:
+        raise NotImplementedError(
+            "Default merging only works for kind='nav' buffers. "
+            "Please implement a suitable custom merge_all function.")
+    chunks = {}
+    for b in ordered_results.values():
+        for key in b:
+            chunks.setdefault(key, []).append(getattr(b, key))
+    return {k: torch.cat(v, dim=0) for k, v in chunks.items()}
+
+
 class UDF:
     USE_NATIVE_DTYPE = bool
     TILE_SIZE_BEST_FIT = object()
@@ -242,6 +256,42 @@ class UDF:
         for k in dest:
             check_cast(getattr(src, k), getattr(dest, k))
             getattr(dest, k)[:] = getattr(src, k)
+
+    @property
+    def requires_custom_merge_all(self):
+        """any buffer with ``kind != 'nav'``: the default merge_all (concatenation) does not
+        apply (base.py:1405-1418)"""
+        return any(b.kind != 'nav' for b in self.get_result_buffers().values())
+
+    #: UDFs whose ``merge`` is a plain ``dest += src`` on every buffer may set this so that the
+    #: multi-rank merge uses one all-reduce(sum) instead of replaying ``merge`` per rank
+    _additive_merge = False
+
+    def _do_merge_all(self, ordered_results):
+        """combine the ordered partition results ``{Slice: MergeAttrMapping}`` in one go
+        (base.py:1208-1224): the UDF's own ``merge_all`` when it defines one, else
+        concatenation of the nav buffers (``_default_merge_all``, base.py:985-1002)."""
+        custom = getattr(self, 'merge_all', None)
+        if custom is not None:
+            tmp = custom(ordered_results)
+        else:
+            tmp = _default_merge_all(self, ordered_results)
+        if not set(tmp.keys()).issubset(set(self.results.keys())):
+            raise ValueError('Returned result names from merge_all (%s) are not contained within '
+                             'declared result buffer names (%s)'
+                             % ([*tmp.keys()], [*self.results.keys()]))
+        for key, value in tmp.items():
+            buf = self.results.get_buffer(key)
+            cur = buf.tensor
+            import torch
+            if isinstance(value, np.ndarray):
+                value = torch.from_numpy(value)
+            if cur is not None:
+                if tuple(value.shape) != tuple(cur.shape) and value.numel() != cur.numel():
+                    raise ValueError("merge_all result '%s' has shape %s, buffer has %s"
+                                     % (key, tuple(value.shape), tuple(cur.shape)))
+                value = value.reshape(cur.shape).to(device=cur.device, dtype=cur.dtype)
+            buf.replace_array(value)
 
     def get_results(self):
         """default: every non-private buffer as it is (base.py:1455-1493)"""

@@ -36,6 +36,8 @@ class SumUDF(UDF):
             v = view.reshape(sig)[sig_slice.get()]
             v += acc.reshape(v.shape)
 
+    _additive_merge = True
+
     def merge(self, dest, src):
         dest.intensity[:] += src.intensity
 

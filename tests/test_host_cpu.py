@@ -208,6 +208,52 @@ def test_default_merge_only_for_nav():
         u.merge(dest={}, src={})
 
 
+def test_merge_all_contract():
+    """reference udf/base.py:944-1002,1208-1224: default merge_all = concatenation of nav
+    buffers in partition order; SumUDF.merge_all = stack-sum (udf/sum.py:54-58); sig buffers
+    without a custom merge_all raise; unknown names raise ValueError"""
+    import torch
+    from collections import OrderedDict
+    from libertem_b200.udf.base import MergeAttrMapping, UDFData
+    from libertem_b200.udf import SumUDF, SumSigUDF
+
+    def prepared(u, shape):
+        u.set_meta(_meta(shape))
+        decl = u.get_result_buffers()
+        for b in decl.values():
+            b.set_shape_ds(Shape(shape, sig_dims=2), None)
+            b.allocate()
+        u.results = UDFData(decl)
+        return u
+
+    u = prepared(SumSigUDF(), (2, 3, 4, 4))
+    parts = OrderedDict([('p0', MergeAttrMapping({'intensity': torch.tensor([1., 2.])})),
+                         ('p1', MergeAttrMapping({'intensity': torch.tensor([3., 4., 5., 6.])}))])
+    u._do_merge_all(parts)
+    assert u.results.get_buffer('intensity').raw_data.tolist() == [1, 2, 3, 4, 5, 6]
+
+    s = prepared(SumUDF(), (2, 3, 4, 4))
+    assert s.requires_custom_merge_all
+    parts = OrderedDict([(i, MergeAttrMapping({'intensity': torch.full((16,), float(i + 1))}))
+                         for i in range(3)])
+    s._do_merge_all(parts)
+    assert np.all(s.results.get_buffer('intensity').raw_data == 6.0)
+
+    class SigUDF(UDF):
+        def get_result_buffers(self):
+            return {'x': self.buffer(kind='sig', dtype=np.float32)}
+    g = prepared(SigUDF(), (2, 3, 4, 4))
+    with pytest.raises(NotImplementedError):
+        g._do_merge_all(OrderedDict([(0, MergeAttrMapping({'x': torch.zeros(16)}))]))
+
+    class BadUDF(SigUDF):
+        def merge_all(self, ordered_results):
+            return {'nope': torch.zeros(16)}
+    b = prepared(BadUDF(), (2, 3, 4, 4))
+    with pytest.raises(ValueError):
+        b._do_merge_all(OrderedDict([(0, MergeAttrMapping({'x': torch.zeros(16)}))]))
+
+
 def test_apply_masks_argument_errors():
     with pytest.raises(ValueError):
         ApplyMasksUDF(mask_factories=_factory, backends=('nonsense',))
