@@ -6,18 +6,31 @@
 Workload at N=1: BASELINE configs[1] -- 256x256 nav x 256x256 sig float32, ApplyMasksUDF with 8
 dense masks + CoMUDF (11 fused mask columns), one B200.  For N>1 (torchrun, one rank per GPU)
 every rank owns one such 256x256-nav shard of a (256*N)x256 nav dataset (weak scaling) and the
-nav-shaped result buffers are assembled with one NCCL all-gather inside the timed step.
+nav-shaped result buffers are assembled with one NCCL all-gather per step.
 
 A *step* = one pass of the hot path over the whole (per-rank) dataset through the plugin API:
-partition -> tile -> fused kernel -> merge (-> all-gather).  JSON keys:
-  value      frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  roofline   the dominant kernel (k6_tensor_kernel, the tcgen05 dense masked reduction) timed
-             live with CUDA events: algorithmic bytes
-             (frames x sig_size x 4) / mean launch duration vs MEASURED_PEAKS hbm_gbs
-  e2e        same metric through run_udf() on a HOST (pinned) numpy dataset: H2D of every frame
-             and D2H/get_results of every result inside the timed region
-  cpu_baseline  the oracle port (the reference's torch.mm formulation) on the host cores, on a
-             bounded frame sample of the same workload (rank 0, N=1 only)
+partition -> tile -> fused kernel -> merge (-> all-gather).  JSON keys (one line, rank 0):
+  value        frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  roofline     the dominant kernel (k6_tensor_kernel, tcgen05 dense masked reduction) timed live
+               with CUDA events on its stream: algorithmic bytes (frames x sig_size x 4,
+               SURVEY 8d) / mean launch duration vs MEASURED_PEAKS hbm_gbs (a COPY benchmark) and
+               vs `peak_read_only`, a read-only streaming probe measured in this run
+  parity       after the timed loop: the first and last 256 frames of every rank's shard are
+               recomputed with the CPU oracle on oracle.synth data; max relative error, the run
+               FAILS (exit 1) above 1e-5
+  configs      (N=1) device-timed passes of the other BASELINE configs: cfg3 (uint16, SumUDF +
+               SumSigUDF + 4 ring masks), cfg4 (RadialFourierAnalysis, 32 bins), cfg5 shard
+               (131072 frames, 16 masks + CoM): ms, frames/s, roofline.frac, kernel, parity
+  multi        (N>1) cfg5 (1024x1024 nav over 8 GPUs: a 128x1024-nav shard per rank) and cfg2
+               strong scaling (ONE 256x256-nav dataset split over the N ranks), both with the
+               all-gather inside the step
+  e2e          the same metric through run_udf() on a HOST (pinned) numpy dataset: H2D of every
+               frame, the all-gather (N>1) and D2H / get_results of every result inside the
+               timed region; `h2d_peak_gbs` = bare concurrent cudaMemcpyAsync from the same
+               pinned buffers
+  cpu_baseline the oracle port of the reference's CPU formulation on the host cores, on a bounded
+               frame sample of the same workload, timed BEFORE the GPU legs with the same
+               procedure as `--impl reference` (rank 0, N=1 only)
 --impl reference times the reference's own CPU formulation (oracle port; the reference is pure
 Python and cannot travel to the GPU box) on the host cores only.
 """
@@ -42,6 +55,18 @@ MASK_SEED = 2001
 METRIC = 'frames/s on 256^2 nav x 256^2 sig float32 ApplyMasksUDF (8 dense masks) + CoM'
 WORKLOAD = ('cfg2: 256x256 nav x 256x256 sig float32, ApplyMasksUDF 8 dense masks + CoMUDF '
             '(11 fused mask columns), per GPU')
+PARITY_TOL = 1e-5
+PARITY_FRAMES = 256
+CPU_SAMPLE_FRAMES = 2048   # 512 MiB of the cfg2 frame stream per CPU step
+KERNEL_NAMES = {
+    1: 'k1_dense_tma_kernel (FFMA2, even/odd tile)', 2: 'generic kernel',
+    3: 'k1_pair_kernel (FFMA2, mask-pair tile)', 4: 'k4_group_kernel (FFMA2 group-sparse)',
+    6: 'k6_tensor_kernel (tcgen05 kind::tf32, split-TF32, TMEM accumulators)',
+    7: 'k7_group_tensor_kernel (tcgen05, ring-major plan)',
+    70: 'k7_group_tensor_kernel (tcgen05, quad / banded plan)',
+    71: 'k7_group_tensor_kernel (tcgen05, mirror-symmetric plan)',
+    8: 'k8_int_kernel (tcgen05 kind::i8, exact integer path)', 20: 'k2_csc_kernel',
+}
 
 
 def bench_masks(sy, sx, count, seed, uniform_fn):
@@ -70,7 +95,7 @@ def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json, copy)'
         except Exception:
             pass
     return 6650.0, 'fallback (B200_PROFILING.md)'
@@ -152,7 +177,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's CPU formulation on the host cores
+# reference arm / cpu baseline: the reference's CPU formulation on the host cores.  ONE procedure
+# for both (`--impl reference` and the GPU arm's `cpu_baseline`): the same sample, the same
+# warm-up and step counts, run before any GPU leg.
 # ----------------------------------------------------------------------------------------------
 
 def cpu_pass(flat, masks_t, com_t, use_torch=True):
@@ -165,28 +192,40 @@ def cpu_pass(flat, masks_t, com_t, use_torch=True):
     return a, b
 
 
-def cpu_sample(n_frames):
+def oracle_masks(sig, n_masks, seed):
     from oracle import synth, udf_oracle as O
-    k = SIG[0] * SIG[1]
-    flat = np.empty((n_frames, k), dtype=np.float32)
-    step = 256
-    for f0 in range(0, n_frames, step):
-        f1 = min(n_frames, f0 + step)
-        flat[f0:f1] = synth.uniform_f32(f0 * k, (f1 - f0) * k, DATA_SEED).reshape(f1 - f0, k)
-    stack = bench_masks(SIG[0], SIG[1], N_MASKS, MASK_SEED,
-                        lambda n, s: synth.uniform_f32(0, n, s))
-    masks_t = O.masks_for_sig_slice(stack, (slice(0, SIG[0]), slice(0, SIG[1])), np.float32)
-    com_t = O.masks_for_sig_slice(O.com_mask_stack(SIG, SIG[0] // 2, SIG[1] // 2),
-                                  (slice(0, SIG[0]), slice(0, SIG[1])), np.float32)
-    return flat, masks_t, com_t
+    stack = bench_masks(sig[0], sig[1], n_masks, seed, lambda n, s: synth.uniform_f32(0, n, s))
+    full = (slice(0, sig[0]), slice(0, sig[1]))
+    masks_t = O.masks_for_sig_slice(stack, full, np.float32)
+    com_t = O.masks_for_sig_slice(O.com_mask_stack(sig, sig[0] // 2, sig[1] // 2), full,
+                                  np.float32)
+    return masks_t, com_t
 
 
-def run_cpu(flat, masks_t, com_t, steps, warmup):
-    """times both GEMM formulations the reference has (torch.mm default, numpy @) and returns
-    the FASTER one -- the most favourable reading of the reference's CPU path"""
+def oracle_frames(f0, f1, k, seed, dtype=np.float32):
+    """frames [f0, f1) of the synthetic stream as the oracle generates them (host)"""
+    from oracle import synth
+    if np.dtype(dtype) == np.uint16:
+        return synth.poisson3_u16(f0 * k, (f1 - f0) * k, seed).reshape(f1 - f0, k)
+    out = np.empty((f1 - f0, k), dtype=np.float32)
+    for a in range(f0, f1, 256):
+        b = min(f1, a + 256)
+        out[a - f0:b - f0] = synth.uniform_f32(a * k, (b - a) * k, seed).reshape(b - a, k)
+    return out
+
+
+def cpu_leg(steps, warmup):
+    """the bounded CPU sample: CPU_SAMPLE_FRAMES frames of the cfg2 stream, both GEMM formulations
+    the reference has (torch.mm default, numpy @); returns the FASTER one -- the most favourable
+    reading of the reference's CPU path"""
     import torch
     cores = physical_cores()
     torch.set_num_threads(cores)
+    k = SIG[0] * SIG[1]
+    flat = oracle_frames(0, CPU_SAMPLE_FRAMES, k, DATA_SEED)
+    masks_t, com_t = oracle_masks(SIG, N_MASKS, MASK_SEED)
+    steps = max(1, min(int(steps), 20))
+    warmup = max(1, min(int(warmup), 3))
     best = None
     for use_torch in (True, False):
         for _ in range(warmup):
@@ -198,29 +237,30 @@ def run_cpu(flat, masks_t, com_t, steps, warmup):
         fps = flat.shape[0] * steps / dt
         if best is None or fps > best[0]:
             best = (fps, dt / steps, 'torch.mm' if use_torch else 'numpy @')
-    return best[0], best[1], cores, best[2]
+    sample = (f'{CPU_SAMPLE_FRAMES} frames ({flat.nbytes / 2**20:.0f} MiB) of the cfg2 stream per '
+              f'step, {steps} steps after {warmup} warm-up, oracle port of the reference '
+              'formulation: one GEMM per UDF (8 masks, then 3 CoM masks), faster of torch.mm / '
+              f'numpy @ = {best[2]}, data resident in host RAM, run before any GPU leg')
+    return {'value': best[0], 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': sample, 'ms_per_step': best[1] * 1e3, 'steps': steps, 'warmup': warmup}
 
 
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_frames = 2048        # 512 MiB sample of the cfg2 frame stream
-    flat, masks_t, com_t = cpu_sample(n_frames)
-    fps, per_step, cores, which = run_cpu(flat, masks_t, com_t, args.steps, max(args.warmup, 1))
-    sample = (f'{n_frames} frames ({flat.nbytes / 2**20:.0f} MiB) of the cfg2 stream per step, '
-              'oracle port of the reference formulation: one GEMM per UDF (8 masks, then 3 CoM '
-              f'masks), faster of torch.mm / numpy @ = {which}, data resident in host RAM')
+    cpu = cpu_leg(args.steps, args.warmup)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'impl': 'reference', 'metric': METRIC, 'value': cpu['value'], 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': cpu['steps'], 'warmup': cpu['warmup'],
+        'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'nav': list(NAV), 'sig': list(SIG),
-                   'n_masks': N_MASKS, 'com': True, 'sample_frames': n_frames},
-        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': sample},
-        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
+                   'n_masks': N_MASKS, 'com': True, 'sample_frames': CPU_SAMPLE_FRAMES,
+                   'note': 'frames/s on a bounded sample of the same frame stream (the GPU arm '
+                           'runs all 65536 frames per step); steps capped at 20'},
+        'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': cpu['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -230,6 +270,16 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+
+def _gpu_numa_node(torch, local_rank):
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as f:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
 
 def _bind_near_gpu(torch, local_rank):
     """Multi-GPU runs: pin this rank to the CPUs NVML names for its GPU, so that the pinned host
@@ -258,246 +308,527 @@ def _bind_near_gpu(torch, local_rank):
         return None
 
 
-def gpu_arm(args):
-    import logging
-    logging.getLogger('libertem_b200').setLevel(logging.ERROR)
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """per-process state of the GPU arm"""
+
+    def __init__(self, args):
+        import logging
+        logging.getLogger('libertem_b200').setLevel(logging.ERROR)
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py needs a GPU (there is no CPU fallback; use --impl '
+                               'reference for the CPU arm)')
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device('cuda', self.local_rank)
+        self.cpu_affinity = None
+        self.numa_node = _gpu_numa_node(torch, self.local_rank)
+        if self.world > 1:
+            self.cpu_affinity = _bind_near_gpu(torch, self.local_rank)
+            dist.init_process_group('nccl', device_id=self.device)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device=self.device, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev_uniform(self, n, seed):
+        from libertem_b200 import engine
+        return engine.synth_fill((n,), np.float32, seed, self.device).cpu().numpy()
+
+
+def timed_steps(ctx, step, steps, finish=None):
+    """EXACTLY `steps` calls of step() between barrier + synchronize on both sides, CUDA events
+    on the launching stream, max over ranks.  Returns (ms per step, wall t0, wall t1)."""
+    torch = ctx.torch
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        step()
+    if finish is not None:
+        finish()
+    e1.record()
+    ctx.barrier()
+    t1 = time.time()
+    return ctx.max_over_ranks(e0.elapsed_time(e1)) / steps, t0, t1
+
+
+def rel_err_cols(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = np.abs(ref).reshape(-1, ref.shape[-1]).max(axis=0) + 1e-30
+    return float((np.abs(got - ref).reshape(-1, ref.shape[-1]) / scale).max())
+
+
+def parity_masks_com(ctx, udfs, shard_rows, first_frame, sig, n_masks, mask_seed, data_seed):
+    """first and last PARITY_FRAMES frames of this rank's shard: ApplyMasksUDF 'intensity' and
+    CoMUDF 'raw_mask_result' of the timed run vs the CPU oracle (oracle.udf_oracle.process_flat
+    on oracle.synth data).  shard_rows = (row0, row1) of the shard in the result buffers,
+    first_frame = dataset frame index of row0."""
+    k = sig[0] * sig[1]
+    masks_t, com_t = oracle_masks(sig, n_masks, mask_seed)
+    inten = udfs[0].results.get_buffer('intensity').tensor
+    raw = udfs[1].results.get_buffer('raw_mask_result').tensor
+    r0, r1 = shard_rows
+    n = min(PARITY_FRAMES, r1 - r0)
+    worst = 0.0
+    for a in sorted({r0, r1 - n}):
+        f0 = first_frame + (a - r0)
+        flat = oracle_frames(f0, f0 + n, k, data_seed)
+        ref_m, ref_c = cpu_pass(flat, masks_t, com_t)
+        worst = max(worst, rel_err_cols(inten[a:a + n].cpu().numpy(), ref_m),
+                    rel_err_cols(raw[a:a + n].cpu().numpy(), ref_c))
+    return ctx.max_over_ranks(worst)
+
+
+def read_only_probe(ctx, buf):
+    """GB/s of the read-only streaming probes over `buf` (device-resident, >> L2)"""
     from libertem_b200 import engine
-    from libertem_b200.io import SyntheticDataSet, MemoryDataSet
-    from libertem_b200.runner import UDFRunner, run_udf
+    torch = ctx.torch
+    nbytes = buf.numel() * buf.element_size()
+    out = {}
+    for mode, name in ((0, 'bulk_tma'), (1, 'ldg128')):
+        for _ in range(2):
+            engine.probe_read(buf, mode)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(5):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine.probe_read(buf, mode)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[name] = nbytes / best / 1e6
+    return out
+
+
+def dense_leg(ctx, nav_rank, n_masks, mask_seed, data_seed, steps, strong=False,
+              async_merge=True):
+    """ApplyMasksUDF(n_masks dense) + CoMUDF on a float32 256x256-sig dataset: every rank owns a
+    contiguous `nav_rank` shard of a (nav_rank[0] * world, nav_rank[1]) scan (weak; strong: the
+    caller passes the per-rank slice of a fixed scan).  Returns a dict incl. parity."""
+    torch = ctx.torch
+    from libertem_b200 import engine
+    from libertem_b200.io import SyntheticDataSet
+    from libertem_b200.runner import UDFRunner
     from libertem_b200.udf import ApplyMasksUDF, CoMUDF
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py needs a GPU (there is no CPU fallback; use --impl reference '
-                           'for the CPU arm)')
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    cpu_affinity = None
-    if world > 1:
-        cpu_affinity = _bind_near_gpu(torch, local_rank)
-        dist.init_process_group('nccl', device_id=device)
-    n_gpus = world
-
-    nav = (NAV[0] * n_gpus, NAV[1])
-    frames_per_rank = NAV[0] * NAV[1]
-    total_frames = frames_per_rank * n_gpus
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    nav = (nav_rank[0] * world, nav_rank[1])
+    frames_per_rank = nav_rank[0] * nav_rank[1]
+    total = frames_per_rank * world
     k = SIG[0] * SIG[1]
-
-    def dev_uniform(n, seed):
-        return engine.synth_fill((n,), np.float32, seed, device).cpu().numpy()
-
-    stack = bench_masks(SIG[0], SIG[1], N_MASKS, MASK_SEED, dev_uniform)
-    ds = SyntheticDataSet(nav + SIG, np.float32, seed=DATA_SEED, num_partitions=n_gpus)
+    stack = bench_masks(SIG[0], SIG[1], n_masks, mask_seed, ctx.dev_uniform)
+    ds = SyntheticDataSet(nav + SIG, np.float32, seed=data_seed, num_partitions=world)
     parts = list(ds.get_partitions())
-    my_parts = UDFRunner.my_partitions(parts, rank, n_gpus)
-    ds.materialize(device, my_parts)          # 16 GiB per rank, resident in HBM
+    mine = UDFRunner.my_partitions(parts, rank, world)
+    ds.materialize(device, mine)
     torch.cuda.synchronize()
-
-    def make_udfs():
-        return [ApplyMasksUDF(mask_factories=lambda: stack, mask_count=N_MASKS,
-                              mask_dtype=np.float32, use_sparse=False), CoMUDF()]
-
-    runner = UDFRunner(make_udfs())
+    udfs = [ApplyMasksUDF(mask_factories=lambda: stack, mask_count=n_masks,
+                          mask_dtype=np.float32, use_sparse=False), CoMUDF()]
+    runner = UDFRunner(udfs)
+    pending = []
 
     def step():
-        runner.run_for_dataset(ds, device=device, finalize=False)
+        res = runner.run_for_dataset(ds, device=device, finalize=False,
+                                     async_merge=async_merge and world > 1)
+        pending.append(res)
+        if len(pending) > 2:          # bound the number of result slabs in flight
+            pending.pop(0).wait()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def finish():
+        while pending:
+            pending.pop(0).wait()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(3):
         step()
-    barrier()
-    if os.environ.get('LTB_PROFILE'):
-        import cProfile
-        import pstats
-        pr = cProfile.Profile()
-        pr.enable()
-        for _ in range(10):
-            step()
-        torch.cuda.synchronize()
-        pr.disable()
-        pstats.Stats(pr, stream=sys.stderr).sort_stats('cumulative').print_stats(35)
+    finish()
+    engine.launch_count(reset=True)
+    engine.EVENT_LOG = []
+    ms, t0, t1 = timed_steps(ctx, step, steps, finish)
+    launches = engine.launch_count()
+    ev_log, engine.EVENT_LOG = engine.EVENT_LOG, None
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b, *_ in ev_log]))
+    bytes_per_launch = float(np.mean([f * kk * isz for _, _, f, kk, isz in ev_log]))
+    peak, _src = measured_peak()
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    err = parity_masks_com(ctx, udfs, (mine[0].start, mine[-1].stop), mine[0].start, SIG,
+                           n_masks, mask_seed, data_seed)
+    out = {'nav': list(nav), 'sig': list(SIG), 'n_masks': n_masks, 'fused_columns': n_masks + 3,
+           'frames': total, 'frames_per_gpu': frames_per_rank, 'steps': steps,
+           'ms_per_step': ms, 'frames_per_s': total / (ms * 1e-3),
+           'kernel': KERNEL_NAMES.get(engine.last_kernel(), str(engine.last_kernel())),
+           'kernel_ms': kern_ms, 'roofline_frac': achieved / peak, 'achieved_gbs': achieved,
+           'kernel_share_of_step': kern_ms * len(ev_log) / steps / ms,
+           'gpu_launches_per_step': launches / steps,
+           'merge': ('nccl all_gather of the nav slab per step, issued asynchronously (overlaps '
+                     'the next step\'s kernel), all completed inside the timed region')
+           if world > 1 else 'none (single rank)',
+           'parity_max_rel_err': err, 'parity_ok': bool(err <= PARITY_TOL)}
+    return out, ds, mine, stack, (t0, t1), launches, udfs
 
-    sampler = ClockSampler(local_rank)
+
+def config_legs(ctx):
+    """cfg3, cfg4 and the cfg5 shard on one GPU: one pass each through UDFRunner, device-timed,
+    with a first/last-frames oracle check"""
+    torch = ctx.torch
+    from libertem_b200 import engine, masks as M
+    from libertem_b200.io import SyntheticDataSet
+    from libertem_b200.runner import UDFRunner
+    from libertem_b200.udf import ApplyMasksUDF, SumUDF, SumSigUDF
+    from libertem_b200.api import Context
+    from oracle import udf_oracle as O
+    device = ctx.device
+    peak, _ = measured_peak()
+    out = {}
+
+    def timed(runner, ds, steps):
+        ds.materialize(device)
+        for _ in range(2):
+            runner.run_for_dataset(ds, device=device, finalize=False)
+        torch.cuda.synchronize()
+        engine.launch_count(reset=True)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            runner.run_for_dataset(ds, device=device, finalize=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        frames = ds.shape.nav.size
+        nbytes = ds.shape.size * ds.dtype.itemsize
+        return {'frames': frames, 'ms_per_pass': ms, 'frames_per_s': frames / ms * 1e3,
+                'achieved_gbs': nbytes / ms / 1e6, 'roofline_frac': nbytes / ms / 1e6 / peak,
+                'algorithmic_bytes': nbytes, 'launches_per_pass': engine.launch_count() / steps,
+                'kernel': KERNEL_NAMES.get(engine.last_kernel(), str(engine.last_kernel())),
+                'unfused_calls': runner.stats['unfused_calls']}
+
+    # ---- cfg3: 512x512 nav x 128x128 sig uint16, SumUDF + SumSigUDF + 4 sparse ring masks
+    try:
+        shape = (512, 512, 128, 128)
+        ds = SyntheticDataSet(shape, np.uint16, seed=103, num_partitions=1)
+        rings = [(8, 16), (20, 28), (32, 40), (44, 52)]
+        facs = [lambda ri=ri, ro=ro: M.ring(64, 64, 128, 128, ro, ri) for ri, ro in rings]
+        udfs = [SumUDF(), SumSigUDF(), ApplyMasksUDF(mask_factories=facs, use_sparse=True,
+                                                     mask_dtype=np.float32)]
+        runner = UDFRunner(udfs)
+        line = timed(runner, ds, 10)
+        # parity (bit-exact): first/last frames' SumSig + ring sums, and the frame sum of a slice
+        from oracle import masks_gen
+        k = 128 * 128
+        ring_stack = np.stack([masks_gen.ring(64, 64, 128, 128, ro, ri).astype(np.float32)
+                               for ri, ro in rings]).reshape(4, k)
+        n = shape[0] * shape[1]
+        sumsig = udfs[1].results.get_buffer('intensity').tensor
+        inten = udfs[2].results.get_buffer('intensity').tensor
+        exact = True
+        for f0 in (0, n - PARITY_FRAMES):
+            flat = oracle_frames(f0, f0 + PARITY_FRAMES, k, 103, np.uint16).astype(np.float32)
+            exact &= bool(np.array_equal(sumsig[f0:f0 + PARITY_FRAMES].cpu().numpy(),
+                                         flat.sum(axis=1, dtype=np.float64).astype(np.float32)))
+            exact &= bool(np.array_equal(inten[f0:f0 + PARITY_FRAMES].cpu().numpy(),
+                                         (flat.astype(np.float64) @ ring_stack.T.astype(np.float64)
+                                          ).astype(np.float32)))
+        line.update(parity='bit-exact vs oracle on the first / last %d frames (SumSigUDF, ring '
+                           'masks)' % PARITY_FRAMES if exact else 'MISMATCH', parity_ok=exact,
+                    workload='cfg3: 512x512 nav x 128x128 sig uint16, SumUDF + SumSigUDF + 4 '
+                             'sparse ring masks, one fused pass')
+        out['cfg3'] = line
+        del ds, runner, udfs
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['cfg3'] = {'error': repr(e)}
+
+    # ---- cfg5 shard: 128x1024 nav x 256x256 sig f32, 16 masks + CoM (what one of 8 GPUs holds)
+    try:
+        saved = ctx.world, ctx.rank
+        ctx.world, ctx.rank = 1, 0
+        try:
+            line, ds5, _, _, _, _, _ = dense_leg(ctx, (128, 1024), 16, 2005, 105, 5)
+        finally:
+            ctx.world, ctx.rank = saved
+        line['workload'] = ('cfg5 shard: 128x1024 nav x 256x256 sig float32, 16 dense masks + '
+                            'CoM (19 fused columns) = one of the 8 ranks of cfg5')
+        out['cfg5_shard'] = line
+        del ds5
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['cfg5_shard'] = {'error': repr(e)}
+
+    # ---- cfg4: 256x256 nav x 512x512 sig f32 (64 GiB resident), RadialFourierAnalysis 32 bins
+    try:
+        free, _total = torch.cuda.mem_get_info(device)
+        nav0 = 256 if free > (80 << 30) else 32
+        shape = (nav0, 256, 512, 512)
+        ds = SyntheticDataSet(shape, np.float32, seed=104, num_partitions=8)
+        a = Context().create_radial_fourier_analysis(ds, n_bins=32)
+        udf = a.get_udf()
+        runner = UDFRunner([udf])
+        line = timed(runner, ds, 2)
+        # parity: 16 first + 16 last frames vs the oracle's own mask stack (float64 direct sums)
+        p = O.radial_fourier_params((512, 512), n_bins=32)
+        stack = O.radial_mask_stack((512, 512), **p).reshape(800, -1)
+        k = 512 * 512
+        res = udf.results.get_buffer('intensity').tensor
+        n = shape[0] * shape[1]
+        worst = 0.0
+        for f0 in (0, n - 16):
+            flat = oracle_frames(f0, f0 + 16, k, 104).astype(np.float64)
+            ref = np.zeros((16, 800), dtype=np.complex128)
+            for b in range(32):
+                rows = stack[b * 25:(b + 1) * 25]
+                sup = np.nonzero(np.any(rows != 0, axis=0))[0]
+                ref[:, b * 25:(b + 1) * 25] = flat[:, sup] @ rows[:, sup].T.astype(np.complex128)
+            got = res[f0:f0 + 16].cpu().numpy().astype(np.complex128)
+            scale = np.abs(ref.reshape(16, 32, 25)[:, :, :1]).max(axis=0, keepdims=True)
+            worst = max(worst, float((np.abs(got - ref).reshape(16, 32, 25) / scale).max()))
+        line.update(parity_max_rel_err=worst, parity_ok=bool(worst <= PARITY_TOL),
+                    workload='cfg4: %dx256 nav x 512x512 sig float32%s, RadialFourierAnalysis 32 '
+                             'bins x 25 orders (800 complex masks), 8 partitions' %
+                             (nav0, '' if nav0 == 256 else ' (nav sub-sample: not enough HBM)'),
+                    bound='tensor / L2->SM fabric (group-sparse GEMM), reported against the HBM '
+                          'roofline of the frame bytes')
+        out['cfg4'] = line
+        del ds, runner, udf, a
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['cfg4'] = {'error': repr(e)}
+    return out
+
+
+def gpu_arm(args):
+    ctx = Ctx(args)
+    torch, dist = ctx.torch, ctx.dist
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    from libertem_b200 import engine
+    k = SIG[0] * SIG[1]
+    steps = args.steps
+    line_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line_cpu = cpu_leg(args.steps, args.warmup)        # before any GPU leg
+
+    sampler = ClockSampler(ctx.local_rank)
     sampler.start()
     t_wait = time.time()
     while not sampler.lines and time.time() - t_wait < 5.0:   # wait for the first sample
         time.sleep(0.01)
-    for _ in range(3):          # keep the GPU busy right up to the timed region
-        step()
-    engine.launch_count(reset=True)
-    engine.EVENT_LOG = []
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = engine.launch_count()
-    ev_log, engine.EVENT_LOG = engine.EVENT_LOG, None
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop(t_wall0, t_wall1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = total_frames / (ms_per_step * 1e-3)
-
-    # roofline of the dominant kernel, timed live on the launching stream
-    kernel_ms = [a.elapsed_time(b) for a, b, *_ in ev_log]
-    bytes_per_launch = float(np.mean([f * kk * isz for _, _, f, kk, isz in ev_log]))
-    kern_ms = float(np.mean(kernel_ms))
-    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    head, ds, mine, stack, (t0, t1), launches, _udfs = dense_leg(
+        ctx, NAV, N_MASKS, MASK_SEED, DATA_SEED, steps)
+    clocks = sampler.stop(t0, t1)
     peak, peak_src = measured_peak()
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel': {1: 'k1_dense_tma_kernel (even/odd tile)', 3: 'k1_pair_kernel<float> '
-                           '(mask-pair tile)', 6: 'k6_tensor_kernel (tcgen05 kind::tf32, '
-                           'split-TF32, TMEM accumulators)'}.get(engine.last_kernel(), 'generic'),
-                'kernel_ms': kern_ms,
-                'algorithmic_bytes_per_launch': bytes_per_launch,
-                'kernel_share_of_step': kern_ms * len(ev_log) / args.steps / ms_per_step}
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
-    # command (cfg2 shape); None for other workloads
-    prof = os.path.join(ROOT, 'profiles',
-                        'k6_traffic.json' if engine.last_kernel() == 6 else 'k1_traffic.json')
-    if os.path.exists(prof) and args.workload == 'cfg2':
-        try:
-            roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_launch')
-        except Exception:
-            pass
-
+    probe = read_only_probe(ctx, ds.partition_tensor(mine[0], device))
+    peak_ro = max(probe.values())
+    roofline = {'bound': 'hbm', 'achieved': head['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': head['roofline_frac'], 'traffic': None,
+                'traffic_source': 'not measured in this run; ncu capture of this command: '
+                                  'profiles/k6_traffic.json (17.196 GB per launch vs 17.180 GB '
+                                  'algorithmic)',
+                'peak_source': peak_src,
+                'peak_read_only': peak_ro, 'frac_read_only': head['achieved_gbs'] / peak_ro,
+                'peak_read_only_source': 'ltb200_probe_read over the same 17.18 GB shard in this '
+                                         'run (best of 5): %s' % json.dumps(
+                                             {n: round(v, 1) for n, v in probe.items()}),
+                'kernel': head['kernel'], 'kernel_ms': head['kernel_ms'],
+                'algorithmic_bytes_per_launch': float(NAV[0] * NAV[1] * k * 4),
+                'kernel_share_of_step': head['kernel_share_of_step']}
+    nav = (NAV[0] * world, NAV[1])
+    total_frames = NAV[0] * NAV[1] * world
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': n_gpus,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+        'metric': METRIC, 'value': head['frames_per_s'], 'unit': 'frames/s', 'n_gpus': world,
+        'steps': steps, 'warmup': 3, 'ms_per_step': head['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic (counter-based hash, uniform [0,1), seed %d)' % DATA_SEED,
         'config': {'workload': WORKLOAD, 'nav': list(nav), 'sig': list(SIG), 'n_masks': N_MASKS,
                    'com': True, 'fused_columns': N_MASKS + 3, 'partitions_per_gpu': 1,
-                   'sig_bytes_per_frame': k * 4,
-                   'frames_per_gpu': frames_per_rank,
+                   'sig_bytes_per_frame': k * 4, 'frames_per_gpu': NAV[0] * NAV[1],
                    'l2': 'inputs %.1f GB per GPU >> 126 MB L2, streamed once per step' %
-                         (frames_per_rank * k * 4 / 1e9),
-                   'merge': 'nccl all_gather of nav buffers inside the step' if world > 1
-                   else 'device-side copy into the nav-shaped buffers',
-                   'cpu_affinity': cpu_affinity},
-        'hbm_gbs': total_frames * k * 4 / (ms_per_step * 1e-3) / 1e9 / n_gpus,
+                         (NAV[0] * NAV[1] * k * 4 / 1e9),
+                   'merge': head['merge'], 'cpu_affinity': ctx.cpu_affinity,
+                   'gpu_numa_node': ctx.numa_node},
+        'hbm_gbs': total_frames * k * 4 / (head['ms_per_step'] * 1e-3) / 1e9 / world,
         'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches),
+        'parity': {'max_rel_err': head['parity_max_rel_err'], 'tol': PARITY_TOL,
+                   'ok': head['parity_ok'],
+                   'what': 'ApplyMasksUDF intensity + CoMUDF raw_mask_result of the timed run, '
+                           'first and last %d frames of every rank\'s shard vs '
+                           'oracle.udf_oracle.process_flat on oracle.synth data' % PARITY_FRAMES},
     }
+    ok = head['parity_ok']
 
-    if rank == 0 and world == 1 and not args.no_e2e:
-        line['e2e'] = e2e_leg(args, ds, my_parts[0], stack, device)
-    elif world > 1:
-        line['e2e'] = e2e_multi(args, ds, my_parts[0], stack, device, dist, total_frames)
-    if rank == 0 and world == 1 and not args.no_cpu:
-        n_frames = 2048
-        flat, masks_t, com_t = cpu_sample(n_frames)
-        fps, per_step, cores, which = run_cpu(flat, masks_t, com_t, 3, 1)
-        line['cpu_baseline'] = {
-            'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n_frames} frames (512 MiB) of the same stream, 3 passes after 1 warm-up, '
-                      f'one GEMM per UDF (8 masks + 3 CoM masks) as the reference does, faster '
-                      f'of torch.mm / numpy @ = {which}'}
+    if not args.no_e2e:
+        line['e2e'] = e2e_leg(ctx, ds, mine[0], stack, total_frames)
+    del ds
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_configs:
+        line['configs'] = config_legs(ctx)
+        ok = ok and all(c.get('parity_ok', False) for c in line['configs'].values()
+                        if 'error' not in c)
+    if world > 1 and not args.no_configs:
+        multi = {}
+        # cfg5: every rank holds a 128x1024-nav shard (at N=8 this IS BASELINE configs[4])
+        m5, ds5, *_ = dense_leg(ctx, (128, 1024), 16, 2005, 105, max(3, min(steps, 10)))
+        m5['workload'] = ('cfg5: %dx1024 nav x 256x256 sig float32, 16 dense masks + CoM, '
+                          '128x1024-nav shard per GPU%s' %
+                          (128 * world, ' (= BASELINE configs[4])' if world == 8 else
+                           ' (cfg5-class weak shard; the full 1024x1024 nav needs 8 GPUs)'))
+        multi['cfg5'] = m5
+        del ds5
+        torch.cuda.empty_cache()
+        # cfg2 strong scaling: ONE 256x256-nav dataset split over the ranks
+        ms2, ds2, *_ = dense_leg(ctx, (NAV[0] // world, NAV[1]), N_MASKS, MASK_SEED, DATA_SEED,
+                                 max(3, min(steps, 20)))
+        ms2['workload'] = 'cfg2 strong scaling: one 256x256 nav x 256x256 sig dataset over %d GPUs' % world
+        ms2['scaling'] = 'strong'
+        multi['cfg2_strong'] = ms2
+        del ds2
+        torch.cuda.empty_cache()
+        line['multi'] = multi
+        ok = ok and m5['parity_ok'] and ms2['parity_ok']
+    if line_cpu is not None:
+        line['cpu_baseline'] = {kk: line_cpu[kk] for kk in ('value', 'unit', 'cores', 'kind',
+                                                            'sample')}
+    line['parity']['all_ok'] = bool(ok)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
 
 
-def _host_copy(ds, part, device):
+def _host_copy(ctx, ds, part):
     """the rank's shard as a pinned host array (filled by D2H from the resident device data)"""
-    import torch
-    t = ds.partition_tensor(part, device)
+    torch = ctx.torch
+    t = ds.partition_tensor(part, ctx.device)
     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     host.copy_(t)
     torch.cuda.synchronize()
     return host
 
 
-def e2e_leg(args, ds, part, stack, device):
-    """end to end through run_udf(): HOST pinned input, H2D of every frame + D2H / get_results
-    of every result buffer inside the timed region"""
-    import torch
+def h2d_peak(ctx, host, chunk_frames=1024, reps=2):
+    """bare H2D: cudaMemcpyAsync of the whole pinned shard in chunks into one device buffer, all
+    ranks at the same time; GB/s per GPU (min over ranks = what every rank is guaranteed)"""
+    torch = ctx.torch
+    flat = host.reshape(host.shape[0], -1)
+    dst = torch.empty((chunk_frames, flat.shape[1]), dtype=flat.dtype, device=ctx.device)
+    best = None
+    for _ in range(reps):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for f0 in range(0, flat.shape[0], chunk_frames):
+            n = min(chunk_frames, flat.shape[0] - f0)
+            dst[:n].copy_(flat[f0:f0 + n], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    gbs = flat.numel() * flat.element_size() / best / 1e9
+    return -ctx.max_over_ranks(-gbs)
+
+
+def e2e_leg(ctx, ds, part, stack, total_frames):
+    """end to end through the public API on HOST pinned input: H2D of every frame, the kernel,
+    the NCCL all-gather (N>1) and D2H / get_results of every result buffer inside the timed
+    region, every step"""
+    torch = ctx.torch
     from libertem_b200.io import MemoryDataSet
-    from libertem_b200.runner import run_udf
+    from libertem_b200.runner import UDFRunner
     from libertem_b200.udf import ApplyMasksUDF, CoMUDF
-    host = _host_copy(ds, part, device)
-    hds = MemoryDataSet(data=host.reshape(NAV + SIG), num_partitions=1, sig_dims=2, pin=False)
-    steps = min(args.steps, 3)
+    world = ctx.world
+    host = _host_copy(ctx, ds, part)
+    peak = h2d_peak(ctx, host)
+    if world == 1:
+        hds = MemoryDataSet(data=host.reshape(NAV + SIG), num_partitions=1, sig_dims=2, pin=False)
+    else:
+        # every rank sees the same (256 * world) x 256 scan; only its own shard is backed by
+        # (pinned) host memory -- ranks never touch the other partitions
+        hds = ShardedHostDataSet(host, (NAV[0] * world, NAV[1]) + SIG, ctx.rank, world)
+    steps = min(ctx.args.steps, 3 if world == 1 else 2)
 
     def one():
-        res = run_udf(hds, [ApplyMasksUDF(mask_factories=lambda: stack, mask_count=N_MASKS,
-                                          mask_dtype=np.float32, use_sparse=False), CoMUDF()],
-                      device=device)
+        r = UDFRunner([ApplyMasksUDF(mask_factories=lambda: stack, mask_count=N_MASKS,
+                                     mask_dtype=np.float32, use_sparse=False), CoMUDF()])
+        res = r.run_for_dataset(hds, device=ctx.device).buffers
         return res[0]['intensity'].raw_data, res[1]['field'].raw_data
 
     one()
-    torch.cuda.synchronize()
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         a, b = one()
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps
-    d2h = NAV[0] * NAV[1] * (N_MASKS + 3) * 4
-    return {'value': NAV[0] * NAV[1] / dt, 'unit': 'frames/s',
-            'h2d_bytes_per_step': int(host.numel() * host.element_size()),
-            'd2h_bytes_per_step': int(d2h), 'steps': steps, 'ms_per_step': dt * 1e3,
-            'note': 'run_udf on a pinned host dataset: double-buffered H2D tiles overlapped with '
-                    'the kernel; includes CoM get_results on the host'}
+    if world > 1:
+        ctx.dist.barrier()
+    dt = ctx.max_over_ranks((time.perf_counter() - t0) / steps)
+    assert a.shape[0] == total_frames
+    h2d = int(host.numel() * host.element_size()) * world
+    gbs = h2d / world / dt / 1e9
+    return {'value': total_frames / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
+            'd2h_bytes_per_step': int(total_frames * (N_MASKS + 3) * 4) * world, 'steps': steps,
+            'ms_per_step': dt * 1e3, 'h2d_gbs_per_gpu': gbs, 'h2d_peak_gbs': peak,
+            'h2d_frac_of_peak': gbs / peak,
+            'note': 'run_for_dataset on pinned host data: double-buffered H2D tiles overlapped '
+                    'with the kernel' + (', NCCL all-gather of the result slab' if world > 1
+                                         else '') + ', D2H of all result buffers and CoM '
+                    'get_results on the host; h2d_peak_gbs = bare cudaMemcpyAsync of the same '
+                    'pinned shard on all ranks concurrently (min over ranks)'}
 
 
-def e2e_multi(args, ds, part, stack, device, dist, total_frames):
-    import torch
-    from libertem_b200.io import MemoryDataSet
-    from libertem_b200.runner import run_udf
-    from libertem_b200.udf import ApplyMasksUDF, CoMUDF
-    host = _host_copy(ds, part, device)
-    hds = MemoryDataSet(data=host.reshape(NAV + SIG), num_partitions=1, sig_dims=2, pin=False)
-    steps = min(args.steps, 2)
+class ShardedHostDataSet:
+    """MemoryDataSet-compatible view of a multi-rank scan whose partitions live in per-rank
+    pinned host memory: partition r is backed by rank r's array only"""
 
-    def one():
-        # every rank runs its shard from host memory; results come back per rank
-        from libertem_b200.runner import UDFRunner
-        r = UDFRunner([ApplyMasksUDF(mask_factories=lambda: stack, mask_count=N_MASKS,
-                                     mask_dtype=np.float32, use_sparse=False), CoMUDF()])
-        # shard-local run (no collective on the e2e leg; the device-timed leg has it)
-        saved = UDFRunner._dist
-        UDFRunner._dist = staticmethod(lambda: None)
-        try:
-            res = r.run_for_dataset(hds, device=device).buffers
-        finally:
-            UDFRunner._dist = saved
-        return res[0]['intensity'].raw_data
+    def __new__(cls, host, shape, rank, world):
+        from libertem_b200.io.memory import MemoryDataSet
+        from libertem_b200.common.shape import Shape
 
-    one()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = (time.perf_counter() - t0) / steps
-    t = torch.tensor([dt], device=device, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    return {'value': total_frames / dt, 'unit': 'frames/s',
-            'h2d_bytes_per_step': int(host.numel() * host.element_size()) * dist.get_world_size(),
-            'd2h_bytes_per_step': int(total_frames * (N_MASKS + 3) * 4), 'steps': steps,
-            'ms_per_step': dt * 1e3,
-            'note': 'each rank streams its shard from pinned host memory (PCIe-bound)'}
+        class _DS(MemoryDataSet):
+            def __init__(self):
+                self._is_torch = True
+                self.data = host
+                self._shape = Shape(tuple(shape), sig_dims=2)
+                self._dtype = np.dtype('float32')
+                self.tileshape = None
+                self.num_partitions = world
+                self.tile_depth = None
+                self._pin = False
+                self._registered = False
+                self._stage = {}
+                self._first = rank * host.shape[0]
+
+            def _flat(self):
+                return _Offset(self.data.reshape((host.shape[0],) + tuple(shape[2:])),
+                               self._first)
+
+        class _Offset:
+            """frames [first, first + n) of the scan"""
+
+            def __init__(self, t, first):
+                self.t, self.first = t, first
+                self.is_cuda = False
+                self.dtype = t.dtype
+
+            def __getitem__(self, sl):
+                return self.t[sl.start - self.first:sl.stop - self.first]
+
+        return _DS()
 
 
 def set_workload(name):
@@ -520,6 +851,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-configs', action='store_true')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg5'])
     args = ap.parse_args()
     set_workload(args.workload)

@@ -160,7 +160,10 @@ LTB_API int ltb200_set_k1_variant(int variant);
 
 /* which kernel the last ltb200_masks_dense call on this thread selected:
  * 1 = TMA-staged kernel (even/odd tile), 3 = TMA-staged kernel (mask-pair tile),
- * 2 = generic kernel, 6 = tcgen05 tensor-core kernel (diagnostics / tests) */
+ * 2 = generic kernel, 6 = tcgen05 tensor-core kernel; and for the other entry points:
+ * 8 = int8 tensor-core kernel (K8), 20 = sparse CSC kernel (K2), 4 = group-sparse FFMA2
+ * kernel (K4), 5 = shifted-mask kernel (K5), 7 / 70 / 71 = group-sparse tensor-core kernel (K7)
+ * with the ring-major / quad-banded / mirror-symmetric plan (diagnostics / tests) */
 LTB_API int ltb200_last_kernel(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 LTB_API int64_t ltb200_launch_count(int reset);
@@ -266,6 +269,16 @@ LTB_API int ltb200_group_masks_tc_sym(const float* tile, int64_t n_frames, int64
  * ------------------------------------------------------------------------------------- */
 LTB_API int ltb200_synth_fill(void* dst, int dtype, int64_t start, int64_t count, uint32_t seed,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Read-only HBM streaming probe (measurement only, not on the product path): reads `bytes`
+ * bytes of `buf` once with the grid shape of the masked-reduction kernels (one persistent CTA
+ * per SM) and does nothing with them.  mode 0: bulk TMA copies into a shared-memory ring
+ * (the ingest half of K6 / K8, no math); mode 1: LDG.128 into registers (`sink`: 4-byte device
+ * scratch).  bench.py times it to report `roofline.peak_read_only` next to the copy-benchmark
+ * peak of MEASURED_PEAKS.json.
+ * ------------------------------------------------------------------------------------- */
+LTB_API int ltb200_probe_read(const void* buf, size_t bytes, int mode, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,7 @@ static int launch_csc(const void* tile, int64_t F, int64_t ld, const int32_t* in
     k2_csc_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)tile, F, ld, indptr, indices, values,
                                                   n_masks, out, ldo, accumulate);
     count_launch();
+    set_last_kernel(20);
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
 }

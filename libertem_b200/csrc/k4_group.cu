@@ -317,6 +317,7 @@ extern "C" int ltb200_group_masks(const void* tile, int tile_dtype, int64_t n_fr
     if (p.n_items < grid) grid = (int)p.n_items;
     k4_group_kernel<<<grid, K4_THREADS, smem, st>>>(tm, p);
     count_launch();
+    set_last_kernel(4);
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
 }

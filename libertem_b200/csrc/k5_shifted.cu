@@ -67,6 +67,7 @@ static int launch_shifted(const void* tile, int64_t F, int sy, int sx, int64_t l
                                                       n_masks, ldm, shifts, per_frame, out, ldo,
                                                       accumulate);
     count_launch();
+    set_last_kernel(5);
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
 }

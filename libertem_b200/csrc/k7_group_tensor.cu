@@ -876,6 +876,7 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
         default: rc = k7_launch<112, false>(tm, tmt, p, grid, st); break;
     }
     if (rc != LTB_OK) return rc;
+    set_last_kernel(sym ? 71 : (quad ? 70 : 7));
     if (banded) {
         const int64_t total = n_frames * (int64_t)n_rings * n_pairs * 2;
         int64_t blocks = (total + 255) / 256;

@@ -282,3 +282,14 @@ def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
             masks.shape[1], shifts.data_ptr(), per_frame, out.data_ptr(), ld_out,
             int(bool(accumulate)), _stream_ptr(tile.device)))
     return out
+
+
+def probe_read(buf, mode=0):
+    """read-only streaming probe over a CUDA tensor (measurement only): mode 0 bulk-TMA ingest
+    into shared memory, mode 1 LDG.128 (include/ltb200.h: ltb200_probe_read)"""
+    _require_cuda(buf, 'buf')
+    lib = get_lib()
+    sink = _workspace(buf.device, 4)
+    with torch.cuda.device(buf.device):
+        check(lib.ltb200_probe_read(buf.data_ptr(), buf.numel() * buf.element_size(), int(mode),
+                                    sink.data_ptr(), _stream_ptr(buf.device)))

@@ -75,9 +75,17 @@ def int8_digit_plan(rows, max_rows=16):
 
 
 class UDFResults:
-    def __init__(self, buffers, damage):
+    def __init__(self, buffers, damage, pending=None):
         self.buffers = buffers
         self.damage = damage
+        self._pending = pending or []     # (collective work handle, tensors kept alive)
+
+    def wait(self):
+        """``async_merge`` runs: make the current stream wait for this run's collectives"""
+        for work, _keep in self._pending:
+            work.wait()
+        self._pending = []
+        return self
 
 
 class ResultBuffer(BufferWrapper):
@@ -129,7 +137,7 @@ class UDFRunner:
     # -- main entry -------------------------------------------------------------------------------
     def run_for_dataset(self, dataset, executor=None, roi=None, progress=False,
                         corrections=None, backends=None, dry=False, device=None,
-                        finalize=True, use_merge_all=False):
+                        finalize=True, use_merge_all=False, async_merge=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
@@ -208,8 +216,14 @@ class UDFRunner:
                 for ui, (udf, parts_) in enumerate(zip(udfs, collected)):
                     if parts_:
                         udf._do_merge_all(parts_)
+        pending = []
         if dist:
-            self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device)
+            # async_merge (only with finalize=False, i.e. results stay on the device): the
+            # collectives are issued asynchronously -- they wait for this run's kernels but the
+            # launching stream does not wait for them, so the next run's kernels overlap them;
+            # the caller completes them with UDFResults.wait()
+            self._merge_ranks(dist, udfs, partitions, roi_flat, damage, device,
+                              pending=pending if (async_merge and not finalize) else None)
         if self._corr is not None and self._sig_sum_folded:
             n_done = int(damage.sum())
             for udf, name in self._sig_sum_folded:
@@ -220,7 +234,7 @@ class UDFRunner:
         if not finalize:
             # hot path only (tiles -> kernels -> merge [-> collectives]); results stay in
             # the UDFs' device buffers (udf.results)
-            return UDFResults(buffers=None, damage=damage)
+            return UDFResults(buffers=None, damage=damage, pending=pending)
         return UDFResults(buffers=self._make_results(udfs, ds_shape, roi, damage), damage=damage)
 
     # -- per partition ------------------------------------------------------------------------------
@@ -615,7 +629,7 @@ class UDFRunner:
         damage[r0:r1] = True
 
     @staticmethod
-    def _gather_rows(dist, comm, bounds, equal):
+    def _gather_rows(dist, comm, bounds, equal, pending=None):
         """assemble a nav buffer whose rows [a_r, b_r) are valid on rank r: all-gather of the
         contiguous row blocks; ragged blocks are padded to the largest one.  bool / complex
         buffers travel as bytes / real pairs (NCCL has no bool, gloo no complex)."""
@@ -629,6 +643,11 @@ class UDFRunner:
         if not comm.is_contiguous():
             raise UDFException('nav buffers must be contiguous for the multi-rank merge')
         if equal:
+            if pending is not None:
+                work = dist.all_gather_into_tensor(comm.view(-1), comm[a:b].contiguous().view(-1),
+                                                   async_op=True)
+                pending.append((work, comm))
+                return orig
             dist.all_gather_into_tensor(comm.view(-1), comm[a:b].contiguous().view(-1))
             return orig
         width = max(bb - aa for aa, bb in bounds)
@@ -645,7 +664,7 @@ class UDFRunner:
                 comm[aa:bb] = gathered[r, :bb - aa]
         return orig
 
-    def _merge_ranks(self, dist, udfs, partitions, roi_flat, damage, device):
+    def _merge_ranks(self, dist, udfs, partitions, roi_flat, damage, device, pending=None):
         """assemble the dataset-sized buffers across ranks.
 
         * the fused slab and every nav buffer of a UDF with the *default* merge: all-gather of
@@ -678,7 +697,8 @@ class UDFRunner:
         if self._slab is not None:
             t = self._slab
             comm = on_wire(t)
-            self._gather_rows(dist, comm, bounds, equal)
+            self._gather_rows(dist, comm, bounds, equal,
+                              pending=pending if comm is t else None)
             if comm is not t:
                 t.copy_(comm)
         for ui, udf in enumerate(udfs):

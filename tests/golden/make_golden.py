@@ -159,6 +159,66 @@ def g_cfg4_small():
         save('cfg4_small_' + ('sparse' if use_sparse else 'dense'), meta, **arrays)
 
 
+def g_cfg4_k7():
+    # RadialFourierAnalysis at a size where this repo's DEFAULT kernel (K7, tcgen05 group-sparse,
+    # >= 96 frames per tile) runs: 16x16 nav x 128x128 sig f32, 8 bins, max_order 24, ONE
+    # partition (256 frames).  'centre': default cx/cy (mirror-symmetric plan applies);
+    # 'offcentre': cx/cy off the pixel grid with an inner radius (banded plan only).
+    shape = (16, 16, 128, 128)
+    data = synth.dataset(shape, np.float32, seed=114)
+    ex = InlineJobExecutor()
+    cases = {'centre': {'n_bins': 8},
+             'offcentre': {'n_bins': 5, 'cx': 60.5, 'cy': 70.25, 'ri': 6., 'ro': 50.,
+                           'max_order': 12}}
+    for name, params in cases.items():
+        ds = MemoryDataSet(data=data, num_partitions=1, sig_dims=2)
+        ds.initialize(ex)
+        a = RadialFourierAnalysis(dataset=ds, parameters=dict(params))
+        udf = a.get_udf()
+        res = UDFRunner([udf]).run_for_dataset(ds, ex)
+        inten = res.buffers[0]['intensity'].data
+        p = a.parameters
+        raw = inten.reshape((256, -1)).T.reshape((p['n_bins'], p['max_order'] + 1, 16, 16))
+        meta = dict(shape=shape, data_seed=114, num_partitions=1,
+                    params={k: (v if not isinstance(v, (np.generic,)) else v.item())
+                            for k, v in p.items() if k not in ('mask_dtype', 'use_sparse')},
+                    call={k: v for k, v in params.items()})
+        save('cfg4_k7_' + name, meta, raw_results=raw.astype(np.complex64))
+
+
+def g_radial_symmetries():
+    # the reference's known-answer test tests/analysis/test_analysis_radialfourier.py:78-188:
+    # four CBED frames with 1- / 2- / 4-fold symmetric spot arrangements; here the 2x2 scan is
+    # tiled to 16x16 (256 frames, one partition) so that the run goes through K7.  Inputs come
+    # from the reference's generator (libertem.utils.generate.cbed_frame) and are stored (they
+    # are mostly zeros and compress to a few KB).
+    from libertem.utils.generate import cbed_frame
+    (d1, i1, p1) = cbed_frame(all_equal=True, radius=3, indices=np.array([(1, 0)]))
+    (d2, i2, p2) = cbed_frame(all_equal=True, radius=3, indices=np.array([(-1, 0)]))
+    (d3, i3, p3) = cbed_frame(all_equal=True, radius=3, indices=np.array([(1, 0), (-1, 0)]))
+    (d4, i4, p4) = cbed_frame(
+        all_equal=True, radius=3, indices=np.array([(1, 0), (-1, 0), (0, 1), (0, -1)]))
+    frames = np.stack([d1[0], d2[0], d3[0], d4[0]]).astype(np.float32)
+    data = np.zeros((16, 16) + frames.shape[1:], dtype=np.float32)
+    for i in range(16):
+        for j in range(16):
+            data[i, j] = frames[(i % 2) * 2 + (j % 2)]
+    r = np.linalg.norm(p2[0] - p1[0]) / 2
+    cy, cx = (p2[0] + p1[0]) / 2
+    ex = InlineJobExecutor()
+    ds = MemoryDataSet(data=data, num_partitions=1, sig_dims=2)
+    ds.initialize(ex)
+    params = dict(cy=float(cy), cx=float(cx), ri=0, ro=float(r + 4), n_bins=2, max_order=8)
+    a = RadialFourierAnalysis(dataset=ds, parameters=dict(params))
+    res = UDFRunner([a.get_udf()]).run_for_dataset(ds, ex)
+    inten = res.buffers[0]['intensity'].data
+    p = a.parameters
+    raw = inten.reshape((256, -1)).T.reshape((p['n_bins'], p['max_order'] + 1, 16, 16))
+    save('radial_symmetries', dict(call=params, num_partitions=1, shape=list(data.shape)),
+         frames=frames, raw_results=raw.astype(np.complex64),
+         frame_sums=frames.sum(axis=(1, 2), dtype=np.float64))
+
+
 def g_com_params():
     # CoM with disk/ring, rotation, flip, regression on a non-square nav/sig
     shape = (12, 10, 32, 40)

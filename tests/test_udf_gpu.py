@@ -554,7 +554,7 @@ def test_host_streaming_many_partitions_no_buffer_reuse_race(lt):
     Run repeatedly (the race was timing dependent) on a stream kept busy."""
     shape = (16, 24, 64, 64)
     data = synth.dataset(shape, np.float32, 91)
-    masks = mixed_masks(4, 64, 64, 5)
+    masks = mixed_masks(64, 64, 4, 5)
     ref = O.apply_masks(data, masks, num_partitions=6)
     ref_sum = data.reshape(-1, 64 * 64).sum(axis=0, dtype=np.float64)
     ds = lt.MemoryDataSet(data=data, num_partitions=6, sig_dims=2, tile_depth=11)
@@ -574,7 +574,7 @@ def test_merge_all_matches_merge(lt):
     udf/sum.py:54-58) gives the same buffers as the sequential merge"""
     shape = (6, 8, 32, 32)
     data = synth.dataset(shape, np.float32, 17)
-    masks = mixed_masks(3, 32, 32, 2)
+    masks = mixed_masks(32, 32, 3, 2)
     src = torch.from_numpy(data).cuda()
     out = []
     for use in (False, True):
@@ -637,7 +637,7 @@ def test_corrections_do_not_leak_between_runs(lt):
     tiling must not apply the previous run's dark / gain"""
     from libertem_b200.corrections import CorrectionSet
     data = synth.dataset((4, 4, 16, 16), np.float32, 9)
-    masks = mixed_masks(2, 16, 16, 1)
+    masks = mixed_masks(16, 16, 2, 1)
     ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=2, sig_dims=2,
                           tileshape=(4, 8, 16))
     runner = lt.UDFRunner([lt.udf.ApplyMasksUDF(mask_factories=lambda: masks)])
@@ -649,3 +649,84 @@ def test_corrections_do_not_leak_between_runs(lt):
         close_cols(got, want)
         outs.append(got)
     assert not np.allclose(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('name', ['centre', 'offcentre'])
+@pytest.mark.parametrize('kernel', ['auto', 'banded', 'ffma'])
+def test_cfg4_k7_radial_fourier_golden(lt, name, kernel, monkeypatch):
+    """RadialFourierAnalysis vs the unmodified reference at a size where the DEFAULT kernel
+    (K7: tcgen05 group-sparse, >= 96 frames per tile) runs: 256 frames, one partition
+    (reference analysis/radialfourier.py:106-146,184-194).  'auto' must pick K7."""
+    from libertem_b200 import engine, group_masks as gm
+    meta, g = load_golden('cfg4_k7_' + name)
+    data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=1, sig_dims=2)
+    ctx = lt.Context()
+    a = ctx.create_radial_fourier_analysis(ds, **meta['call'])
+    for k in ('cx', 'cy', 'ri', 'ro', 'n_bins', 'max_order', 'mask_count'):
+        assert a.parameters[k] == pytest.approx(meta['params'][k]), k
+    if kernel != 'auto':
+        orig = gm.group_masks
+        monkeypatch.setattr(gm, 'group_masks',
+                            lambda *args, **kw: orig(*args, **{**kw, 'kernel': kernel}))
+    res = ctx.run(a)
+    want_kernel = {'auto': (70, 71), 'banded': (70,), 'ffma': (4,)}[kernel]
+    assert engine.last_kernel() in want_kernel, engine.last_kernel()
+    raw = res.raw_results
+    ref = g['raw_results']
+    assert raw.shape == ref.shape and raw.dtype == np.complex64
+    # per (bin, order) scale, like close_cols: every output column within 1e-5 of its own
+    # magnitude scale (the o = 0 column of its bin bounds |sum| of every order of that bin)
+    scale = np.abs(ref[:, :1]).max(axis=(2, 3), keepdims=True)
+    err = (np.abs(raw - ref) / scale).max()
+    assert err <= RTOL, err
+
+
+@pytest.mark.parametrize('kernel', ['auto', 'ffma'])
+def test_radial_fourier_symmetries_known_answer(lt, kernel, monkeypatch):
+    """the reference's known-answer test tests/analysis/test_analysis_radialfourier.py:78-188
+    (CBED frames with 1- / 2- / 4-fold spot symmetry), tiled to 256 frames so that it runs
+    through K7; inputs from the reference's cbed_frame generator (golden fixture), checked
+    against the reference's outputs AND against the analytic statements of that test."""
+    from libertem_b200 import engine, group_masks as gm
+    meta, g = load_golden('radial_symmetries')
+    frames = g['frames']
+    data = np.zeros((16, 16) + frames.shape[1:], dtype=np.float32)
+    for i in range(16):
+        for j in range(16):
+            data[i, j] = frames[(i % 2) * 2 + (j % 2)]
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=1, sig_dims=2)
+    ctx = lt.Context()
+    a = ctx.create_radial_fourier_analysis(ds, **meta['call'])
+    if kernel != 'auto':
+        orig = gm.group_masks
+        monkeypatch.setattr(gm, 'group_masks',
+                            lambda *args, **kw: orig(*args, **{**kw, 'kernel': kernel}))
+    res = ctx.run(a)
+    assert engine.last_kernel() in ((70, 71, 7) if kernel == 'auto' else (4,))
+    raw = res.raw_results
+    ref = g['raw_results']
+    tot = float(g['frame_sums'].max())
+    assert np.abs(raw - ref).max() <= RTOL * tot
+    sums = data.sum(axis=(2, 3), dtype=np.float64)
+    # bin 0 holds (numerically) nothing, so its channels are not normalised (normal = max(1, .));
+    # bin 1's higher orders are divided by |c_1_0| = the frame sum
+    tol = dict(atol=2e-5 * tot, rtol=1e-5)
+    tol1 = dict(atol=2e-5, rtol=1e-5)
+    c = lambda b, o: res[f'complex_{b}_{o}'].raw_data[:2, :2]      # the original 2x2 scan
+    np.testing.assert_allclose(np.abs(c(0, 0)), 0, **tol)
+    np.testing.assert_allclose(np.abs(c(1, 0)), sums[:2, :2], rtol=1e-5)
+    for o in (1, 2, 3, 4, 5):
+        np.testing.assert_allclose(np.abs(c(0, o)), 0, **tol)
+    # odd harmonics suppressed in 2-fold symmetry, 2-fold suppressed in 4-fold symmetry
+    for o in (1, 3, 5, 7):
+        np.testing.assert_allclose(np.abs(c(1, o)[1]), 0, **tol1)
+    np.testing.assert_allclose(np.abs(c(1, 2)[1, 1]), 0, **tol1)
+    assert np.all(np.abs(c(1, 1)[0]) > 0.1)
+    np.testing.assert_allclose(np.angle(c(1, 1)[0, 0]), np.pi / 2, atol=1e-4)
+    np.testing.assert_allclose(np.angle(c(1, 1)[0, 1]), -np.pi / 2, atol=1e-4)
+    np.testing.assert_allclose(np.abs(np.angle(c(1, 2)[0])), np.pi, atol=1e-4)
+    np.testing.assert_allclose(np.angle(c(1, 3)[0, 0]), -np.pi / 2, atol=1e-4)
+    np.testing.assert_allclose(np.angle(c(1, 3)[0, 1]), np.pi / 2, atol=1e-4)
+    np.testing.assert_allclose(np.angle(c(1, 4)), 0, atol=1e-4)
+    np.testing.assert_allclose(np.angle(c(1, 8)), 0, atol=1e-4)
