@@ -44,9 +44,13 @@ constexpr int K7_DSTAGES = 3;          // gathered data stages (ring size; p.dst
 constexpr int K7_TSTAGES = 3;          // weight-table stages (ring size; p.tstages in use)
 constexpr int K7_QLEN = 8;             // items queued from the gather producers to the table warp
 constexpr int K7_AS = 4;              // TMEM operand ring (sub-tiles)
-constexpr int K7_PWARPS = 4;
+#ifndef K7_PWARPS_N
+#define K7_PWARPS_N 4
+#endif
+constexpr int K7_PWARPS = K7_PWARPS_N;   // gather producer warps (multiple of 4: keeps warp % 4 = lane quarter)
 constexpr int K7_CWARPS = 8;
-constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + 2) * 32;   // + MMA warp + table warp
+constexpr int K7_DWARPS = 4;          // accumulator drain warps, one per TMEM lane quarter
+constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + K7_DWARPS + 2) * 32;   // + MMA + table warp
 constexpr uint32_t K7_SUB_BYTES = K7_FB * 32 * 4;          // 16 KiB per sub-tile
 constexpr uint32_t K7_DATA_BYTES = 2 * K7_SUB_BYTES;
 constexpr int K7_TMEM_COLS = 512;
@@ -70,9 +74,6 @@ struct K7Params {
     int n_bands;                   // banded plan: groups = n_bands x n_rings, band-major
     int prefetch;                  // banded plan: dense L2 prefetch of the next band
     int quad;                      // entry_px lists QUADS (4 consecutive, 16-byte aligned pixels)
-    int dstages;                   // data stages in use (<= K7_DSTAGES)
-    int tstages;                   // table stages in use (<= K7_TSTAGES)
-    int late_release;              // converters free a data stage after converting it (A/B)
     int64_t sig_size;
 };
 
@@ -163,6 +164,15 @@ __device__ __forceinline__ void k7_ld8(uint32_t taddr, uint32_t (&r)[8]) {
           "=r"(r[7])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void k7_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void k7_ld_fence4(uint32_t (&r)[4]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
 }
 __device__ __forceinline__ void k7_ld_fence8(uint32_t (&r)[8]) {
     asm volatile(""
@@ -264,7 +274,9 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
     uint64_t* tab_free = tab_full + K7_TSTAGES;                             // [TSTAGES]
     uint64_t* a_full = tab_free + K7_TSTAGES;                               // [AS]
     uint64_t* mma_done = a_full + K7_AS;                                    // [AS]
-    uint64_t* q_full = mma_done + K7_AS;                                    // [QLEN]
+    uint64_t* acc_full = mma_done + K7_AS;                                  // [2]
+    uint64_t* acc_free = acc_full + 2;                                      // [2]
+    uint64_t* q_full = acc_free + 2;                                        // [QLEN]
     uint64_t* q_free = q_full + K7_QLEN;                                    // [QLEN]
     K7Meta* meta = reinterpret_cast<K7Meta*>(q_free + K7_QLEN);             // [DSTAGES]
     K7Meta* tmeta = meta + K7_DSTAGES;                                      // [TSTAGES]
@@ -274,8 +286,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    constexpr int MMA_WARP = K7_PWARPS + K7_CWARPS;
+    constexpr int DRAIN_WARP0 = K7_PWARPS + K7_CWARPS;        // a multiple of 4: warp % 4 =
+    constexpr int MMA_WARP = DRAIN_WARP0 + K7_DWARPS;         // TMEM lane quarter
     constexpr int TABLE_WARP = MMA_WARP + 1;
+    static_assert(DRAIN_WARP0 % 4 == 0 && K7_DWARPS == 4, "K7: one drain warp per lane quarter");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K7_DSTAGES; s++) {
@@ -290,9 +304,13 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
             mbar_init(&a_full[s], K7_CWARPS);
             mbar_init(&mma_done[s], 1);
         }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_free[s], K7_DWARPS);
+        }
         for (int s = 0; s < K7_QLEN; s++) {
             mbar_init(&q_full[s], 1);
-            mbar_init(&q_free[s], 1);
+            mbar_init(&q_free[s], 1 + K7_DWARPS);     // table warp + the drain warps read it
         }
         fence_mbar_init();
     }
@@ -326,8 +344,9 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     ((((uint32_t)(el >> 2)) ^ (uint32_t)c) << 4) + (uint32_t)(el & 3) * 4u;
         // quad plan: 16 quads per stage; thread = (quad qd of sub-tile qsub, rows rg + 8 j)
         const int qd = pt & 7, qsub = (pt >> 3) & 1, rg = pt >> 4;
-        uint32_t it = 0, qn = 0;
-        const uint32_t nd = (uint32_t)p.dstages;
+        uint32_t qn = 0;
+        int stage = 0;                 // data ring position (no division in the stage loop)
+        uint32_t dphase = 0;
         while (true) {
             if (pt == 0) *cur_item = atomicAdd(p.counter, 1);
             named_bar_sync(2, K7_PWARPS * 32);
@@ -363,7 +382,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 if (nchunks == 0) continue;   // empty ring: nothing to add
             }
             if (pt == 0) {
-                // hand the item to the weight-table warp
+                // hand the item to the weight-table warp and the drain warps
                 const int q = qn % K7_QLEN;
                 mbar_wait(&q_free[q], ((qn / K7_QLEN) & 1) ^ 1);
                 queue[q] = K7QItem{done ? -1 : item, e0, nchunks, 0};
@@ -377,24 +396,24 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
             int px_next = done ? 0
                                : (p.quad ? p.entry_px[(e0 >> 2) + qsub * 8 + qd]
                                          : p.entry_px[e0 + sub * 32 + el]);
-            for (int c = 0; c < nchunks; c++, it++) {
-                const int stage = (int)(it % nd);
-                mbar_wait(&data_free[stage], ((it / nd) & 1) ^ 1);
+            for (int c = 0; c < nchunks; c++) {
+                mbar_wait(&data_free[stage], dphase ^ 1);
                 uint8_t* dst = smem + (size_t)stage * K7_DATA_BYTES;
+                uint64_t* full = &data_full[stage];
+                if (pt == 0) {
+                    // sentinel stage (done): tells the converters to stop (all arrivals, no data)
+                    meta[stage] = K7Meta{done ? -1 : item, c, nchunks, 0};
+                    mbar_arrive(full);
+                }
+                if (++stage == K7_DSTAGES) {
+                    stage = 0;
+                    dphase ^= 1;
+                }
                 if (done) {
-                    // sentinel stage: tells the converters to stop (all arrivals, no data)
-                    if (pt == 0) {
-                        meta[stage] = K7Meta{-1, 0, 0, 0};
-                        mbar_arrive(&data_full[stage]);
-                    }
-                    mbar_arrive(&data_full[stage]);
+                    mbar_arrive(full);
                     continue;
                 }
                 const int ebase = e0 + c * K7_KT;
-                if (pt == 0) {
-                    meta[stage] = K7Meta{item, c, nchunks, 0};
-                    mbar_arrive(&data_full[stage]);
-                }
                 const int px = px_next;
                 if (c + 1 < nchunks)
                     px_next = p.quad ? p.entry_px[((ebase + K7_KT) >> 2) + qsub * 8 + qd]
@@ -404,26 +423,28 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     // one 16-byte copy moves 4 consecutive pixels of a frame into one swizzled
                     // chunk: a quarter of the copy instructions and of the shared-memory write
                     // wavefronts of the 4-byte gather
+                    constexpr int RS = K7_PWARPS * 2;          // frame rows per copy step
                     const uint32_t d0 = sdst + (uint32_t)qsub * K7_SUB_BYTES + (uint32_t)rg * 128u +
-                                        ((uint32_t)(qd ^ rg) << 4);
+                                        ((uint32_t)(qd ^ (rg & 7)) << 4);
                     const int64_t fr0 = fb * K7_FB + rg;
                     if (!ragged) {
                         const float* src = p.tile + px + fr0 * p.ld_tile;
-                        const int64_t step = 8 * p.ld_tile;
+                        const int64_t step = RS * p.ld_tile;
 #pragma unroll 4
-                        for (int j = 0; j < K7_FB / 8; j++) {
+                        for (int j = 0; j < K7_FB / RS; j++) {
                             if constexpr (CA)
-                                k7_cp_async_16_ca(d0 + (uint32_t)j * 1024u, src);
+                                k7_cp_async_16_ca(d0 + (uint32_t)j * (RS * 128u), src);
                             else
-                                k7_cp_async_16(d0 + (uint32_t)j * 1024u, src);
+                                k7_cp_async_16(d0 + (uint32_t)j * (RS * 128u), src);
                             src += step;
                         }
                     } else {
 #pragma unroll 4
-                        for (int j = 0; j < K7_FB / 8; j++) {
-                            int64_t fr = fr0 + 8 * j;
+                        for (int j = 0; j < K7_FB / RS; j++) {
+                            int64_t fr = fr0 + RS * j;
                             if (fr >= p.n_frames) fr = p.n_frames - 1;
-                            k7_cp_async_16(d0 + (uint32_t)j * 1024u, p.tile + px + fr * p.ld_tile);
+                            k7_cp_async_16(d0 + (uint32_t)j * (RS * 128u),
+                                           p.tile + px + fr * p.ld_tile);
                         }
                     }
                 } else if (!ragged) {
@@ -450,7 +471,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                         }
                     }
                 }
-                k7_cp_async_mbar_arrive_noinc(&data_full[stage]);
+                k7_cp_async_mbar_arrive_noinc(full);
             }
             if (done) break;
         }
@@ -459,35 +480,36 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
         if (lane == 0) {
             prefetch_tmap(&tm_table);
             const uint64_t pol_keep = l2_policy_evict_last();
-            uint32_t tit = 0;
-            const uint32_t nt = (uint32_t)p.tstages;
+            int ts = 0;
+            uint32_t tphase = 0;
             for (uint32_t qn = 0;; qn++) {
                 const int q = qn % K7_QLEN;
                 mbar_wait(&q_full[q], (qn / K7_QLEN) & 1);
                 const K7QItem qi = queue[q];
                 mbar_arrive(&q_free[q]);
                 const int nch = qi.item < 0 ? 1 : qi.nchunks;
-                for (int c = 0; c < nch; c++, tit++) {
-                    const int ts = (int)(tit % nt);
-                    mbar_wait(&tab_free[ts], ((tit / nt) & 1) ^ 1);
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&tab_free[ts], tphase ^ 1);
                     uint8_t* dst = smem + SM::TABLE_OFF + (size_t)ts * SM::TABLE_BYTES;
+                    uint64_t* full = &tab_full[ts];
+                    tmeta[ts] = K7Meta{qi.item, c, qi.nchunks, 0};
+                    if (++ts == K7_TSTAGES) {
+                        ts = 0;
+                        tphase ^= 1;
+                    }
                     if (qi.item < 0) {
-                        tmeta[ts] = K7Meta{-1, 0, 0, 0};
-                        mbar_arrive(&tab_full[ts]);
+                        mbar_arrive(full);
                         continue;
                     }
                     const int ebase = qi.e0 + c * K7_KT;
-                    tmeta[ts] = K7Meta{qi.item, c, qi.nchunks, 0};
-                    mbar_arrive_expect_tx(&tab_full[ts], SM::TABLE_BYTES);
+                    mbar_arrive_expect_tx(full, SM::TABLE_BYTES);
                     if constexpr (SYM) {
                         // 32 orbits: rows [0, 64) = real parts (hi | lo), [64, 128) = imaginary
-                        tma_load_2d(dst, &tm_table, ebase >> 1, 0, &tab_full[ts], pol_keep);
-                        tma_load_2d(dst + NMMA * 128, &tm_table, ebase >> 1, 64, &tab_full[ts],
-                                    pol_keep);
+                        tma_load_2d(dst, &tm_table, ebase >> 1, 0, full, pol_keep);
+                        tma_load_2d(dst + NMMA * 128, &tm_table, ebase >> 1, 64, full, pol_keep);
                     } else {
-                        tma_load_2d(dst, &tm_table, ebase, 0, &tab_full[ts], pol_keep);
-                        tma_load_2d(dst + N * 128, &tm_table, ebase + 32, 0, &tab_full[ts],
-                                    pol_keep);
+                        tma_load_2d(dst, &tm_table, ebase, 0, full, pol_keep);
+                        tma_load_2d(dst + N * 128, &tm_table, ebase + 32, 0, full, pol_keep);
                     }
                 }
                 if (qi.item < 0) break;
@@ -495,24 +517,24 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
-        uint32_t tit = 0;      // table stages
-        uint32_t st = 0;       // sub-tiles (TMEM slots)
-        int in_chain = 0, cbuf = 0;
-        const uint32_t nt = (uint32_t)p.tstages;
-        for (;; tit++) {
-            const int ts = (int)(tit % nt);
-            mbar_wait(&tab_full[ts], (tit / nt) & 1);
+        // Accumulators: two buffers of N TMEM columns; a CHAIN of `chain` sub-tiles accumulates
+        // into one of them and is then handed to the drain warps (acc_full / acc_free), so the
+        // float32 accumulate in the tensor core -- which truncates -- never runs long.
+        int ts = 0, as = 0, cbuf = 0, in_chain = 0;
+        uint32_t tphase = 0, aphase = 0, cuse = 0;      // cuse bit b: parity of the uses of buffer b
+        for (;;) {
+            mbar_wait(&tab_full[ts], tphase);
             const K7Meta m = tmeta[ts];
             if (m.item < 0) break;
-            if (m.chunk == 0) {
-                in_chain = 0;
-                cbuf = 0;
-            }
+            const bool last_stage = m.chunk == m.nchunks - 1;
             const uint32_t tbl = smem_u32(smem + SM::TABLE_OFF + (size_t)ts * SM::TABLE_BYTES);
 #pragma unroll
-            for (int s = 0; s < 2; s++, st++) {
-                const int as = st % K7_AS;
-                mbar_wait(&a_full[as], (st / K7_AS) & 1);
+            for (int s = 0; s < 2; s++) {
+                if (in_chain == 0) {
+                    // the drain warps have read the previous chain out of this buffer
+                    mbar_wait(&acc_free[cbuf], ((cuse >> cbuf) & 1) ^ 1);
+                }
+                mbar_wait(&a_full[as], aphase);
                 k7_fence_after();
                 const uint64_t bdesc0 = k7_desc_k_sw128(tbl + (uint32_t)s * NMMA * 128u);
                 const uint32_t a0 = tmem_base + (uint32_t)(K7_A_BASE + as * 64);
@@ -520,6 +542,8 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 // a chain starts with the first STAGE (both sub-tiles zero-initialise)
                 const uint32_t d0 = tmem_base + (uint32_t)(cbuf * N + (SYM ? s * 64 : 0));
                 const int first = SYM ? (in_chain < 2 ? 0 : 1) : in_chain;
+                in_chain++;
+                const bool chain_done = in_chain == chain || (last_stage && s == 1);
                 if (k7_elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {
@@ -529,61 +553,123 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     }
                     k7_commit(&mma_done[as]);
                     if (s == 1) k7_commit(&tab_free[ts]);
+                    if (chain_done) k7_commit(&acc_full[cbuf]);
                 }
                 __syncwarp();
-                if (++in_chain == chain) {
-                    in_chain = 0;
+                if (chain_done) {
+                    cuse ^= 1u << cbuf;
                     cbuf ^= 1;
+                    in_chain = 0;
+                }
+                if (++as == K7_AS) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+            if (++ts == K7_TSTAGES) {
+                ts = 0;
+                tphase ^= 1;
+            }
+        }
+    } else if (warp >= DRAIN_WARP0) {
+        // ===== accumulator drain: chain totals -> float32 registers (round to nearest) -> out
+        // One warp per TMEM lane quarter; thread <-> frame row.  The item sequence comes from
+        // the same queue the table warp reads, the chain segmentation is the MMA warp's.
+        const int dw = warp - DRAIN_WARP0;
+        const int row = dw * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(dw * 32) << 16;
+        int cbuf = 0;
+        uint32_t duse = 0;
+        for (uint32_t qn = 0;; qn++) {
+            const int q = qn % K7_QLEN;
+            mbar_wait(&q_full[q], (qn / K7_QLEN) & 1);
+            const K7QItem qi = queue[q];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_free[q]);
+            if (qi.item < 0) break;
+            float acc[2][NQ];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int c = 0; c < NQ; c++) acc[h][c] = 0.f;
+            const int n_sub = 2 * qi.nchunks;
+            for (int done = 0; done < n_sub; done += chain) {
+                mbar_wait(&acc_full[cbuf], (duse >> cbuf) & 1);
+                k7_fence_after();
+                const uint32_t d = tmem_base + lane_sel + (uint32_t)(cbuf * N);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+#pragma unroll
+                    for (int jb0 = 0; jb0 < NQ / 4; jb0 += 4) {
+                        uint32_t vh[4][4], vl[4][4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (jb0 + u < NQ / 4) {
+                                k7_ld4(d + h * NHALF + (jb0 + u) * 4, vh[u]);
+                                k7_ld4(d + h * NHALF + NQ + (jb0 + u) * 4, vl[u]);
+                            }
+                        k7_wait_ld();
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (jb0 + u < NQ / 4) {
+                                k7_ld_fence4(vh[u]);
+                                k7_ld_fence4(vl[u]);
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    acc[h][(jb0 + u) * 4 + t] +=
+                                        __uint_as_float(vh[u][t]) + __uint_as_float(vl[u][t]);
+                            }
+                    }
+                }
+                k7_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_free[cbuf]);
+                duse ^= 1u << cbuf;
+                cbuf ^= 1;
+            }
+            int g;
+            int64_t fb;
+            k7_decode_item(p, qi.item, g, fb);
+            const int64_t f = fb * K7_FB + row;
+            if (f < p.n_frames) {
+                float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2;
+                if constexpr (SYM) {
+                    // half 0 holds the real parts, half 1 the imaginary parts
+#pragma unroll
+                    for (int c = 0; c < NQ; c++)
+                        if (c < p.n_pairs) {
+                            o[2 * c] = p.accumulate ? (o[2 * c] + acc[0][c]) : acc[0][c];
+                            o[2 * c + 1] = p.accumulate ? (o[2 * c + 1] + acc[1][c]) : acc[1][c];
+                        }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int c = 0; c < NQ; c++)
+                            if (h * NQ + c < 2 * p.n_pairs)
+                                o[h * NQ + c] =
+                                    p.accumulate ? (o[h * NQ + c] + acc[h][c]) : acc[h][c];
                 }
             }
         }
     } else {
-        // ===== converters / accumulator drain =====
+        // ===== converters: gathered float32 pixels -> split-TF32 A operand in TMEM =====
+        // thread <-> frame row (TMEM lane); warps 4..7 take entries 0..15 of a sub-tile, warps
+        // 8..11 entries 16..31.  Nothing else happens here: this loop is what bounds the kernel
+        // (profiles/r2_k7_*), so ring positions are wrapping counters and the accumulator
+        // drain lives in its own warps.
         const int cw = warp - K7_PWARPS;
         const int w = cw & 3;                       // TMEM lane quarter (== warp % 4)
-        const int hh = cw >> 2;                     // entries hh*16 .. +15 of a sub-tile; drains
-                                                    // accumulator columns [hh*N/2, (hh+1)*N/2)
+        const int hh = cw >> 2;
         const int row = w * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(w * 32) << 16;
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
-
-        float acc[NQ];
-        uint32_t it = 0, st = 0;
-        int i = 0, n_sub = 0, next_chain = 0;
-
-        auto chain_end = [&](int c) {
-            const int e = (c + 1) * chain;
-            return (e < n_sub ? e : n_sub) - 1;
-        };
-        auto drain_one = [&]() {
-            const uint32_t d = tmem_base + lane_sel + (uint32_t)((next_chain & 1) * N + hh * NHALF);
-            uint32_t v[NHALF / 8][8];
-#pragma unroll
-            for (int q = 0; q < NHALF / 8; q++) k7_ld8(d + q * 8, v[q]);
-            k7_wait_ld();
-#pragma unroll
-            for (int q = 0; q < NHALF / 8; q++) k7_ld_fence8(v[q]);
-#pragma unroll
-            for (int c = 0; c < NQ; c++)
-                acc[c] += __uint_as_float(v[c / 8][c % 8]) +
-                          __uint_as_float(v[(NQ + c) / 8][(NQ + c) % 8]);
-            next_chain++;
-        };
-
-        const uint32_t nd = (uint32_t)p.dstages;
-        for (;; it++) {
-            const int stage = (int)(it % nd);
-            mbar_wait(&data_full[stage], (it / nd) & 1);
-            const K7Meta m = meta[stage];
-            if (m.item < 0) break;
-            if (m.chunk == 0) {
-#pragma unroll
-                for (int c = 0; c < NQ; c++) acc[c] = 0.f;
-                i = 0;
-                n_sub = 2 * m.nchunks;
-                next_chain = 0;
-            }
+        int stage = 0, as = 0;
+        uint32_t dphase = 0, aphase = 0;
+        for (;;) {
+            mbar_wait(&data_full[stage], dphase);
+            if (meta[stage].item < 0) break;
             const uint8_t* dbase = smem + (size_t)stage * K7_DATA_BYTES + row_off;
             float4 x[2][4];
 #pragma unroll
@@ -600,6 +686,12 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 for (int j = 0; j < 4; j++)
                     asm volatile("" : "+f"(x[s][j].x), "+f"(x[s][j].y), "+f"(x[s][j].z),
                                       "+f"(x[s][j].w)::"memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&data_free[stage]);
+            if (++stage == K7_DSTAGES) {
+                stage = 0;
+                dphase ^= 1;
+            }
             if constexpr (SYM) {
                 // butterflies of the mirror pairs: sub-tile 0 <- I(p) + I(p'), 1 <- I(p) - I(p')
 #pragma unroll
@@ -609,25 +701,11 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     x[1][j] = make_float4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w);
                 }
             }
-            __syncwarp();
-            if (lane == 0 && !p.late_release) mbar_arrive(&data_free[stage]);
+            // both sub-tiles are written before ONE tcgen05.wait::st: the store latency is paid
+            // once per stage
+            int as_used[2];
 #pragma unroll
-            for (int s = 0; s < 2; s++, st++, i++) {
-                const int as = st % K7_AS;
-                // slot `as` is free once the MMAs of sub-tile st - AS have completed
-                mbar_wait(&mma_done[as], ((st / K7_AS) & 1) ^ 1);
-                int known = i - K7_AS;
-                if (i % chain == 0 && i >= 2 * chain) {
-                    // the chain that shares its accumulator with the one starting now
-                    const int must = i - chain - 1;
-                    if (must > known) {
-                        const uint32_t stm = st - (uint32_t)(i - must);
-                        mbar_wait(&mma_done[stm % K7_AS], (stm / K7_AS) & 1);
-                        known = must;
-                    }
-                }
-                k7_fence_after();
-                while (next_chain * chain < n_sub && chain_end(next_chain) <= known) drain_one();
+            for (int s = 0; s < 2; s++) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -639,44 +717,24 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                         lo[j * 4 + t] = __float_as_uint(e[t] - __uint_as_float(hb)) + 0x1000u;
                     }
                 }
+                // slot `as` is free once the MMAs of the sub-tile K7_AS back have completed
+                mbar_wait(&mma_done[as], aphase ^ 1);
+                k7_fence_after();
                 const uint32_t a = tmem_base + lane_sel + (uint32_t)(K7_A_BASE + as * 64 + hh * 16);
                 k7_st16(a, hi);
                 k7_st16(a + 32, lo);
-                k7_wait_st();
-                k7_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&a_full[as]);
-                    if (s == 1 && p.late_release) mbar_arrive(&data_free[stage]);
+                as_used[s] = as;
+                if (++as == K7_AS) {
+                    as = 0;
+                    aphase ^= 1;
                 }
             }
-            if (m.chunk == m.nchunks - 1) {
-                // item tail: the last commit covers every earlier MMA of the item
-                const uint32_t stl = st - 1;
-                mbar_wait(&mma_done[stl % K7_AS], (stl / K7_AS) & 1);
-                k7_fence_after();
-                while (next_chain * chain < n_sub) drain_one();
-                k7_fence_before();
-                int g;
-                int64_t fb;
-                k7_decode_item(p, m.item, g, fb);
-                const int64_t f = fb * K7_FB + row;
-                if (f < p.n_frames) {
-                    if constexpr (SYM) {
-                        // warp half hh = 0 holds the real parts, 1 the imaginary parts
-                        float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2 + hh;
-#pragma unroll
-                        for (int c = 0; c < NQ; c++)
-                            if (c < p.n_pairs)
-                                o[2 * c] = p.accumulate ? (o[2 * c] + acc[c]) : acc[c];
-                    } else {
-                        float* o = p.out + f * p.ld_out + (int64_t)g * p.n_pairs * 2 + hh * NQ;
-#pragma unroll
-                        for (int c = 0; c < NQ; c++)
-                            if (hh * NQ + c < 2 * p.n_pairs)
-                                o[c] = p.accumulate ? (o[c] + acc[c]) : acc[c];
-                    }
-                }
+            k7_wait_st();
+            k7_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_full[as_used[0]]);
+                mbar_arrive(&a_full[as_used[1]]);
             }
         }
     }
@@ -821,15 +879,6 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     if (p.rgroup > n_groups) p.rgroup = n_groups;
     p.fbgroup = 0;
     p.quad = quad ? 1 : 0;
-    // pipeline depths in use (rings: K7_DSTAGES data, K7_TSTAGES table stages)
-    p.dstages = K7_DSTAGES;
-    p.tstages = K7_TSTAGES;
-    if (const char* e = getenv("LTB200_K7_DS"))
-        if (atoi(e) >= 1 && atoi(e) <= K7_DSTAGES) p.dstages = atoi(e);
-    p.late_release = 0;
-    if (const char* e = getenv("LTB200_K7_LATE")) p.late_release = atoi(e);
-    if (const char* e = getenv("LTB200_K7_TS"))
-        if (atoi(e) >= 1 && atoi(e) <= K7_TSTAGES) p.tstages = atoi(e);
     if (quad)
         LTB_REQUIRE((uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0,
                     "group_masks_tc: the quad plan needs 16-byte aligned frame rows");

@@ -42,8 +42,8 @@ constexpr uint32_t K8_STAGE_BYTES = K8_FB * 128;          // 32 KiB
 constexpr int K8_TMEM_COLS = 512;
 constexpr int K8_ONES_COL = 128;       // TMEM columns [128, 136): all-ones A operand (32 int8 / row)
 constexpr int K8_SUM_COL = 256;        // TMEM columns [256, 512): 2 x 128 byte-sum accumulators
-constexpr int K8_MAX_COLUMNS = 32;     // rows 17..32 (N = 64 / uint8 N = 32): EXPERIMENTAL, not yet
-                                       // validated on hardware; the runner stays at <= 16 rows
+constexpr int K8_MAX_COLUMNS = 32;     // rows 17..32: N = 64 (uint16) / N = 32 (uint8) with one
+                                       // accumulator buffer per item (tests/test_k8_gpu.py)
 
 struct K8Params {
     int64_t n_frames;
@@ -555,7 +555,12 @@ static int k8_choose_ksplit(int64_t n_fb, int64_t sig_size, int sms, int px) {
         }
         if (eff >= 0.95) break;
     }
-    return best;
+    // every split must own at least one stage: with `per` stages per split only
+    // ceil(stages / per) splits are non-empty (an empty split would never commit its
+    // accumulator and the drain warps would wait for it forever)
+    const int64_t subs = (sig_size + px - 1) / px;
+    const int64_t per = (subs + best - 1) / best;
+    return (int)((subs + per - 1) / per);
 }
 
 static size_t k8_align256(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -65,7 +65,7 @@ class GroupPlan:
         #: dict(n_bands, entry_px, table_split, group_off_host, group_off_dev, n_groups)
         self.banded = banded
         self._band_ws = None
-        #: experimental mirror-symmetric plan (dict(main=..., rest=...)) or None
+        #: opt-in mirror-symmetric plan (dict(main=..., rest=...)) or None
         self.sym = None
 
     def band_workspace(self, n_frames, which=None):
@@ -106,9 +106,11 @@ def pack_rows(table):
 
 
 TC_KT = 64                        # entries per stage of the tensor-core kernel (K7_KT)
-#: EXPERIMENTAL mirror-symmetric plan (ltb200_group_masks_tc_sym): written without access to
-#: the hardware, validated only through its CPU emulation (tests/test_host_cpu.py); off by
-#: default until it has passed tests/test_k4_gpu.py::test_group_masks_sym on a B200
+#: mirror-symmetric plan (ltb200_group_masks_tc_sym) for stacks with m(sy - y, x) = conj m(y, x):
+#: validated on B200 (tests/test_k4_gpu.py::test_group_masks_sym) and timed in round 2 -- 2.94 ms
+#: vs 3.02 ms for the banded plan on the cfg4 geometry (8192 frames): the kernel is bound by the
+#: gather / L2->SM fabric, not by the tensor work or the table bytes the symmetry saves, so it
+#: stays opt-in (build_plan(sym=True) or LTB200_K7_SYM=1); the banded plan is the default.
 SYM_PATH = os.environ.get('LTB200_K7_SYM', '0') == '1'
 #: frame-stream bytes of one band of one 128-frame block aimed at by the band count (a handful
 #: of frame blocks x this must stay L2-resident together with the band's weight-table slices)
@@ -181,7 +183,7 @@ SYM_TOL = 2e-5
 
 
 def build_sym(stack3, group_size, n_bands):
-    """Mirror-symmetric plan of the tensor-core kernel (EXPERIMENTAL, ltb200_group_masks_tc_sym)
+    """Mirror-symmetric plan of the tensor-core kernel (opt-in, ltb200_group_masks_tc_sym)
     for a (M, sy, sx) complex stack with m(sy - y, x) = conj(m(y, x)), or None.
 
     Orbits are pixel pairs {(y, x), (sy - y, x)}, 1 <= y < sy/2.  Groups are (row band of the
@@ -243,7 +245,7 @@ def build_sym(stack3, group_size, n_bands):
                 group_off=np.array(offs, dtype=np.int32), residual=residual)
 
 
-def build_plan(stack, group_size, device, n_bands=None, sig_shape=None):
+def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None):
     """stack: complex (M, *sig) dense array with M = n_groups * group_size (``sig_shape`` gives
     the 2D signal shape when the stack comes flattened)"""
     M = stack.shape[0]
@@ -294,7 +296,7 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None):
                           group_off_dev=torch.from_numpy(b['group_off']).to(device))
     plan = GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
                      group_size, M, device, table_split=split, n_cols=n_cols, banded=banded)
-    if SYM_PATH and banded is not None and len(sig_shape) == 2:
+    if (SYM_PATH if sym is None else sym) and banded is not None and len(sig_shape) == 2:
         plan.sym = _sym_to_device(flat, sig_shape, group_size, max(1, n_bands // 2), n_cols,
                                   device)
     return plan
@@ -353,7 +355,7 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     if kernel == 'banded' and not aligned:
         raise _lib.LTB200Error('the banded plan needs 16-byte aligned frame rows')
     if kernel == 'sym' and plan.sym is None:
-        raise _lib.LTB200Error('no mirror-symmetric plan (LTB200_K7_SYM=1 and a symmetric stack)')
+        raise _lib.LTB200Error('no mirror-symmetric plan (build_plan(sym=True) and a symmetric stack)')
     if use_tc and plan.sym is not None and aligned and kernel in ('sym', 'auto'):
         stream = torch.cuda.current_stream(tile.device).cuda_stream
         with torch.cuda.device(tile.device):

@@ -30,6 +30,7 @@ from . import engine
 
 MAX_FUSED_COLUMNS = 24
 MAX_FUSED_COLUMNS_F32 = 32
+K8_MAX_ROWS = 32             # int8 rows per pass of the integer tensor-core kernel (K8)
 # uint16 tiles x integer-valued masks -> exact int8 tensor-core kernel (LTB200_INT8=0: off)
 INT8_PATH = os.environ.get('LTB200_INT8', '1') != '0'
 
@@ -524,15 +525,17 @@ class UDFRunner:
         if flat.dtype not in (torch.uint16, torch.uint8):
             return None
         align = 16 // flat.element_size()            # pixels per 16 bytes
-        if (not INT8_PATH or not 1 <= M <= 16 or F < 256 or K % align
-                or not 64 * align // 2 <= K <= 65536 or flat.stride(1) != 1
+        # 1..32 int8 rows per pass (digit rows included); signals beyond 65536 pixels are K-split
+        # inside the library so that every int32 accumulator stays exact (<= 4 Mi pixels)
+        if (not INT8_PATH or not 1 <= M <= K8_MAX_ROWS or F < 256 or K % align
+                or not 64 * align // 2 <= K <= (4 << 20) or flat.stride(1) != 1
                 or (F > 1 and flat.stride(0) % align) or flat.data_ptr() % 16
                 or rows.dtype != torch.float32):
             return None
         key = (rows.data_ptr(), tuple(rows.shape))
         hit = self._int8_cache.get(key)
         if hit is None:
-            hit = (int8_digit_plan(rows), rows)      # keep the source alive (cache key)
+            hit = (int8_digit_plan(rows, max_rows=K8_MAX_ROWS), rows)   # source kept alive (key)
             self._int8_cache[key] = hit
         return hit[0]
 

@@ -458,7 +458,7 @@ def _emulate_quad_plan(b, data, n_rings, size, n_cols):
 
 
 def test_mirror_symmetric_plan_emulation():
-    """host plan of the experimental mirror-symmetric kernel (group_masks.build_sym), emulated
+    """host plan of the opt-in mirror-symmetric kernel (group_masks.build_sym), emulated
     stage by stage exactly as the kernel walks it: 8 upper quads + their 8 mirror images per
     stage, float32 butterflies, real weights on the sums and imaginary weights on the
     differences, one table column per orbit; plus the rows without a partner through the

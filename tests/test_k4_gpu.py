@@ -105,8 +105,6 @@ def test_group_masks_banded(F, K, n_groups, size, n_bands):
     assert np.array_equal(out4, out)              # schedule does not change the arithmetic
 
 
-@pytest.mark.skipif(__import__('os').environ.get('LTB200_K7_SYM') != '1',
-                    reason='experimental mirror-symmetric plan: run with LTB200_K7_SYM=1')
 @pytest.mark.parametrize('S,n_bins,max_order,F', [(64, 4, 6, 300), (128, 8, 24, 1000)])
 def test_group_masks_sym(S, n_bins, max_order, F):
     """mirror-symmetric plan of K7 on the reference's radial masks: same result as the banded
@@ -116,7 +114,7 @@ def test_group_masks_sym(S, n_bins, max_order, F):
     ro = M.bounding_radius(S / 2, S / 2, S, S)
     stack = np.asarray(radial_mask_factory(S, S, S / 2, S / 2, 0, ro, n_bins, max_order,
                                            use_sparse=False)()).astype(np.complex64)
-    plan = gm.build_plan(stack, max_order + 1, torch.device('cuda'), n_bands=2)
+    plan = gm.build_plan(stack, max_order + 1, torch.device('cuda'), n_bands=2, sym=True)
     assert plan.sym is not None
     data = synth.uniform_f32(0, F * S * S, 12).reshape(F, S * S)
     t = torch.from_numpy(data).cuda()

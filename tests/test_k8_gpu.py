@@ -145,12 +145,6 @@ def test_i8_unsupported(eng):
         eng.masks_dense_i8(big, torch.ones((1, K), dtype=torch.int8, device='cuda'))
 
 
-EXPERIMENTAL = pytest.mark.skipif(
-    __import__('os').environ.get('LTB200_TEST_EXPERIMENTAL') != '1',
-    reason='written after the round-1 GPU budget ran out; run with LTB200_TEST_EXPERIMENTAL=1')
-
-
-@EXPERIMENTAL
 @pytest.mark.parametrize('n_masks', [17, 24, 32])
 @pytest.mark.parametrize('dt', ['u16', 'u8'])
 def test_i8_wide_stacks(eng, n_masks, dt):
@@ -169,7 +163,6 @@ def test_i8_wide_stacks(eng, n_masks, dt):
         check_exact_u8(eng, data[:300], masks, with_sum=False)
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize('K', [65536 + 64, 512 * 512, 3 * 65536 + 8 * 5])
 def test_i8_large_signals(eng, K):
     """signals beyond 65536 pixels are K-split so that every int32 accumulator stays exact; the

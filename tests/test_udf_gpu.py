@@ -730,3 +730,58 @@ def test_radial_fourier_symmetries_known_answer(lt, kernel, monkeypatch):
     np.testing.assert_allclose(np.angle(c(1, 3)[0, 1]), np.pi / 2, atol=1e-4)
     np.testing.assert_allclose(np.angle(c(1, 4)), 0, atol=1e-4)
     np.testing.assert_allclose(np.angle(c(1, 8)), 0, atol=1e-4)
+
+
+def test_udf_level_k6_tensor_path(lt):
+    """the runner -> result slab -> K6 (tcgen05 dense kernel) combination that produces the
+    headline number: one partition of 2048 frames, 8 masks + CoM + SumSig fused in one pass,
+    against the oracle (the bench path was only covered piecewise)"""
+    from libertem_b200 import engine
+    shape = (32, 64, 64, 64)
+    data = synth.dataset(shape, np.float32, 33)
+    masks = mixed_masks(64, 64, 8, 4)
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=1, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.ApplyMasksUDF(mask_factories=lambda: masks), lt.udf.CoMUDF(),
+                           lt.udf.SumSigUDF()])
+    res = runner.run_for_dataset(ds).buffers
+    assert engine.last_kernel() == 6, engine.last_kernel()
+    assert runner.stats['unfused_calls'] == 0 and runner.stats['fused_launch_groups'] == 1
+    close_cols(res[0]['intensity'].raw_data, O.apply_masks(data, masks, num_partitions=1))
+    com = O.com_udf(data, num_partitions=1)
+    close_cols(res[1]['raw_com'].raw_data, com['raw_com'])
+    np.testing.assert_allclose(res[1]['field'].raw_data, com['field'], rtol=RTOL, atol=2e-4)
+    np.testing.assert_allclose(res[2]['intensity'].raw_data, O.sumsig_udf(data), rtol=RTOL)
+    # and the same through 4 partitions of 512 frames (FFMA2 kernel): same results within tol
+    ds4 = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=4, sig_dims=2)
+    res4 = lt.run_udf(ds4, [lt.udf.ApplyMasksUDF(mask_factories=lambda: masks)])
+    close_cols(res4[0]['intensity'].raw_data, res[0]['intensity'].raw_data)
+
+
+def test_udf_level_k8_large_signal_and_wide_stack(lt):
+    """uint16 frames x integer masks beyond the round-1 routing limits go to the int8
+    tensor-core kernel: a 288x256 detector (73728 px > 65536: K-split with int64
+    recombination) with CoM (coordinate masks up to 287 -> base-128 digit rows) + SumUDF +
+    SumSigUDF + 20 binary masks (> 16 int8 rows per pass) -- bit-exact"""
+    from libertem_b200 import engine
+    sy, sx = 288, 256
+    shape = (16, 20, sy, sx)
+    data = synth.dataset(shape, np.uint16, 44)
+    yy, xx = np.mgrid[:sy, :sx]
+    masks = np.stack([((yy // 12 + xx // 16 + i) % 3 == 0) for i in range(20)]).astype(np.float32)
+    ds = lt.MemoryDataSet(
+        data=torch.from_numpy(data.view(np.int16)).view(torch.uint16).cuda(),
+        num_partitions=1, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.SumUDF(), lt.udf.SumSigUDF(), lt.udf.CoMUDF(),
+                           lt.udf.ApplyMasksUDF(mask_factories=lambda: masks)])
+    res = runner.run_for_dataset(ds).buffers
+    assert engine.last_kernel() == 8 and runner.stats.get('int8_passes', 0) >= 1
+    assert runner.stats['unfused_calls'] == 0
+    f32 = data.astype(np.float32)
+    flat64 = data.reshape(-1, sy * sx).astype(np.float64)
+    assert np.array_equal(res[0]['intensity'].raw_data.reshape(-1),
+                          flat64.sum(axis=0).astype(np.float32))
+    assert np.array_equal(res[1]['intensity'].raw_data, flat64.sum(axis=1).astype(np.float32))
+    exact = (flat64 @ masks.reshape(20, -1).T.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(res[3]['intensity'].raw_data, exact)
+    com = O.com_udf(f32, num_partitions=1)
+    close_cols(res[2]['raw_com'].raw_data, com['raw_com'])
