@@ -334,6 +334,13 @@ class Ctx:
         if self.world > 1:
             self.cpu_affinity = _bind_near_gpu(torch, self.local_rank)
             dist.init_process_group('nccl', device_id=self.device)
+            if self.rank == 0:
+                try:       # for the record (stderr): which GPUs share a PCIe switch / NUMA node
+                    topo = subprocess.run(['nvidia-smi', 'topo', '-m'], capture_output=True,
+                                          text=True, timeout=20).stdout
+                    print(topo, file=sys.stderr, flush=True)
+                except Exception:
+                    pass
 
     def barrier(self):
         if self.world > 1:
@@ -741,23 +748,48 @@ def _host_copy(ctx, ds, part):
 
 
 def h2d_peak(ctx, host, chunk_frames=1024, reps=2):
-    """bare H2D: cudaMemcpyAsync of the whole pinned shard in chunks into one device buffer, all
-    ranks at the same time; GB/s per GPU (min over ranks = what every rank is guaranteed)"""
+    """bare H2D: cudaMemcpyAsync of the whole pinned shard in chunks into one device buffer.
+    Returns (GB/s per GPU with all ranks copying at the same time, as a list over ranks;
+    GB/s of every rank copying ALONE, list over ranks): placement problems (a rank whose pinned
+    memory sits on the far socket) show up in the second list, shared-resource limits (host
+    memory bandwidth, PCIe switch uplinks) as the difference between the two."""
     torch = ctx.torch
     flat = host.reshape(host.shape[0], -1)
     dst = torch.empty((chunk_frames, flat.shape[1]), dtype=flat.dtype, device=ctx.device)
-    best = None
-    for _ in range(reps):
-        ctx.barrier()
+    nbytes = flat.numel() * flat.element_size()
+
+    def once():
         t0 = time.perf_counter()
         for f0 in range(0, flat.shape[0], chunk_frames):
             n = min(chunk_frames, flat.shape[0] - f0)
             dst[:n].copy_(flat[f0:f0 + n], non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    def gather(x):
+        if ctx.world == 1:
+            return [float(x)]
+        t = torch.zeros(ctx.world, device=ctx.device, dtype=torch.float64)
+        t[ctx.rank] = x
+        ctx.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    best = None
+    for _ in range(reps):
+        ctx.barrier()
+        dt = once()
         best = dt if best is None else min(best, dt)
-    gbs = flat.numel() * flat.element_size() / best / 1e9
-    return -ctx.max_over_ranks(-gbs)
+    together = gather(nbytes / best / 1e9)
+    alone = together
+    if ctx.world > 1:
+        mine = 0.0
+        for r in range(ctx.world):
+            ctx.barrier()
+            if r == ctx.rank:
+                mine = nbytes / once() / 1e9
+        ctx.barrier()
+        alone = gather(mine)
+    return together, alone
 
 
 def e2e_leg(ctx, ds, part, stack, total_frames):
@@ -770,7 +802,8 @@ def e2e_leg(ctx, ds, part, stack, total_frames):
     from libertem_b200.udf import ApplyMasksUDF, CoMUDF
     world = ctx.world
     host = _host_copy(ctx, ds, part)
-    peak = h2d_peak(ctx, host)
+    together, alone = h2d_peak(ctx, host)
+    peak = min(together)
     if world == 1:
         hds = MemoryDataSet(data=host.reshape(NAV + SIG), num_partitions=1, sig_dims=2, pin=False)
     else:
@@ -801,6 +834,8 @@ def e2e_leg(ctx, ds, part, stack, total_frames):
             'd2h_bytes_per_step': int(total_frames * (N_MASKS + 3) * 4) * world, 'steps': steps,
             'ms_per_step': dt * 1e3, 'h2d_gbs_per_gpu': gbs, 'h2d_peak_gbs': peak,
             'h2d_frac_of_peak': gbs / peak,
+            'h2d_peak_gbs_per_rank_concurrent': [round(v, 2) for v in together],
+            'h2d_peak_gbs_per_rank_alone': [round(v, 2) for v in alone],
             'note': 'run_for_dataset on pinned host data: double-buffered H2D tiles overlapped '
                     'with the kernel' + (', NCCL all-gather of the result slab' if world > 1
                                          else '') + ', D2H of all result buffers and CoM '

@@ -162,7 +162,8 @@ LTB_API int ltb200_set_k1_variant(int variant);
  * 2 = generic kernel, 6 = tcgen05 tensor-core kernel; and for the other entry points:
  * 8 = int8 tensor-core kernel (K8), 20 = sparse CSC kernel (K2), 4 = group-sparse FFMA2
  * kernel (K4), 5 = shifted-mask kernel (K5), 7 / 70 / 71 = group-sparse tensor-core kernel (K7)
- * with the ring-major / quad-banded / mirror-symmetric plan (diagnostics / tests) */
+ * with the ring-major / quad-banded / mirror-symmetric plan, 9 = nav-space CoM kernels (K9)
+ * (diagnostics / tests) */
 LTB_API int ltb200_last_kernel(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 LTB_API int64_t ltb200_launch_count(int reset);
@@ -268,6 +269,47 @@ LTB_API int ltb200_group_masks_tc_sym(const float* tile, int64_t n_frames, int64
  * ------------------------------------------------------------------------------------- */
 LTB_API int ltb200_synth_fill(void* dst, int dtype, int64_t start, int64_t count, uint32_t seed,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Nav-space post-processing of the centre-of-mass moments (K9) -- CoMUDF.get_results
+ * (udf/com.py:650-717) on the device.  raw: (rows, ld_raw >= 3) float32 [m00, m10, m01] per
+ * scan position; row_of_nav (nullable, ny*nx int32): row of raw for every scan position, -1
+ * outside the roi (outputs NaN there); valid (nullable, ny*nx uint8): positions that enter the
+ * regression (default: row >= 0).  center_shifts (com.py:100-107) in float32, then the 2x2
+ * float64 `transform` (apply_correction, com.py:110-127), the regression (mode -1 none, 0
+ * subtract the mean, 1 subtract the least-squares plane c0 + c1 y + c2 x -- both over the valid
+ * positions --, 2 subtract the given plane; `regression` is the (3, 2) float64 device array,
+ * read in mode 2 and written otherwise; com.py:600-648), magnitude / divergence / curl with
+ * np.gradient stencils (com.py:130-142) in float64, rounded to float32 on store.  Outputs cover
+ * the full scan grid: raw_shifts / raw_com / field (ny*nx, 2) as (y, x), the others (ny*nx).
+ * ny, nx >= 2 (np.gradient).  Sums are reduced in a fixed order (deterministic).
+ * ------------------------------------------------------------------------------------- */
+LTB_API size_t ltb200_com_workspace(int ny, int nx);
+LTB_API int ltb200_com_postprocess(const float* raw, int64_t ld_raw, const int32_t* row_of_nav,
+                                   const uint8_t* valid, int ny, int nx, double cy, double cx,
+                                   const double* transform /* host, 4 */, int regression_mode,
+                                   double* regression /* device, 6 */, float* raw_shifts,
+                                   float* raw_com, float* field, float* field_y, float* field_x,
+                                   float* magnitude, float* divergence, float* curl,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+/* guess_corrections (udf/com.py:145-295) without 720 passes: the curl of a linearly transformed
+ * field is linear in the gradient fields g = (dy/d0, dy/d1, dx/d0, dx/d1) of the (ny, nx) float32
+ * maps y_centers / x_centers, so its RMS for any 2x2 matrix is a quadratic form in their Gram
+ * matrix.  sums17 (device, float64): the 10 upper-triangular Gram entries (row-major), the 4
+ * sums of g, sum(y), sum(x) and the count, over the window rows [r0, r1) x columns [c0, c1)
+ * (gradients are taken on the full grid, like np.gradient before slicing).
+ * workspace: >= 296 * 17 * 8 bytes. */
+LTB_API int ltb200_com_gradient_gram(const float* y_centers, const float* x_centers, int ny,
+                                     int nx, int r0, int r1, int c0, int c1, double* sums17,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+/* divergence of transform . (y, x) over the same window: pass 0 -> per-block (min, max) pairs in
+ * minmax_blocks (device, 2 * 296 float64; *n_blocks pairs are valid), pass 1 -> counts of the 5
+ * equal bins over [-range, range] (np.histogram(bins=5, range=...)) added to hist5 (device). */
+LTB_API int ltb200_com_divergence_stats(const float* y_centers, const float* x_centers, int ny,
+                                        int nx, int r0, int r1, int c0, int c1,
+                                        const double* transform /* host, 4 */, int pass,
+                                        double range, double* minmax_blocks, int* n_blocks,
+                                        unsigned long long* hist5, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Read-only HBM streaming probe (measurement only, not on the product path): reads `bytes`

@@ -202,6 +202,29 @@ class MaskContainer:
             self._device_cache[key] = hit
         return hit
 
+    def get_device_dense_for_complex(self, slice_, device, compute=np.float32):
+        """mask rows for COMPLEX frames read as their interleaved (re, im) float view (F, 2K):
+        for mask m = c + i d the rows ``[c_k at 2k, -d_k at 2k+1]`` (real part of the product
+        sum) and ``[d_k at 2k, c_k at 2k+1]`` (imaginary part), so that the (F, 2M) float result
+        of the dense kernel *is* the complex (F, M) result in memory."""
+        import torch
+        fl = np.dtype(compute)
+        key = ('dense_cplx', fl.str, slice_, str(device))
+        hit = self._device_cache.get(key)
+        if hit is None:
+            m = np.asarray(self._dense_stack_for(slice_))
+            c = np.ascontiguousarray(m.real, dtype=fl)
+            d = np.ascontiguousarray(m.imag, dtype=fl) if m.dtype.kind == 'c' else np.zeros_like(c)
+            M, K = c.shape
+            rows = np.empty((M, 2, K, 2), dtype=fl)
+            rows[:, 0, :, 0] = c
+            rows[:, 0, :, 1] = -d
+            rows[:, 1, :, 0] = d
+            rows[:, 1, :, 1] = c
+            hit = torch.from_numpy(rows.reshape(2 * M, 2 * K)).to(device)
+            self._device_cache[key] = hit
+        return hit
+
     def get_group_plan(self, slice_, device):
         """group-sparse plan for the K4 kernel (libertem_b200/group_masks.py) or None when
         the stack has no uniform group structure / is not sparse enough to pay off"""

@@ -4,8 +4,11 @@ Mirrors the reference ``libertem.udf.com`` (src/libertem/udf/com.py): same param
 (``CoMParams`` / ``CoMUDF.with_params``), same result buffers, same post-processing semantics.
 The per-frame moments (m00, m10, m01) are three mask rows [D, y*D, x*D] of the dense kernel
 (com.py:47-97,534-582), normally riding in the same pass as ApplyMasksUDF's masks (fused
-runner); the nav-sized post-processing (com.py:650-717) is a few floats per frame and stays on
-the host in numpy with the reference's exact operation order and dtypes.
+runner).  The nav-sized post-processing (com.py:650-717) runs in the nav-space kernels (K9,
+``libertem_b200/nav.py``) when the moments are in HBM -- float32 shifts, float64 from the
+rotation matrix on, rounded once, like the reference's dtypes; the module-level helpers below
+(``center_shifts``, ``apply_correction``, ``guess_corrections`` ...) keep the reference's numpy
+call signatures for host arrays, ``libertem_b200.nav.guess_corrections`` is the device form.
 """
 from enum import IntEnum
 from typing import NamedTuple, Union
@@ -285,7 +288,56 @@ class CoMUDF(UDF):
     def apply_lin_regression(self, regression, inp, field_inout, valid_mask):
         field_inout[valid_mask] -= inp[valid_mask] @ regression
 
+    def _get_results_device(self, raw):
+        """the same pipeline in the nav-space kernels (libertem_b200/nav.py, csrc/k9_nav.cu)
+        when the moments live in HBM: one upload of the roi / valid maps, four small launches,
+        one D2H of the finished float32 buffers"""
+        from .. import nav
+        p = self.get_params()
+        nav_shape = tuple(self.meta.dataset_shape.nav)
+        n = int(np.prod(nav_shape))
+        roi = self.meta.roi
+        row_of_nav = None
+        if roi is not None:
+            flat = np.asarray(roi).reshape(-1).astype(bool)
+            row_of_nav = np.where(flat, np.cumsum(flat) - 1, -1).astype(np.int32)
+        valid = self.meta.get_valid_nav_mask(full_nav=True).reshape(-1)
+        reg = p.regression
+        coeffs = None
+        if isinstance(reg, (int, np.integer)):
+            if reg not in (-1, 0, 1):
+                raise ValueError(f'Unrecognized regression option {reg}')
+            mode = int(reg)
+        else:
+            coeffs = np.array(reg, dtype=np.float64)
+            if coeffs.shape != (3, 2):
+                raise ValueError(
+                    f"Regression parameter {reg} doesn't have required shape (3, 2).")
+            mode = 2
+        transform = rotate_deg(p.scan_rotation) @ (flip_y_matrix() if p.flip_y else identity())
+        out = nav.com_postprocess(raw, nav_shape, p.cy, p.cx, transform, mode, coeffs,
+                                  row_of_nav=row_of_nav, valid=valid)
+        results = {}
+        sel = None if roi is None else torch.from_numpy(
+            np.nonzero(np.asarray(roi).reshape(-1))[0]).to(raw.device)
+        for key, t in out.items():
+            if key == 'regression':
+                results[key] = t.cpu().numpy()
+                continue
+            if sel is not None:
+                t = t.index_select(0, sel)
+            arr = t.cpu().numpy()
+            results[key] = arr if (sel is not None or arr.ndim == 2) else arr.reshape(n, 1)
+        return results
+
     def get_results(self):
+        raw_buf = self.results.get_buffer('raw_mask_result').tensor
+        nav_shape = tuple(self.meta.dataset_shape.nav)
+        if (isinstance(raw_buf, torch.Tensor) and raw_buf.is_cuda
+                and raw_buf.dtype == torch.float32 and len(nav_shape) == 2
+                and min(nav_shape) >= 2):
+            return self._get_results_device(raw_buf)
+        # host tensors (and complex moments): numpy, operation for operation as the reference
         p = self.get_params()
         rmr = self.results.get_buffer('raw_mask_result').data     # (*nav, 3), NaN off-roi
         raw_shifts = center_shifts(img_sum=rmr[..., 0], img_y=rmr[..., 1], img_x=rmr[..., 2],

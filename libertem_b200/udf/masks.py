@@ -36,8 +36,11 @@ class ApplyMasksEngine:
         self.masks = masks
         self.meta = meta
         self.result_dtype = np.result_type(meta.input_dtype, masks.dtype)
-        if np.dtype(meta.input_dtype).kind == 'c':
-            raise UDFException('complex input data is not supported by the B200 engine yet')
+        # complex frames (reference udf/masks.py:360-368: result_type(input, mask) is complex;
+        # tests/analysis/test_analysis_masks.py:151-212): the tile is read ONCE as its
+        # interleaved (re, im) float view (F, 2K) against mask rows expanded over that view --
+        # the same dense kernels, no separate real / imaginary planes
+        self.complex_input = np.dtype(meta.input_dtype).kind == 'c'
         self.sparse = bool(masks.use_sparse) and self.result_dtype == np.float32
         # dtype the kernels accumulate in
         if self.result_dtype in (np.float32, np.complex64):
@@ -49,7 +52,7 @@ class ApplyMasksEngine:
         """K4 plan when the masks are complex64, numerous and group-sparse (all members of a
         run of consecutive masks share one support -- radial Fourier rings), else None.
         Built once per MaskContainer (shared by the partition copies of the UDF)."""
-        if self.result_dtype != np.complex64 or len(self.masks) <= 12:
+        if self.result_dtype != np.complex64 or len(self.masks) <= 12 or self.complex_input:
             return None
         sl = self.meta.sig_slice if sig_slice is None else sig_slice
         return self.masks.get_group_plan(sl, self.device)
@@ -68,9 +71,21 @@ class ApplyMasksEngine:
         return 2 * n if self.result_dtype.kind == 'c' else n
 
     def dense_rows(self, sig_slice=None):
-        """device mask rows ``(R, K_tile)`` in the compute dtype (complex -> re/im rows)"""
+        """device mask rows ``(R, K_tile)`` in the compute dtype (complex -> re/im rows); for
+        complex frames ``(2M, 2 K_tile)`` rows over the interleaved (re, im) view of the tile"""
         sl = self.meta.sig_slice if sig_slice is None else sig_slice
+        if self.complex_input:
+            return self.masks.get_device_dense_for_complex(sl, self.device, self.compute)
         return self.masks.get_device_dense(sl, self.device, self._mask_dtype_for_device())
+
+    @staticmethod
+    def _float_view(flat_tile):
+        """(F, K) complex tile -> (F, 2K) float view [re0, im0, re1, im1, ...] (no copy)"""
+        if flat_tile.is_complex():
+            if flat_tile.shape[1] > 0 and flat_tile.stride(1) != 1:
+                flat_tile = flat_tile.contiguous()
+            return torch.view_as_real(flat_tile).reshape(flat_tile.shape[0], -1)
+        return flat_tile
 
     def process_flat(self, flat_tile, out=None, accumulate=False, sig_slice=None):
         """the seam of masks.py:31-83: ``flat_tile (F, K) -> (F, R)`` real columns"""
@@ -90,6 +105,11 @@ class ApplyMasksEngine:
             return engine.masks_csc(flat_tile, indptr, indices, values, len(self.masks),
                                     out=out, accumulate=accumulate)
         rows = self.dense_rows(sig_slice)
+        if self.complex_input:
+            if not flat_tile.is_complex():
+                flat_tile = flat_tile.to(torch.complex64 if self.compute == np.float32
+                                         else torch.complex128)
+            flat_tile = self._float_view(flat_tile)
         if self.compute == np.float64 and flat_tile.dtype in (torch.uint16, torch.uint8):
             flat_tile = flat_tile.to(torch.int32)
         return engine.masks_dense(flat_tile, rows, out=out, accumulate=accumulate)
@@ -120,8 +140,17 @@ class ApplyMasksEngine:
         frame = as_device_tile(frame, self.device).reshape(sig_shape)
         data = left.get(frame).reshape(1, -1)
         rows = self.dense_rows()
-        rows = rows.reshape((rows.shape[0],) + tuple(sig.shape))
-        sub = right.get(rows, sig_only=True).reshape(rows.shape[0], -1).contiguous()
+        if self.complex_input:
+            # rows run over the interleaved (re, im) view: (R, sy, sx, 2)
+            rows = rows.reshape((rows.shape[0],) + tuple(sig.shape) + (2,))
+            sub = right.get(rows[..., 0], sig_only=True)
+            sub = torch.stack([sub, right.get(rows[..., 1], sig_only=True)], dim=-1)
+            sub = sub.reshape(rows.shape[0], -1).contiguous()
+            data = self._float_view(data.contiguous().to(
+                torch.complex64 if self.compute == np.float32 else torch.complex128))
+        else:
+            rows = rows.reshape((rows.shape[0],) + tuple(sig.shape))
+            sub = right.get(rows, sig_only=True).reshape(rows.shape[0], -1).contiguous()
         res = engine.masks_dense(data.contiguous(), sub)
         return self.as_result(res).reshape((n,))
 

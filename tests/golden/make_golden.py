@@ -219,6 +219,36 @@ def g_radial_symmetries():
          frame_sums=frames.sum(axis=(1, 2), dtype=np.float64))
 
 
+def g_complex_input():
+    # complex64 frames (reference udf/masks.py:360-368; tests/analysis/test_analysis_masks.py:
+    # 151-212, tests/analysis/test_analysis_com.py:132-231): real masks, complex masks, and the
+    # COMAnalysis formulation (3 CoM masks + center_shifts / apply_correction of udf/com.py)
+    from libertem.udf.com import center_shifts, apply_correction
+    shape = (6, 7, 24, 32)
+    data = (synth.dataset(shape, np.float32, seed=301)
+            + 1j * (synth.dataset(shape, np.float32, seed=302) - 0.5)).astype(np.complex64)
+    real_masks = mixed_masks(24, 32, 3, 31)
+    cmasks = (mixed_masks(24, 32, 2, 41) + 1j * mixed_masks(24, 32, 2, 51)).astype(np.complex64)
+    out = {}
+    for name, kw in (('p2', dict(num_partitions=2)),
+                     ('tiled', dict(num_partitions=3, tileshape=(5, 8, 32)))):
+        dskw = dict(data=data, sig_dims=2, **kw)
+        _, b = run(dskw, [ApplyMasksUDF(mask_factories=lambda: real_masks, mask_count=3,
+                                        mask_dtype=np.float32, use_sparse=False)])
+        out['real_masks_' + name] = b[0]['intensity'].raw_data
+        _, b = run(dskw, [ApplyMasksUDF(mask_factories=lambda: cmasks, mask_count=2,
+                                        mask_dtype=np.complex64, use_sparse=False)])
+        out['complex_masks_' + name] = b[0]['intensity'].raw_data
+    raw = com_raw(dict(data=data, num_partitions=2, sig_dims=2), cy=0, cx=0)
+    out['com_raw'] = raw
+    img = raw.reshape(6, 7, 3)
+    y, x = center_shifts(img[..., 0], img[..., 1], img[..., 2], 0, 0)
+    y, x = apply_correction(y, x, scan_rotation=0., flip_y=False)
+    out['com_x'] = np.asarray(x)
+    out['com_y'] = np.asarray(y)
+    save('complex_input', dict(shape=shape, seeds=[301, 302], mask_seeds=[31, 41, 51]), **out)
+
+
 def g_com_params():
     # CoM with disk/ring, rotation, flip, regression on a non-square nav/sig
     shape = (12, 10, 32, 40)

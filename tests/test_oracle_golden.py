@@ -264,3 +264,36 @@ def test_int_detector(name):
               'divergence', 'curl', 'regression'):
         assert com[k].dtype == g['com_' + k].dtype and com[k].shape == g['com_' + k].shape, k
         np.testing.assert_allclose(com[k], g['com_' + k], rtol=1e-6, atol=1e-6, err_msg=k)
+
+
+def _complex_inputs(meta):
+    shape = tuple(meta['shape'])
+    s0, s1 = meta['seeds']
+    data = (synth.dataset(shape, np.float32, s0)
+            + 1j * (synth.dataset(shape, np.float32, s1) - 0.5)).astype(np.complex64)
+    m0, m1, m2 = meta['mask_seeds']
+    real_masks = mixed_masks(shape[2], shape[3], 3, m0)
+    cmasks = (mixed_masks(shape[2], shape[3], 2, m1)
+              + 1j * mixed_masks(shape[2], shape[3], 2, m2)).astype(np.complex64)
+    return data, real_masks, cmasks
+
+
+def test_complex_input():
+    """complex64 frames: result_type(input, mask) is complex64, numpy `@` path
+    (udf/masks.py:76-77,360-368)"""
+    meta, g = load_golden('complex_input')
+    data, real_masks, cmasks = _complex_inputs(meta)
+    for name, kw in (('p2', dict(num_partitions=2)),
+                     ('tiled', dict(num_partitions=3, tileshape=(5, 8, 32)))):
+        for key, masks in (('real_masks_', real_masks), ('complex_masks_', cmasks)):
+            got = O.apply_masks(data, masks, **kw)
+            ref = g[key + name]
+            assert got.dtype == ref.dtype == np.complex64
+            assert np.abs(got - ref).max() <= RTOL * np.abs(ref).max()
+    raw = O.apply_masks(data, O.com_mask_stack(data.shape[-2:], 0, 0), num_partitions=2)
+    assert np.abs(raw - g['com_raw']).max() <= RTOL * np.abs(g['com_raw']).max()
+    img = raw.reshape(data.shape[:2] + (3,))
+    y, x = O.center_shifts(img[..., 0], img[..., 1], img[..., 2], 0, 0)
+    y, x = O.apply_correction(y, x, 0., False)
+    np.testing.assert_allclose(x, g['com_x'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(y, g['com_y'], rtol=1e-4, atol=1e-4)

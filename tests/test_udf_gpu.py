@@ -785,3 +785,131 @@ def test_udf_level_k8_large_signal_and_wide_stack(lt):
     assert np.array_equal(res[3]['intensity'].raw_data, exact)
     com = O.com_udf(f32, num_partitions=1)
     close_cols(res[2]['raw_com'].raw_data, com['raw_com'])
+
+
+def _complex_inputs(meta):
+    shape = tuple(meta['shape'])
+    s0, s1 = meta['seeds']
+    data = (synth.dataset(shape, np.float32, s0)
+            + 1j * (synth.dataset(shape, np.float32, s1) - 0.5)).astype(np.complex64)
+    m0, m1, m2 = meta['mask_seeds']
+    real_masks = mixed_masks(shape[2], shape[3], 3, m0)
+    cmasks = (mixed_masks(shape[2], shape[3], 2, m1)
+              + 1j * mixed_masks(shape[2], shape[3], 2, m2)).astype(np.complex64)
+    return data, real_masks, cmasks
+
+
+@pytest.mark.parametrize('where', ['device', 'host'])
+def test_complex_input_golden(lt, where):
+    """complex64 frames vs the unmodified reference (udf/masks.py:360-368: the result dtype is
+    result_type(input, mask) = complex64): real masks, complex masks, full-frame and sub-frame
+    tiles.  The tile is read once as its interleaved (re, im) float view."""
+    meta, g = load_golden('complex_input')
+    data, real_masks, cmasks = _complex_inputs(meta)
+    src = torch.from_numpy(data).cuda() if where == 'device' else data
+    for name, kw in (('p2', dict(num_partitions=2)),
+                     ('tiled', dict(num_partitions=3, tileshape=(5, 8, 32)))):
+        ds = lt.MemoryDataSet(data=src, sig_dims=2, **kw)
+        for key, masks, dt in (('real_masks_', real_masks, np.float32),
+                               ('complex_masks_', cmasks, np.complex64)):
+            res = lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=lambda: masks,
+                                                      mask_dtype=dt, use_sparse=False))
+            got = res['intensity'].raw_data
+            ref = g[key + name]
+            assert got.dtype == np.complex64 and got.shape == ref.shape
+            scale = np.abs(ref).max(axis=0)
+            assert (np.abs(got - ref) / scale).max() <= RTOL, key + name
+
+
+def test_com_analysis_complex_known_answers(lt):
+    """tests/analysis/test_analysis_com.py:132-231: COMAnalysis on complex frames returns
+    x_real / y_real / x_imag / y_imag; handcrafted frames with exact answers, and the
+    reference's outputs on random complex data"""
+    ctx = lt.Context()
+    cases = [
+        ([[0, 0, 0, 0], [0, 1 + 2j, 1 - 2j, 0], [0, 1 - 2j, 1 + 2j, 0], [0, 0, 0, 0]], 1.5, 1.5),
+        ([[0, 0, 0, 0], [0, 0, 1 - 2j, 0], [0, 1 - 2j, 0, 0], [0, 0, 0, 0]], 1.5, 1.5),
+        ([[0, 0, 0, 0], [0, 0, 1 - 2j, 0], [0, 0, 0, 0], [0, 0, 0, 0]], 2, 1),
+    ]
+    for frame, want_x, want_y in cases:
+        data = np.ones((3, 3, 4, 4), dtype=np.complex64)
+        data[0, 0] = np.array(frame, dtype=np.complex64)
+        ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=9, sig_dims=2)
+        res = ctx.run(ctx.create_com_analysis(dataset=ds, cx=0, cy=0, mask_radius=None))
+        fx = res['x_real'].raw_data + 1j * res['x_imag'].raw_data
+        fy = res['y_real'].raw_data + 1j * res['y_imag'].raw_data
+        assert fx[0, 0] == want_x and fy[0, 0] == want_y
+    meta, g = load_golden('complex_input')
+    data, _, _ = _complex_inputs(meta)
+    ds = lt.MemoryDataSet(data=torch.from_numpy(data).cuda(), num_partitions=2, sig_dims=2)
+    res = ctx.run(ctx.create_com_analysis(dataset=ds, cx=0, cy=0, mask_radius=None))
+    fx = res['x_real'].raw_data + 1j * res['x_imag'].raw_data
+    fy = res['y_real'].raw_data + 1j * res['y_imag'].raw_data
+    np.testing.assert_allclose(fx, g['com_x'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(fy, g['com_y'], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('reg', [-1, 0, 1, 'given'])
+@pytest.mark.parametrize('use_roi', [False, True])
+def test_com_postprocess_device_matches_host(lt, reg, use_roi):
+    """CoMUDF.get_results through the nav-space kernels (K9) vs the numpy pipeline on the same
+    moments: all nine result buffers, every regression mode, with and without a roi"""
+    from libertem_b200.udf.com import CoMUDF
+    from libertem_b200.udf.base import UDFMeta, UDFData
+    from libertem_b200.common import Shape
+    nav, sig = (9, 13), (16, 16)
+    ds_shape = Shape(nav + sig, sig_dims=2)
+    n = nav[0] * nav[1]
+    roi = roi_from_seed(nav, 5) if use_roi else None
+    n_rows = n if roi is None else int(roi.sum())
+    rng = np.random.default_rng(3)
+    raw = np.empty((n_rows, 3), dtype=np.float32)
+    raw[:, 0] = rng.uniform(50, 100, n_rows)
+    raw[:, 1] = raw[:, 0] * rng.uniform(6, 10, n_rows)
+    raw[:, 2] = raw[:, 0] * rng.uniform(5, 9, n_rows)
+    raw[3] = 0                                    # empty frame: shifts fall back to (cy, cx)
+    regression = np.array([[0.3, -0.2], [0.01, 0.02], [-0.03, 0.005]]) if reg == 'given' else reg
+    out = []
+    for device in ('cuda', 'cpu'):
+        udf = CoMUDF.with_params(cy=7.3, cx=8.1, scan_rotation=27., flip_y=True,
+                                 regression=regression)
+        udf.set_meta(UDFMeta(dataset_shape=ds_shape, roi=roi, dataset_dtype=np.float32,
+                             input_dtype=np.float32, device=torch.device('cuda')))
+        decl = udf.get_result_buffers()
+        for b in decl.values():
+            b.set_shape_ds(ds_shape, roi)
+        decl['raw_mask_result'].replace_array(torch.from_numpy(raw).to(device))
+        udf.results = UDFData(decl)
+        out.append(udf.get_results())
+    dev, host = out
+    assert set(dev) == set(host)
+    for k in host:
+        a, b = np.asarray(dev[k]), np.asarray(host[k], dtype=np.float64)
+        assert a.reshape(-1).shape == b.reshape(-1).shape, k
+        np.testing.assert_allclose(a.reshape(b.shape), b, rtol=2e-6, atol=2e-6, err_msg=k,
+                                   equal_nan=True)
+
+
+def test_guess_corrections_device(lt):
+    """libertem_b200.nav.guess_corrections (one Gram-matrix pass + closed-form sweep) returns
+    what the reference's 720-pass search returns (udf/com.py:207-295)"""
+    from libertem_b200 import nav
+    from libertem_b200.udf.com import guess_corrections, apply_correction
+    ny, nx = 24, 31
+    yy, xx = np.mgrid[:ny, :nx].astype(np.float64)
+    # an anisotropic, mostly divergent field seen through a rotated, flipped scan + an offset
+    fy, fx = (yy - 11.5) * 0.3 + 0.05 * np.sin(xx / 3), (xx - 15.0) * 0.12
+    rng = np.random.default_rng(1)
+    fy += rng.normal(0, 0.01, fy.shape)
+    fx += rng.normal(0, 0.01, fx.shape)
+    for rot, flip in ((33, False), (-71, True), (170, False)):
+        y, x = apply_correction(fy, fx, scan_rotation=rot, flip_y=flip, forward=False)
+        y = (y + 2.5).astype(np.float32)
+        x = (x - 1.25).astype(np.float32)
+        want = guess_corrections(y, x)
+        got = nav.guess_corrections(y, x)
+        assert got.scan_rotation == want.scan_rotation and got.flip_y == want.flip_y
+        assert got.cy == pytest.approx(float(want.cy), rel=1e-5)
+        assert got.cx == pytest.approx(float(want.cx), rel=1e-5)
+        sub = (slice(2, 20), slice(3, 25))
+        assert nav.guess_corrections(y, x, roi=sub)[:2] == guess_corrections(y, x, roi=sub)[:2]
