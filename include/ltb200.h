@@ -162,8 +162,8 @@ LTB_API int ltb200_set_k1_variant(int variant);
  * 2 = generic kernel, 6 = tcgen05 tensor-core kernel; and for the other entry points:
  * 8 = int8 tensor-core kernel (K8), 20 = sparse CSC kernel (K2), 4 = group-sparse FFMA2
  * kernel (K4), 5 = shifted-mask kernel (K5), 7 / 70 / 71 = group-sparse tensor-core kernel (K7)
- * with the ring-major / quad-banded / mirror-symmetric plan, 9 = nav-space CoM kernels (K9)
- * (diagnostics / tests) */
+ * with the ring-major / quad-banded / mirror-symmetric plan
+ * (diagnostics / tests; the nav-space kernels K9 do not change it) */
 LTB_API int ltb200_last_kernel(void);
 /* number of kernel launches issued by this library on this thread since the last reset */
 LTB_API int64_t ltb200_launch_count(int reset);
@@ -280,8 +280,9 @@ LTB_API int ltb200_synth_fill(void* dst, int dtype, int64_t start, int64_t count
  * subtract the mean, 1 subtract the least-squares plane c0 + c1 y + c2 x -- both over the valid
  * positions --, 2 subtract the given plane; `regression` is the (3, 2) float64 device array,
  * read in mode 2 and written otherwise; com.py:600-648), magnitude / divergence / curl with
- * np.gradient stencils (com.py:130-142) in float64, rounded to float32 on store.  Outputs cover
- * the full scan grid: raw_shifts / raw_com / field (ny*nx, 2) as (y, x), the others (ny*nx).
+ * np.gradient stencils (com.py:130-142) in float64 -- the reference's result arrays for these are
+ * float64 too.  Outputs cover the full scan grid: raw_shifts / raw_com (float32) and field
+ * (float64) are (ny*nx, 2) as (y, x), the others (ny*nx) float64.
  * ny, nx >= 2 (np.gradient).  Sums are reduced in a fixed order (deterministic).
  * ------------------------------------------------------------------------------------- */
 LTB_API size_t ltb200_com_workspace(int ny, int nx);
@@ -289,8 +290,9 @@ LTB_API int ltb200_com_postprocess(const float* raw, int64_t ld_raw, const int32
                                    const uint8_t* valid, int ny, int nx, double cy, double cx,
                                    const double* transform /* host, 4 */, int regression_mode,
                                    double* regression /* device, 6 */, float* raw_shifts,
-                                   float* raw_com, float* field, float* field_y, float* field_x,
-                                   float* magnitude, float* divergence, float* curl,
+                                   float* raw_com, double* field, double* field_y,
+                                   double* field_x, double* magnitude, double* divergence,
+                                   double* curl,
                                    void* workspace, size_t workspace_bytes, void* stream);
 /* guess_corrections (udf/com.py:145-295) without 720 passes: the curl of a linearly transformed
  * field is linear in the gradient fields g = (dy/d0, dy/d1, dx/d0, dx/d1) of the (ny, nx) float32

@@ -6,10 +6,10 @@
 //   center_shifts (com.py:100-107)  -> apply_correction (2x2 float64 matrix, com.py:110-127)
 //   -> regression (mean / least-squares plane over the valid scan positions, com.py:600-648)
 //   -> magnitude / divergence / curl with np.gradient stencils (com.py:130-142).
-// Arithmetic follows the reference's dtypes: the shifts are float32 (divide, subtract the
-// reference point), everything after the float64 matrix product is float64 and rounded to
-// float32 once, on store.  Sums (regression normal equations, gradient Gram matrix) are reduced
-// in a fixed order (per-block partials, then one block): deterministic.
+// Arithmetic follows the reference's dtypes: the shifts and raw_com are float32 (divide,
+// subtract the reference point); everything after the float64 rotation matrix is float64 and is
+// returned as float64, like the reference's result arrays.  Sums (regression normal equations,
+// gradient Gram matrix) are reduced in a fixed order (per-block partials, then one block).
 //
 // The rotation / flip sweep needs no 720 passes: curl(T f) is linear in the four gradient
 // fields d(y,x)/d(axis 0,1), so its RMS for ANY 2x2 matrix T is a quadratic form in the 4x4 Gram
@@ -133,13 +133,13 @@ __global__ void com_regression_kernel(const double* __restrict__ partials, int n
         for (int k = 0; k < 2; k++) regression[2 * i + k] = c[i][k];
 }
 
-// field -= plane (valid positions), store float32 field / components / magnitude
+// field -= plane (valid positions), store field / components / magnitude
 __global__ void __launch_bounds__(NAV_THREADS)
 com_apply_regression_kernel(double* __restrict__ field, const int32_t* __restrict__ row_of_nav,
                             const uint8_t* __restrict__ valid, int ny, int nx,
-                            const double* __restrict__ regression, float* __restrict__ field_out,
-                            float* __restrict__ field_y, float* __restrict__ field_x,
-                            float* __restrict__ magnitude) {
+                            const double* __restrict__ regression, double* __restrict__ field_out,
+                            double* __restrict__ field_y, double* __restrict__ field_x,
+                            double* __restrict__ magnitude) {
     const int64_t n = (int64_t)ny * nx;
     double c[6];
 #pragma unroll
@@ -164,11 +164,11 @@ com_apply_regression_kernel(double* __restrict__ field, const int32_t* __restric
             field[2 * i] = fy;
             field[2 * i + 1] = fx;
         }
-        field_out[2 * i] = (float)fy;
-        field_out[2 * i + 1] = (float)fx;
-        field_y[i] = (float)fy;
-        field_x[i] = (float)fx;
-        magnitude[i] = (float)sqrt(fy * fy + fx * fx);
+        field_out[2 * i] = fy;
+        field_out[2 * i + 1] = fx;
+        field_y[i] = fy;
+        field_x[i] = fx;
+        magnitude[i] = sqrt(fy * fy + fx * fx);
     }
 }
 
@@ -181,8 +181,8 @@ __device__ __forceinline__ double grad_axis(const double* f, int64_t i, int64_t 
 }
 
 __global__ void __launch_bounds__(NAV_THREADS)
-com_div_curl_kernel(const double* __restrict__ field, int ny, int nx, float* __restrict__ divergence,
-                    float* __restrict__ curl) {
+com_div_curl_kernel(const double* __restrict__ field, int ny, int nx, double* __restrict__ divergence,
+                    double* __restrict__ curl) {
     const int64_t n = (int64_t)ny * nx;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -193,8 +193,8 @@ com_div_curl_kernel(const double* __restrict__ field, int ny, int nx, float* __r
         const double dyx = grad_axis(fy, 2 * i, 2, x, nx);
         const double dxy = grad_axis(fx, 2 * i, 2 * (int64_t)nx, y, ny);
         const double dxx = grad_axis(fx, 2 * i, 2, x, nx);
-        divergence[i] = (float)(dyy + dxx);     // d(y)/d(axis 0) + d(x)/d(axis 1)
-        curl[i] = (float)(dyx - dxy);           // d(y)/d(axis 1) - d(x)/d(axis 0)
+        divergence[i] = dyy + dxx;     // d(y)/d(axis 0) + d(x)/d(axis 1)
+        curl[i] = dyx - dxy;           // d(y)/d(axis 1) - d(x)/d(axis 0)
     }
 }
 
@@ -314,8 +314,8 @@ extern "C" int ltb200_com_postprocess(const float* raw, int64_t ld_raw, const in
                                       const uint8_t* valid, int ny, int nx, double cy, double cx,
                                       const double* transform, int regression_mode,
                                       double* regression, float* raw_shifts, float* raw_com,
-                                      float* field, float* field_y, float* field_x,
-                                      float* magnitude, float* divergence, float* curl,
+                                      double* field, double* field_y, double* field_x,
+                                      double* magnitude, double* divergence, double* curl,
                                       void* workspace, size_t workspace_bytes, void* stream) {
     LTB_REQUIRE(ny >= 2 && nx >= 2, "com_postprocess: np.gradient needs at least 2 scan positions "
                                     "per axis, got %d x %d", ny, nx);
@@ -341,7 +341,6 @@ extern "C" int ltb200_com_postprocess(const float* raw, int64_t ld_raw, const in
                                                                 field_x, magnitude);
     com_div_curl_kernel<<<blocks, NAV_THREADS, 0, st>>>(fld, ny, nx, divergence, curl);
     count_launch(4);
-    set_last_kernel(9);
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
 }

@@ -17,10 +17,10 @@ def com_postprocess(raw, nav_shape, cy, cx, transform, regression_mode, regressi
                     row_of_nav=None, valid=None):
     """raw: CUDA float32 ``(rows, >= 3)`` moments [m00, m10, m01] per (roi-compressed) scan
     position; transform: 2x2 float64 (rotation @ flip); regression_mode: -1 none, 0 mean,
-    1 least-squares plane, 2 given ``regression`` (3, 2).  Returns a dict of CUDA float32 tensors
-    over the FULL scan grid -- raw_shifts / raw_com / field ``(n, 2)``, field_y / field_x /
-    magnitude / divergence / curl ``(n,)``, NaN outside ``row_of_nav`` -- and 'regression'
-    ``(3, 2)`` float64."""
+    1 least-squares plane, 2 given ``regression`` (3, 2).  Returns a dict of CUDA tensors over
+    the FULL scan grid -- raw_shifts / raw_com ``(n, 2)`` float32, field ``(n, 2)`` and field_y /
+    field_x / magnitude / divergence / curl ``(n,)`` float64 (the reference's dtypes), NaN
+    outside ``row_of_nav`` -- and 'regression' ``(3, 2)`` float64."""
     lib = get_lib()
     ny, nx = (int(v) for v in nav_shape)
     n = ny * nx
@@ -28,8 +28,10 @@ def com_postprocess(raw, nav_shape, cy, cx, transform, regression_mode, regressi
     if raw.dtype != torch.float32 or raw.dim() != 2 or raw.shape[1] < 3 or raw.stride(1) != 1:
         raise ValueError('raw must be a float32 (rows, 3) CUDA tensor')
     f32 = dict(dtype=torch.float32, device=dev)
-    out = {k: torch.empty((n, 2), **f32) for k in ('raw_shifts', 'raw_com', 'field')}
-    out.update({k: torch.empty((n,), **f32)
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = {k: torch.empty((n, 2), **f32) for k in ('raw_shifts', 'raw_com')}
+    out['field'] = torch.empty((n, 2), **f64)
+    out.update({k: torch.empty((n,), **f64)
                 for k in ('field_y', 'field_x', 'magnitude', 'divergence', 'curl')})
     reg = torch.zeros((3, 2), dtype=torch.float64, device=dev)
     if regression_mode == 2:

@@ -83,7 +83,8 @@ def test_cfg2_small(lt, fuse):
         assert runner.stats['unfused_calls'] == 0
         assert runner.stats['fused_launch_groups'] == runner.stats['tiles'] == \
             meta['num_partitions']
-        assert launches <= 5 * meta['num_partitions'], launches
+        # (+ the four nav-space launches of CoMUDF.get_results, K9)
+        assert launches <= 5 * meta['num_partitions'] + 4, launches
     close_cols(res[0]['intensity'].raw_data, g['intensity'])
     assert 'raw_mask_result' not in res[1]          # private buffer stays private
     check_com(res[1], g)
