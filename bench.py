@@ -697,7 +697,10 @@ def gpu_arm(args):
     ok = head['parity_ok']
 
     if not args.no_e2e:
-        line['e2e'] = e2e_leg(ctx, ds, mine[0], stack, total_frames)
+        del ds
+        torch.cuda.empty_cache()
+        line['e2e'] = e2e_leg(ctx, stack, total_frames)
+        ds = None
     del ds
     torch.cuda.empty_cache()
     if world == 1 and not args.no_configs:
@@ -737,32 +740,39 @@ def gpu_arm(args):
         sys.exit(1)
 
 
-def _host_copy(ctx, ds, part):
-    """the rank's shard as a pinned host array (filled by D2H from the resident device data)"""
+def _host_frames(ctx, f0, f1):
+    """frames [f0, f1) of the synthetic scan as a pinned host array (generated on the device in
+    chunks by the counter-based generator, then copied down)"""
     torch = ctx.torch
-    t = ds.partition_tensor(part, ctx.device)
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    host.copy_(t)
+    from libertem_b200 import engine
+    k = SIG[0] * SIG[1]
+    host = torch.empty((f1 - f0,) + SIG, dtype=torch.float32, pin_memory=True)
+    step = 4096
+    for a in range(f0, f1, step):
+        b = min(f1, a + step)
+        t = engine.synth_fill((b - a,) + SIG, np.float32, DATA_SEED, ctx.device, start=a * k)
+        host[a - f0:b - f0].copy_(t)
     torch.cuda.synchronize()
     return host
 
 
-def h2d_peak(ctx, host, chunk_frames=1024, reps=2):
-    """bare H2D: cudaMemcpyAsync of the whole pinned shard in chunks into one device buffer.
-    Returns (GB/s per GPU with all ranks copying at the same time, as a list over ranks;
-    GB/s of every rank copying ALONE, list over ranks): placement problems (a rank whose pinned
-    memory sits on the far socket) show up in the second list, shared-resource limits (host
-    memory bandwidth, PCIe switch uplinks) as the difference between the two."""
+def h2d_peak(ctx, probe_frames=4096, passes=8, reps=2):
+    """bare H2D: cudaMemcpyAsync from a pinned 1 GiB host buffer (`passes` times per measurement)
+    into one device buffer.  Returns (GB/s per GPU with all ranks copying at the same time, list
+    over ranks; GB/s of every rank copying ALONE, list over ranks): placement problems (a rank
+    whose pinned memory sits on a far socket) show up in the second list, shared-resource limits
+    (host memory / IO-die bandwidth, PCIe switch uplinks) as the difference between the two."""
     torch = ctx.torch
-    flat = host.reshape(host.shape[0], -1)
-    dst = torch.empty((chunk_frames, flat.shape[1]), dtype=flat.dtype, device=ctx.device)
-    nbytes = flat.numel() * flat.element_size()
+    k = SIG[0] * SIG[1]
+    flat = torch.empty((probe_frames, k), dtype=torch.float32, pin_memory=True)
+    flat.zero_()
+    dst = torch.empty_like(flat, device=ctx.device)
+    nbytes = flat.numel() * flat.element_size() * passes
 
     def once():
         t0 = time.perf_counter()
-        for f0 in range(0, flat.shape[0], chunk_frames):
-            n = min(chunk_frames, flat.shape[0] - f0)
-            dst[:n].copy_(flat[f0:f0 + n], non_blocking=True)
+        for _ in range(passes):
+            dst.copy_(flat, non_blocking=True)
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
@@ -774,6 +784,7 @@ def h2d_peak(ctx, host, chunk_frames=1024, reps=2):
         ctx.dist.all_reduce(t)
         return [float(v) for v in t.tolist()]
 
+    once()
     best = None
     for _ in range(reps):
         ctx.barrier()
@@ -792,29 +803,40 @@ def h2d_peak(ctx, host, chunk_frames=1024, reps=2):
     return together, alone
 
 
-def e2e_leg(ctx, ds, part, stack, total_frames):
+def e2e_leg(ctx, stack, total_frames):
     """end to end through the public API on HOST pinned input: H2D of every frame, the kernel,
     the NCCL all-gather (N>1) and D2H / get_results of every result buffer inside the timed
-    region, every step"""
+    region, every step.  N>1: the scan is cut into 8 x N partitions and every rank takes a
+    contiguous share proportional to its measured concurrent host-link rate
+    (UDFRunner(rank_weights=...)), so all ranks finish together even when the host links of the
+    box are not equal."""
     torch = ctx.torch
     from libertem_b200.io import MemoryDataSet
+    from libertem_b200.io.memory import partition_boundaries
     from libertem_b200.runner import UDFRunner
     from libertem_b200.udf import ApplyMasksUDF, CoMUDF
-    world = ctx.world
-    host = _host_copy(ctx, ds, part)
-    together, alone = h2d_peak(ctx, host)
-    peak = min(together)
+    world, rank = ctx.world, ctx.rank
+    together, alone = h2d_peak(ctx)
+    weights = None
     if world == 1:
+        host = _host_frames(ctx, 0, total_frames)
         hds = MemoryDataSet(data=host.reshape(NAV + SIG), num_partitions=1, sig_dims=2, pin=False)
+        my_frames = total_frames
     else:
-        # every rank sees the same (256 * world) x 256 scan; only its own shard is backed by
-        # (pinned) host memory -- ranks never touch the other partitions
-        hds = ShardedHostDataSet(host, (NAV[0] * world, NAV[1]) + SIG, ctx.rank, world)
+        n_parts = 8 * world
+        weights = [round(w, 1) for w in together]
+        bounds = partition_boundaries(total_frames, n_parts)
+        mine = UDFRunner.my_partitions(bounds, rank, world, weights)
+        f0, f1 = mine[0][0], mine[-1][1]
+        host = _host_frames(ctx, f0, f1)
+        hds = ShardedHostDataSet(host, (NAV[0] * world, NAV[1]) + SIG, f0, n_parts)
+        my_frames = f1 - f0
     steps = min(ctx.args.steps, 3 if world == 1 else 2)
 
     def one():
         r = UDFRunner([ApplyMasksUDF(mask_factories=lambda: stack, mask_count=N_MASKS,
-                                     mask_dtype=np.float32, use_sparse=False), CoMUDF()])
+                                     mask_dtype=np.float32, use_sparse=False), CoMUDF()],
+                      rank_weights=weights)
         res = r.run_for_dataset(hds, device=ctx.device).buffers
         return res[0]['intensity'].raw_data, res[1]['field'].raw_data
 
@@ -828,28 +850,48 @@ def e2e_leg(ctx, ds, part, stack, total_frames):
         ctx.dist.barrier()
     dt = ctx.max_over_ranks((time.perf_counter() - t0) / steps)
     assert a.shape[0] == total_frames
-    h2d = int(host.numel() * host.element_size()) * world
-    gbs = h2d / world / dt / 1e9
+    k = SIG[0] * SIG[1]
+    h2d = int(total_frames * k * 4)
+    # every rank moves its own share; the aggregate is what the box's host links deliver
+    agg = h2d / dt / 1e9
+    peak_agg = float(sum(together))
     return {'value': total_frames / dt, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': int(total_frames * (N_MASKS + 3) * 4) * world, 'steps': steps,
-            'ms_per_step': dt * 1e3, 'h2d_gbs_per_gpu': gbs, 'h2d_peak_gbs': peak,
-            'h2d_frac_of_peak': gbs / peak,
+            'ms_per_step': dt * 1e3, 'h2d_gbs_aggregate': agg,
+            'h2d_peak_gbs': peak_agg, 'h2d_frac_of_peak': agg / peak_agg,
             'h2d_peak_gbs_per_rank_concurrent': [round(v, 2) for v in together],
             'h2d_peak_gbs_per_rank_alone': [round(v, 2) for v in alone],
+            'frames_this_rank0': my_frames, 'rank_weights': weights,
             'note': 'run_for_dataset on pinned host data: double-buffered H2D tiles overlapped '
-                    'with the kernel' + (', NCCL all-gather of the result slab' if world > 1
-                                         else '') + ', D2H of all result buffers and CoM '
-                    'get_results on the host; h2d_peak_gbs = bare cudaMemcpyAsync of the same '
-                    'pinned shard on all ranks concurrently (min over ranks)'}
+                    'with the kernel' + (', NCCL all-gather of the result slab, partition '
+                                         'shares proportional to the measured per-rank H2D rate'
+                                         if world > 1 else '') +
+                    ', D2H of all result buffers and CoM get_results; h2d_peak_gbs = sum over '
+                    'ranks of a bare cudaMemcpyAsync loop from pinned memory with all ranks '
+                    'copying concurrently (per rank: ..._concurrent; one rank at a time: '
+                    '..._alone)'}
 
 
 class ShardedHostDataSet:
     """MemoryDataSet-compatible view of a multi-rank scan whose partitions live in per-rank
-    pinned host memory: partition r is backed by rank r's array only"""
+    pinned host memory: `host` holds frames [first, first + len(host)) of the scan, which is
+    cut into `num_partitions` partitions; a rank only ever touches its own partitions"""
 
-    def __new__(cls, host, shape, rank, world):
+    def __new__(cls, host, shape, first, num_partitions):
         from libertem_b200.io.memory import MemoryDataSet
         from libertem_b200.common.shape import Shape
+
+        class _Offset:
+            """frames [first, first + n) of the scan"""
+
+            def __init__(self, t):
+                self.t = t
+                self.is_cuda = False
+                self.dtype = t.dtype
+
+            def __getitem__(self, sl):
+                assert sl.start >= first and sl.stop <= first + self.t.shape[0]
+                return self.t[sl.start - first:sl.stop - first]
 
         class _DS(MemoryDataSet):
             def __init__(self):
@@ -858,27 +900,14 @@ class ShardedHostDataSet:
                 self._shape = Shape(tuple(shape), sig_dims=2)
                 self._dtype = np.dtype('float32')
                 self.tileshape = None
-                self.num_partitions = world
+                self.num_partitions = num_partitions
                 self.tile_depth = None
                 self._pin = False
                 self._registered = False
                 self._stage = {}
-                self._first = rank * host.shape[0]
 
             def _flat(self):
-                return _Offset(self.data.reshape((host.shape[0],) + tuple(shape[2:])),
-                               self._first)
-
-        class _Offset:
-            """frames [first, first + n) of the scan"""
-
-            def __init__(self, t, first):
-                self.t, self.first = t, first
-                self.is_cuda = False
-                self.dtype = t.dtype
-
-            def __getitem__(self, sl):
-                return self.t[sl.start - self.first:sl.stop - self.first]
+                return _Offset(self.data.reshape((host.shape[0],) + tuple(shape[2:])))
 
         return _DS()
 

@@ -187,6 +187,12 @@ LTB_API int ltb200_masks_shifted(const void* tile, int tile_dtype, int64_t n_fra
                                  int sig_x, int64_t ld_tile, const float* masks, int n_masks,
                                  int64_t ld_masks, const int32_t* shifts, int per_frame,
                                  float* out, int64_t ld_out, int accumulate, void* stream);
+/* float64 masks / accumulation / result: the reference's dtype rule for float64 masks or frames
+ * (result_type(input, mask), udf/masks.py:360-368); tile dtypes f32, f64, u8, u16, i16, i32 */
+LTB_API int ltb200_masks_shifted_f64(const void* tile, int tile_dtype, int64_t n_frames, int sig_y,
+                                     int sig_x, int64_t ld_tile, const double* masks, int n_masks,
+                                     int64_t ld_masks, const int32_t* shifts, int per_frame,
+                                     double* out, int64_t ld_out, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Group-sparse masked reduction (K4) -- RadialFourierAnalysis: masks come in groups (rings)

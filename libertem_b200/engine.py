@@ -259,8 +259,8 @@ def set_k1_variant(variant):
 
 
 def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
-    """per-frame shifted masks: tile (F, sy, sx), masks (M, sy*sx) float32, shifts int32
-    (F, 2) or (1, 2) (dy, dx) -> out (F, M)"""
+    """per-frame shifted masks: tile (F, sy, sx), masks (M, sy*sx) float32 or float64 (-> float64
+    accumulation and result), shifts int32 (F, 2) or (1, 2) (dy, dx) -> out (F, M)"""
     lib = get_lib()
     _require_cuda(tile, 'tile')
     _require_cuda(masks, 'masks')
@@ -268,19 +268,24 @@ def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
     tile = tile.contiguous()
     masks = masks.contiguous()
     M = masks.shape[0]
+    if masks.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f'masks must be float32 or float64, got {masks.dtype}')
+    f64 = masks.dtype == torch.float64
     shifts = shifts.to(device=tile.device, dtype=torch.int32).contiguous()
     per_frame = int(shifts.shape[0] != 1)
     if per_frame and shifts.shape[0] != F:
         raise ValueError('need one (dy, dx) per frame or a single pair')
     if out is None:
-        out = torch.zeros((F, M), dtype=torch.float32, device=tile.device)
+        out = torch.zeros((F, M), dtype=masks.dtype, device=tile.device)
         accumulate = False
+    elif out.dtype != masks.dtype or (M > 1 and out.stride(1) != 1):
+        raise ValueError('out must have the dtype of the masks and unit inner stride')
     ld_out = out.stride(0) if F > 1 else max(M, 1)
+    fn = lib.ltb200_masks_shifted_f64 if f64 else lib.ltb200_masks_shifted
     with torch.cuda.device(tile.device):
-        check(lib.ltb200_masks_shifted(
-            tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, sy, sx, sy * sx, masks.data_ptr(), M,
-            masks.shape[1], shifts.data_ptr(), per_frame, out.data_ptr(), ld_out,
-            int(bool(accumulate)), _stream_ptr(tile.device)))
+        check(fn(tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, sy, sx, sy * sx, masks.data_ptr(),
+                 M, masks.shape[1], shifts.data_ptr(), per_frame, out.data_ptr(), ld_out,
+                 int(bool(accumulate)), _stream_ptr(tile.device)))
     return out
 
 

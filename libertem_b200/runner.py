@@ -50,29 +50,68 @@ def _get_dtype(udfs, dtype, corrections=None):
     return tmp
 
 
-def int8_digit_plan(rows, max_rows=16):
-    """int8 form of a float32 mask stack (M, K) for the integer tensor-core kernel K8, or None.
+#: fixed-point digits (base 128) of a non-integer mask weight: 4 digits = 28 bits relative to the
+#: power of two above the row's largest weight, i.e. |m - q s| <= 2^-27 max|m| -- below float32
+#: resolution for every weight within a factor 8 of the largest one
+FLOAT_MASK_DIGITS = 4
+FLOAT_MASKS_INT8 = os.environ.get('LTB200_FLOAT_MASKS_INT8', '1') != '0'
 
-    Every weight must be an integer.  ``|m| <= 127``: ``(rows as int8, None, None)``.  Up to
-    ``127 * 129``: the wide rows are split into two base-128 digits ``m = d0 + 128 d1`` (both in
-    [-127, 127], ``d1 = trunc(m / 128)``); the high digits are appended as extra rows and the
-    caller adds ``128 x`` their results to the source rows: ``(int8 rows, source row indices,
-    positions of the appended rows)``.  None when the weights are not integers, too large, or
-    the digits do not fit in ``max_rows`` rows."""
+
+def int8_digit_plan(rows, max_rows=16, float_digits=FLOAT_MASK_DIGITS):
+    """int8 form of a float32 mask stack (M, K) for the integer tensor-core kernel K8, or None:
+    ``(int8 rows (R, K), combine)`` with ``masks = combine @ int8 rows`` -- ``combine`` is None
+    when the int8 rows ARE the masks, else a float64 (M, R) matrix.
+
+    * integer weights with ``|m| <= 127``: the row itself;
+    * integer weights up to ``127 * 129`` (CoM coordinate masks of detectors up to 16k wide): two
+      base-128 digits ``m = d0 + 128 d1`` (both in [-127, 127], ``d1 = trunc(m / 128)``) -- exact;
+    * any other float32 row (``float_digits > 0``): fixed point ``m ~ s * q`` with the power of two
+      ``s = 2^(e - 27)``, ``2^e >= max|m|``, ``q = round(m / s)`` split into four balanced
+      base-128 digits.  The integer sums of K8 are exact, so the only error of the pass is the
+      quantisation ``|m - s q| <= s / 2 <= 2^-27 max|m|`` per weight (bound on a result:
+      ``2^-27 max|m| sum|x|``; the reference's float32 GEMM carries ~1e-7 sum|x||m|).
+    None when the digits do not fit in ``max_rows`` rows."""
     M = rows.shape[0]
     amax = rows.abs().amax(dim=1)
-    if not bool((rows == rows.round()).all().item()) or float(amax.max()) > 127 * 129:
+    is_int = (rows == rows.round()).all(dim=1) & (amax <= 127 * 129)
+    if bool(is_int.all()) and float(amax.max()) <= 127:
+        return (rows.to(torch.int8).contiguous(), None)
+    if not bool(is_int.all()) and (float_digits <= 0 or not FLOAT_MASKS_INT8):
         return None
-    wide = torch.nonzero(amax > 127).reshape(-1)
-    if len(wide) == 0:
-        return (rows.to(torch.int8).contiguous(), None, None)
-    if M + len(wide) > max_rows:
+    if not bool(torch.isfinite(rows).all()):
         return None
-    d1 = torch.trunc(rows[wide] / 128.0)
-    d0 = rows.clone()
-    d0[wide] -= 128.0 * d1
-    i8 = torch.cat([d0, d1]).to(torch.int8).contiguous()
-    return (i8, wide, torch.arange(M, M + len(wide), device=rows.device))
+    pieces, combine = [], []
+    for c in range(M):
+        r = rows[c]
+        if bool(is_int[c]):
+            if float(amax[c]) <= 127:
+                pieces.append(r[None])
+                combine.append((c, 1.0))
+            else:
+                d1 = torch.trunc(r / 128.0)
+                pieces.append(torch.stack([r - 128.0 * d1, d1]))
+                combine += [(c, 1.0), (c, 128.0)]
+            continue
+        e = int(np.ceil(np.log2(float(amax[c]))))
+        if float(amax[c]) > 2.0 ** e:          # guard against log2 rounding
+            e += 1
+        shift = 7 * float_digits - 1 - e        # q = m * 2^shift, |q| <= 2^(7 D - 1)
+        q = torch.round(r.double() * (2.0 ** shift)).to(torch.int64)
+        digits = []
+        for _ in range(float_digits - 1):
+            d = torch.remainder(q + 64, 128) - 64
+            digits.append(d)
+            q = (q - d) // 128
+        digits.append(q)                        # top digit: |q| <= 64
+        pieces.append(torch.stack(digits).to(torch.float32))
+        combine += [(c, 2.0 ** -shift * 128.0 ** j) for j in range(float_digits)]
+    if len(combine) > max_rows:
+        return None
+    i8 = torch.cat(pieces).to(torch.int8).contiguous()
+    C = torch.zeros((M, len(combine)), dtype=torch.float64, device=rows.device)
+    for j, (c, w) in enumerate(combine):
+        C[c, j] = w
+    return (i8, C)
 
 
 class UDFResults:
@@ -105,10 +144,15 @@ class ResultBuffer(BufferWrapper):
 
 
 class UDFRunner:
-    def __init__(self, udfs, debug=False, fuse=True):
+    def __init__(self, udfs, debug=False, fuse=True, rank_weights=None):
         self._udfs = list(udfs)
         self._debug = debug
         self._fuse = fuse
+        #: multi-rank runs: relative share of the partitions every rank takes (default: equal).
+        #: Host-resident data is bound by each GPU's host link, and the links of one box are not
+        #: always equal (bench.py measures 23 vs 35 GB/s per GPU with 8 concurrent copies): a
+        #: share proportional to the link rate lets every rank finish at the same time.
+        self._rank_weights = None if rank_weights is None else [float(w) for w in rank_weights]
         self.stats = {'tiles': 0, 'fused_launch_groups': 0, 'unfused_calls': 0}
         self._cat_cache = {}
         self._int8_cache = {}
@@ -129,10 +173,17 @@ class UDFRunner:
         return None
 
     @staticmethod
-    def my_partitions(partitions, rank, world):
-        """contiguous block of partitions per rank"""
+    def my_partitions(partitions, rank, world, weights=None):
+        """contiguous block of partitions per rank; with ``weights`` the block sizes
+        are proportional to them (every rank computes the same boundaries)"""
         n = len(partitions)
-        b = np.linspace(0, n, world + 1, dtype=int)
+        if weights is None:
+            b = np.linspace(0, n, world + 1, dtype=int)
+        else:
+            w = np.asarray(weights, dtype=np.float64)
+            if len(w) != world or not np.all(w > 0):
+                raise UDFException('rank_weights: one positive weight per rank')
+            b = np.concatenate([[0], np.rint(np.cumsum(w) / w.sum() * n)]).astype(int)
         return partitions[b[rank]:b[rank + 1]]
 
     # -- main entry -------------------------------------------------------------------------------
@@ -199,7 +250,7 @@ class UDFRunner:
         partitions = list(dataset.get_partitions())
         dist = self._dist()
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-        mine = self.my_partitions(partitions, rank, world)
+        mine = self.my_partitions(partitions, rank, world, self._rank_weights)
         damage = np.zeros(n_frames if roi_flat is None else int(roi_flat.sum()), dtype=bool)
 
         self._input_tdtype = torch_dtype(input_dtype) if np.dtype(input_dtype) in _NP2TORCH \
@@ -489,26 +540,25 @@ class UDFRunner:
             self.stats['fused_launch_groups'] += 1
 
     def _dense(self, flat, rows, out=None, accumulate=False, sig_sum=None):
-        """One fused pass.  uint16 / uint8 tiles against integer-valued mask rows (binary virtual
-        detectors, the all-ones row of SumSigUDF, the CoM coordinate masks, ...) take the exact
-        int8 tensor-core kernel (K8); everything else the float kernels behind
-        ``masks_dense``."""
+        """One fused pass.  uint16 / uint8 tiles take the integer tensor-core kernel (K8) whenever
+        the mask rows fit its int8 digit rows: integer-valued rows (binary virtual detectors, the
+        all-ones row of SumSigUDF, the CoM coordinate masks) exactly, other float32 rows as
+        28-bit fixed point (error <= 2^-27 max|m| sum|x|); everything else the float kernels behind ``masks_dense``."""
         plan = self._int8_rows(flat, rows)
         if plan is None:
             return engine.masks_dense(flat, rows, out=out, accumulate=accumulate,
                                       sig_sum=sig_sum)
-        i8, hi_src, hi_rows = plan
+        i8, combine = plan
         self.stats['int8_passes'] = self.stats.get('int8_passes', 0) + 1
-        if hi_src is None:
+        if combine is None:
             return engine.masks_dense_i8(flat, i8, out=out, accumulate=accumulate,
                                          sig_sum=sig_sum)
-        # rows with weights beyond int8 were split into two base-128 digits: recombine
+        # digit rows (wide integer weights, fixed-point float weights): recombine the exact
+        # per-digit sums in float64, round once
         res = engine.masks_dense_i8(flat, i8, sig_sum=sig_sum)
-        M = rows.shape[0]
-        val = res[:, :M]
-        val[:, hi_src] += 128.0 * res[:, hi_rows]
+        val = (res.double() @ combine.T).float()
         if out is None:
-            return val.contiguous()
+            return val
         if accumulate:
             out += val
         else:
@@ -516,10 +566,8 @@ class UDFRunner:
         return out
 
     def _int8_rows(self, flat, rows):
-        """int8 form of the mask rows when K8 applies to this tile, cached per row stack:
-        ``(int8 rows, None, None)`` when every weight is an integer in [-127, 127], else
-        ``(int8 rows incl. appended high digits, source row indices, their positions)`` for
-        integer weights up to 127 * 129 (m = d0 + 128 d1, both digits int8), else None."""
+        """int8 form of the mask rows when K8 applies to this tile (``int8_digit_plan``), cached
+        per row stack, else None"""
         F, K = flat.shape
         M = rows.shape[0]
         if flat.dtype not in (torch.uint16, torch.uint8):
@@ -684,7 +732,7 @@ class UDFRunner:
         backend = dist.get_backend()
         bounds = []
         for r in range(world):
-            mine = self.my_partitions(partitions, r, world)
+            mine = self.my_partitions(partitions, r, world, self._rank_weights)
             if mine:
                 a, _ = self._roi_range(mine[0], roi_flat)
                 _, b = self._roi_range(mine[-1], roi_flat)

@@ -247,17 +247,30 @@ class ApplyMasksUDF(UDF):
 
     def process_tile_shifted(self, tile, shifts):
         """all frames of a full-frame tile with their own (dy, dx) in ONE launch (K5) instead
-        of the reference's frame-by-frame loop; returns False if this case needs the loop"""
+        of the reference's frame-by-frame loop (udf/masks.py:85-124): float32 and float64
+        results, complex masks as interleaved (re, im) rows; returns False if this case needs
+        the loop (complex frames, sub-frame tiles)"""
         eng = self.task_data['engine']
         view = self.results.intensity
         sig = tuple(self.meta.dataset_shape.sig)
-        if (eng.compute != np.float32 or eng.result_dtype != np.float32 or len(sig) != 2
-                or tuple(tile.shape[1:]) != sig or not view.is_cuda
-                or tile.dtype not in (torch.float32, torch.uint16, torch.uint8, torch.int16)):
+        if (eng.complex_input or len(sig) != 2 or tuple(tile.shape[1:]) != sig
+                or not view.is_cuda or eng.result_dtype not in (
+                    np.float32, np.float64, np.complex64, np.complex128)):
             return False
-        rows = eng.dense_rows()
+        f64 = eng.compute == np.float64
+        ok = (torch.float32, torch.float64, torch.uint16, torch.uint8, torch.int16, torch.int32)
+        if tile.dtype not in ok:
+            return False
+        rows = eng.dense_rows()          # complex masks: (2M, K) interleaved (re, im) rows
+        if rows.dtype != (torch.float64 if f64 else torch.float32):
+            return False
+        out = view
+        if view.is_complex():
+            out = torch.view_as_real(view).reshape(view.shape[0], -1)
+        if out.dtype != rows.dtype or (out.shape[1] > 1 and out.stride(1) != 1):
+            return False
         sh = torch.from_numpy(np.ascontiguousarray(shifts, dtype=np.int32).reshape(-1, 2))
-        engine.masks_shifted(tile, rows, sh, out=view, accumulate=True)
+        engine.masks_shifted(tile, rows, sh, out=out, accumulate=True)
         return True
 
     def process_frame(self, frame):

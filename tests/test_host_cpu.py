@@ -322,6 +322,9 @@ def test_memory_dataset_partitions_and_roi_tiles():
     assert [(p.start, p.stop) for p in parts] == O.partition_boundaries(30, 4)
     assert parts[1].slice.origin == (parts[1].start, 0, 0)
     assert UDFRunner.my_partitions(parts, 1, 2) == parts[2:4]
+    # weighted shares: contiguous, disjoint, complete
+    blocks = [UDFRunner.my_partitions(parts, r, 3, weights=[1, 2, 1]) for r in range(3)]
+    assert sum(blocks, []) == parts and [len(b) for b in blocks] == [1, 2, 1]
     # sub-frame tiles in the reference's order: depth blocks outer, sig slices inner
     ds2 = MemoryDataSet(data=data, num_partitions=1, sig_dims=2, tileshape=(8, 2, 4))
     seen = [(f0, f1, t.origin, tuple(t.shape)) for _, f0, f1, t in
@@ -413,32 +416,46 @@ def test_banded_quad_plan_random(seed, K, size, n_rings, n_bands):
 
 
 def test_int8_digit_plan():
-    """host side of the integer fast path: which mask stacks K8 takes and how wide integer
-    weights are split into base-128 int8 digits"""
+    """host side of the integer fast path: which mask stacks K8 takes, how wide integer weights
+    are split into base-128 int8 digits and how float weights become 28-bit fixed point"""
     from libertem_b200.runner import int8_digit_plan
     K = 64
     binary = torch.zeros((3, K))
     binary[0] = 1
     binary[1, ::3] = 1
     binary[2, 5:9] = -127
-    i8, src, pos = int8_digit_plan(binary)
-    assert src is None and pos is None and i8.dtype == torch.int8
+    i8, comb = int8_digit_plan(binary)
+    assert comb is None and i8.dtype == torch.int8
     assert torch.equal(i8.float(), binary)
     # CoM coordinate rows of a 256-wide detector: 0..255 needs a second digit
     grad = torch.arange(K, dtype=torch.float32).repeat(2, 1) * 4.0          # 0 .. 252
     grad[1] = -grad[1] - 16000 + 3                                          # down to -16249
     stack = torch.cat([binary[:1], grad])
-    i8, src, pos = int8_digit_plan(stack)
-    assert i8.shape == (5, K) and src.tolist() == [1, 2] and pos.tolist() == [3, 4]
+    i8, comb = int8_digit_plan(stack)
+    assert i8.shape == (5, K) and comb.shape == (3, 5)
     assert int(i8.abs().max()) <= 127
-    rebuilt = i8[:3].float()
-    rebuilt[src] += 128.0 * i8[pos].float()
-    assert torch.equal(rebuilt, stack)
-    # not representable: fractional weights, too large, too many rows
-    assert int8_digit_plan(stack * 0.5 + 0.25) is None
-    assert int8_digit_plan(stack * 2) is None
+    assert torch.equal((comb @ i8.double()).float(), stack)                 # exact
+    # integer weights beyond two digits / too many rows: not representable as integer digits
+    assert int8_digit_plan(stack * 2, float_digits=0) is None
+    assert int8_digit_plan(stack * 0.5 + 0.25, float_digits=0) is None
     assert int8_digit_plan(grad[:1].repeat(9, 1)) is None                   # 9 + 9 rows > 16
     assert int8_digit_plan(grad[:1].repeat(8, 1)) is not None
+    # float weights: four balanced base-128 digits of round(m 2^(27 - e)); |m - s q| <= 2^-27 max|m|
+    rng = np.random.default_rng(7)
+    fl = torch.from_numpy(np.stack([
+        rng.uniform(0, 1, K), rng.normal(0, 3e-4, K), rng.uniform(-5e6, 5e6, K),
+        np.exp(rng.uniform(-30, 3, K))]).astype(np.float32))
+    both = torch.cat([binary[:1], fl, grad[:1]])
+    i8, comb = int8_digit_plan(both, max_rows=32)
+    assert i8.shape[0] == 1 + 4 * 4 + 2 and int(i8.abs().max()) <= 127
+    rebuilt = comb @ i8.double()
+    err = (rebuilt - both.double()).abs().amax(dim=1)
+    bound = both.abs().amax(dim=1).double() * 2.0 ** -27
+    assert bool((err <= bound).all()), (err, bound)
+    assert torch.equal(rebuilt[0].float(), both[0]) and torch.equal(rebuilt[5].float(), both[5])
+    assert int8_digit_plan(fl.repeat(3, 1), max_rows=32) is None            # 48 rows > 32
+    z = int8_digit_plan(torch.zeros((2, K)))
+    assert z[1] is None and not z[0].any()
 
 
 def _emulate_quad_plan(b, data, n_rings, size, n_cols):

@@ -414,12 +414,25 @@ def test_shifts(lt):
     engine.launch_count(reset=True)
     lt.run_udf(ds, udf)
     assert engine.launch_count() == 2          # one per partition
-    # float64 masks: falls back to the reference-style frame loop, same numbers
+    # float64 masks (float64 result, the reference's dtype rule) and complex masks go through the
+    # same kernel -- one launch per partition, no frame loop -- with the same numbers
     stack64 = stack.astype(np.float64)
+    engine.launch_count(reset=True)
     r64 = lt.run_udf(ds, lt.udf.ApplyMasksUDF(mask_factories=lambda: stack64,
                                               shifts=tuple(meta['const'])))
+    assert engine.launch_count() == 2
     assert r64['intensity'].raw_data.dtype == np.float64
-    close_cols(r64['intensity'].raw_data, g['const'])
+    close_cols(r64['intensity'].raw_data, g['const'], rtol=1e-6)
+    stackc = (stack[:1] + 1j * stack[1:2]).astype(np.complex64)
+    udfc = lt.udf.ApplyMasksUDF(
+        mask_factories=lambda: stackc,
+        shifts=lt.udf.ApplyMasksUDF.aux_data(sh.ravel(), kind='nav', extra_shape=(2,),
+                                             dtype=sh.dtype))
+    engine.launch_count(reset=True)
+    rc = lt.run_udf(ds, udfc)['intensity'].raw_data
+    assert engine.launch_count() == 2 and rc.dtype == np.complex64
+    close_cols(rc.real, g['perframe'][:, :1])
+    close_cols(rc.imag, g['perframe'][:, 1:2])
 
 
 def test_process_tile_seam_with_numpy_tile(lt):
@@ -914,3 +927,34 @@ def test_guess_corrections_device(lt):
         assert got.cx == pytest.approx(float(want.cx), rel=1e-5)
         sub = (slice(2, 20), slice(3, 25))
         assert nav.guess_corrections(y, x, roi=sub)[:2] == guess_corrections(y, x, roi=sub)[:2]
+
+
+def test_u16_float_masks_fixed_point_int8_path(lt):
+    """uint16 frames x NON-integer masks: the masks become 28-bit fixed-point int8 digit rows
+    (runner.int8_digit_plan) and the pass runs on the integer tensor cores (K8) with exact
+    integer sums -- the result is closer to the float64 sums than the reference's float32 GEMM
+    and within the north-star tolerance of it; SumUDF / SumSigUDF stay bit-exact"""
+    from libertem_b200 import engine
+    shape = (24, 32, 64, 64)
+    data = synth.dataset(shape, np.uint16, 77)
+    yy, xx = np.mgrid[:64, :64]
+    r = np.hypot(yy - 31.5, xx - 30.2)
+    masks = np.stack([np.exp(-((r - r0) / 4.0) ** 2) * w
+                      for r0, w in ((8, 1.0), (16, 0.37), (24, 2.5e-3), (28, -41.7))]
+                     ).astype(np.float32)
+    ds = lt.MemoryDataSet(
+        data=torch.from_numpy(data.view(np.int16)).view(torch.uint16).cuda(),
+        num_partitions=1, sig_dims=2)
+    runner = lt.UDFRunner([lt.udf.SumUDF(), lt.udf.SumSigUDF(),
+                           lt.udf.ApplyMasksUDF(mask_factories=lambda: masks)])
+    res = runner.run_for_dataset(ds).buffers
+    assert engine.last_kernel() == 8 and runner.stats.get('int8_passes', 0) == 1
+    flat64 = data.reshape(-1, 4096).astype(np.float64)
+    assert np.array_equal(res[0]['intensity'].raw_data.reshape(-1),
+                          flat64.sum(axis=0).astype(np.float32))
+    assert np.array_equal(res[1]['intensity'].raw_data, flat64.sum(axis=1).astype(np.float32))
+    exact = flat64 @ masks.reshape(4, -1).T.astype(np.float64)
+    got = res[2]['intensity'].raw_data
+    scale = np.abs(exact).max(axis=0)
+    assert (np.abs(got - exact) / scale).max() <= 2e-7          # one float32 rounding
+    close_cols(got, O.apply_masks(data, masks, num_partitions=1))
