@@ -44,13 +44,17 @@ constexpr int K7_DSTAGES = 3;          // gathered data stages (ring size; p.dst
 constexpr int K7_TSTAGES = 3;          // weight-table stages (ring size; p.tstages in use)
 constexpr int K7_QLEN = 8;             // items queued from the gather producers to the table warp
 constexpr int K7_AS = 4;              // TMEM operand ring (sub-tiles)
-#ifndef K7_PWARPS_N
-#define K7_PWARPS_N 4
-#endif
-constexpr int K7_PWARPS = K7_PWARPS_N;   // gather producer warps (multiple of 4: keeps warp % 4 = lane quarter)
+// gather modes (template parameter GM): 0 = cp.async.cg 16 B (4 producer warps), 1 = cp.async.ca
+// (A/B, measured slower), 2 = LDG.128 into registers + STS.128 (8 producer warps, quad plans):
+// scripts/ubench/gather_mix_probe.cu measures 2.0 vs 1.1 copies per clock per SM for 2 vs 0
+// on L2-resident data.  Producer warps come in multiples of 4 (warp % 4 = TMEM lane quarter of
+// the converter / drain warps that follow).
+__host__ __device__ constexpr int k7_pwarps(int gm) { return gm == 2 ? 8 : 4; }
 constexpr int K7_CWARPS = 8;
 constexpr int K7_DWARPS = 4;          // accumulator drain warps, one per TMEM lane quarter
-constexpr int K7_THREADS = (K7_PWARPS + K7_CWARPS + K7_DWARPS + 2) * 32;   // + MMA + table warp
+__host__ __device__ constexpr int k7_threads(int gm) {      // + MMA warp + table warp
+    return (k7_pwarps(gm) + K7_CWARPS + K7_DWARPS + 2) * 32;
+}
 constexpr uint32_t K7_SUB_BYTES = K7_FB * 32 * 4;          // 16 KiB per sub-tile
 constexpr uint32_t K7_DATA_BYTES = 2 * K7_SUB_BYTES;
 constexpr int K7_TMEM_COLS = 512;
@@ -72,7 +76,8 @@ struct K7Params {
     int rgroup;                    // adjacent rings scheduled back to back (L2 sharing)
     int fbgroup;                   // > 0: banded plan, frame blocks per scheduling group
     int n_bands;                   // banded plan: groups = n_bands x n_rings, band-major
-    int prefetch;                  // banded plan: dense L2 prefetch of the next band
+    int prefetch;                  // banded plan: dense L2 prefetch of the next round's data
+    int band_major;                // banded plan: item order [band][frame-block group][ring][fb]
     int quad;                      // entry_px lists QUADS (4 consecutive, 16-byte aligned pixels)
     int64_t sig_size;
 };
@@ -94,6 +99,25 @@ __device__ __forceinline__ void k7_tma_prefetch_2d(const CUtensorMap* map, int32
 // weight-table slices in use at any time stay at rgroup x 4 MB.
 __device__ __forceinline__ void k7_decode_item(const K7Params& p, int64_t item, int& g,
                                                int64_t& fb) {
+    if (p.fbgroup > 0 && p.band_major) {
+        // band outermost: the band's slice of the weight table (table / n_bands) stays
+        // L2-resident for the whole pass over the frame blocks, and at any time the CTAs work on
+        // ONE band of `fbgroup` frame blocks -- a working set small enough for L2, which the
+        // producers prefetch densely one round ahead (see the prefetch in the producer loop)
+        const int n_rings = p.n_groups / p.n_bands;
+        const int64_t per_band = p.n_fb * n_rings;
+        const int64_t b = item / per_band;
+        const int64_t rem = item - b * per_band;
+        const int64_t per = (int64_t)p.fbgroup * n_rings;
+        const int64_t j = rem / per;
+        const int64_t rem2 = rem - j * per;
+        int64_t f_here = p.n_fb - j * p.fbgroup;
+        if (f_here > p.fbgroup) f_here = p.fbgroup;
+        const int64_t ring = rem2 / f_here;
+        g = (int)(b * n_rings + ring);
+        fb = j * p.fbgroup + (rem2 - ring * f_here);
+        return;
+    }
     if (p.fbgroup > 0) {
         // banded plan (groups = (pixel band, ring), band-major): `fbgroup` frame blocks
         // outermost, groups next, the frame blocks of the group innermost.  All CTAs then work
@@ -252,11 +276,26 @@ struct K7QItem {
 // parts of the weights in accumulator columns [0, 64), the differences the IMAGINARY parts in
 // [64, 128): two MMAs of N = 64 per k-step instead of two of N = 112 per pixel pair, and a
 // weight table of 128 rows per orbit instead of 112 per pixel.
-template <int N, bool SYM, bool CA = false>
-__global__ void __launch_bounds__(K7_THREADS, 1)
+__device__ __forceinline__ uint4 k7_ldg128(const void* src) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(src));
+    return v;
+}
+__device__ __forceinline__ void k7_sts128(uint32_t dst, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+template <int N, bool SYM, int GM = 0>
+__global__ void __launch_bounds__(k7_threads(GM), 1)
 k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                        const __grid_constant__ CUtensorMap tm_tile, const K7Params p) {
     constexpr int NMMA = SYM ? 64 : N;    // columns of one MMA
+    constexpr int K7_PWARPS = k7_pwarps(GM);
+    constexpr bool CA = GM == 1;
     using SM = K7Smem<NMMA>;
     constexpr int NHALF = N / 2;          // accumulator columns drained per converter warp
     constexpr int NQ = N / 4;             // real columns per half
@@ -359,17 +398,31 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 int g;
                 k7_decode_item(p, item, g, fb);
                 if (p.prefetch && pt == 0) {
-                    // Optional dense DRAM -> L2 prefetch of the NEXT pixel band of this frame
-                    // block (LTB200_K7_PF=1; measured slower: it competes with the gathers)
+                    // dense DRAM -> L2 prefetch, one round ahead: the items of a round
+                    // (band, frame-block group) share out the NEXT round's data -- item
+                    // (ring r, frame block f of the group) prefetches, for the matching frame
+                    // block of the next round, every n_rings-th 256-pixel box of the band.
+                    // The gathers of the next round then hit L2 (dense 1 KiB rows from DRAM
+                    // instead of scattered 128-byte lines).
                     const int n_rings = p.n_groups / p.n_bands;
-                    int nb = g / n_rings + 1;
+                    int nb = g / n_rings;
                     const int r = g % n_rings;
-                    int64_t pfb = fb;
-                    if (nb == p.n_bands) {
-                        nb = 0;
-                        pfb = fb + p.fbgroup;
+                    int64_t pfb;
+                    if (p.band_major) {
+                        pfb = fb + p.fbgroup;               // same band, next frame-block group
+                        if ((fb / p.fbgroup + 1) * p.fbgroup >= p.n_fb) {
+                            nb += 1;                        // first group of the next band
+                            pfb = fb % p.fbgroup;
+                        }
+                    } else {
+                        nb += 1;                            // next band of the same frame blocks
+                        pfb = fb;
+                        if (nb == p.n_bands) {
+                            nb = 0;
+                            pfb = fb + p.fbgroup;
+                        }
                     }
-                    if (pfb < p.n_fb) {
+                    if (pfb < p.n_fb && nb < p.n_bands) {
                         const int64_t b0 = (p.sig_size * nb) / p.n_bands;
                         const int64_t b1 = (p.sig_size * (nb + 1)) / p.n_bands;
                         for (int64_t x = b0 + (int64_t)r * K7_PF_PX; x < b1;
@@ -427,7 +480,22 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                     const uint32_t d0 = sdst + (uint32_t)qsub * K7_SUB_BYTES + (uint32_t)rg * 128u +
                                         ((uint32_t)(qd ^ (rg & 7)) << 4);
                     const int64_t fr0 = fb * K7_FB + rg;
-                    if (!ragged) {
+                    if constexpr (GM == 2) {
+                        // synchronous gather: all copies of the thread in flight as LDG.128,
+                        // then STS.128 into the swizzled stage; the plain arrive below releases
+                        // the stores to the converters
+                        uint4 v[K7_FB / RS];
+                        const float* src = p.tile + px;
+#pragma unroll
+                        for (int j = 0; j < K7_FB / RS; j++) {
+                            int64_t fr = fr0 + RS * j;
+                            if (ragged && fr >= p.n_frames) fr = p.n_frames - 1;
+                            v[j] = k7_ldg128(src + fr * p.ld_tile);
+                        }
+#pragma unroll
+                        for (int j = 0; j < K7_FB / RS; j++)
+                            k7_sts128(d0 + (uint32_t)j * (RS * 128u), v[j]);
+                    } else if (!ragged) {
                         const float* src = p.tile + px + fr0 * p.ld_tile;
                         const int64_t step = RS * p.ld_tile;
 #pragma unroll 4
@@ -471,7 +539,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                         }
                     }
                 }
-                k7_cp_async_mbar_arrive_noinc(full);
+                if constexpr (GM == 2)
+                    mbar_arrive(full);
+                else
+                    k7_cp_async_mbar_arrive_noinc(full);
             }
             if (done) break;
         }
@@ -749,10 +820,10 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
     }
 }
 
-template <int N, bool SYM, bool CA = false>
+template <int N, bool SYM, int GM = 0>
 static int k7_launch(const CUtensorMap& tm, const CUtensorMap& tmt, const K7Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k7_group_tensor_kernel<N, SYM, CA>;
+    auto kern = k7_group_tensor_kernel<N, SYM, GM>;
     const size_t smem = K7Smem<SYM ? 64 : N>::TOTAL;
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -762,7 +833,7 @@ static int k7_launch(const CUtensorMap& tm, const CUtensorMap& tmt, const K7Para
                                             (int)smem));
         configured_dev = dev;
     }
-    kern<<<grid, K7_THREADS, smem, st>>>(tm, tmt, p);
+    kern<<<grid, k7_threads(GM), smem, st>>>(tm, tmt, p);
     count_launch();
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
@@ -884,13 +955,15 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
                     "group_masks_tc: the quad plan needs 16-byte aligned frame rows");
     p.n_bands = n_bands;
     p.prefetch = 0;
+    p.band_major = 0;
     p.sig_size = sig_size;
     CUtensorMap tmt = tm;
     if (quad) {
         p.fbgroup = 8;
         if (const char* e = getenv("LTB200_K7_FBG"))
             if (atoi(e) > 0) p.fbgroup = atoi(e);
-        int want_pf = 0;   // measured: the dense prefetch competes with the gathers (slower)
+        if (const char* e = getenv("LTB200_K7_BM")) p.band_major = atoi(e) != 0;
+        int want_pf = 0;
         if (const char* e = getenv("LTB200_K7_PF")) want_pf = atoi(e);
         if (want_pf && (uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0 && sig_size >= K7_PF_PX &&
             sig_size < (1ll << 31)) {
@@ -911,11 +984,17 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     }
     int grid = sm_count();
     if (p.n_items < grid) grid = (int)p.n_items;
-    bool gather_ca = false;                 // A/B: quad gather through L1 (cp.async.ca)
-    if (const char* e = getenv("LTB200_K7_CA")) gather_ca = atoi(e) != 0;
-    if (gather_ca && quad && (sym || n == 112)) {
-        rc = sym ? k7_launch<128, true, true>(tm, tmt, p, grid, st)
-                 : k7_launch<112, false, true>(tm, tmt, p, grid, st);
+    int gm = 0;                             // gather mode of the quad plans (see k7_pwarps)
+    if (const char* e = getenv("LTB200_K7_GM")) gm = atoi(e);
+    if (const char* e = getenv("LTB200_K7_CA"))
+        if (atoi(e) != 0) gm = 1;
+    if (gm != 0 && quad && (sym || n == 112)) {
+        if (gm == 2)
+            rc = sym ? k7_launch<128, true, 2>(tm, tmt, p, grid, st)
+                     : k7_launch<112, false, 2>(tm, tmt, p, grid, st);
+        else
+            rc = sym ? k7_launch<128, true, 1>(tm, tmt, p, grid, st)
+                     : k7_launch<112, false, 1>(tm, tmt, p, grid, st);
     } else
     switch (sym ? 128 : n) {
         case 16: rc = k7_launch<16, false>(tm, tmt, p, grid, st); break;
