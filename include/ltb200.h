@@ -161,7 +161,7 @@ LTB_API int ltb200_set_k1_variant(int variant);
  * 1 = TMA-staged kernel (even/odd tile), 3 = TMA-staged kernel (mask-pair tile),
  * 2 = generic kernel, 6 = tcgen05 tensor-core kernel; and for the other entry points:
  * 8 = int8 tensor-core kernel (K8), 20 = sparse CSC kernel (K2), 4 = group-sparse FFMA2
- * kernel (K4), 5 = shifted-mask kernel (K5), 7 / 70 / 71 = group-sparse tensor-core kernel (K7)
+ * kernel (K4), 5 / 50 = shifted-mask kernel (K5, warp-per-frame / banded), 7 / 70 / 71 = group-sparse tensor-core kernel (K7)
  * with the ring-major / quad-banded / mirror-symmetric plan
  * (diagnostics / tests; the nav-space kernels K9 do not change it) */
 LTB_API int ltb200_last_kernel(void);
@@ -187,6 +187,22 @@ LTB_API int ltb200_masks_shifted(const void* tile, int tile_dtype, int64_t n_fra
                                  int sig_x, int64_t ld_tile, const float* masks, int n_masks,
                                  int64_t ld_masks, const int32_t* shifts, int per_frame,
                                  float* out, int64_t ld_out, int accumulate, void* stream);
+/* Banded form for float32 results (the default when it applies).  The frames are visited in
+ * the order `order` (device, n_frames int32: a permutation that sorts the frames by dy; the
+ * identity for per_frame == 0), in chunks of 256: a block keeps the row band of 4 or 8 masks a
+ * chunk needs -- the band's frame rows widened by the chunk's dy span -- in <= 48 KiB of shared
+ * memory and streams the chunk through it.  max_span: the largest (dy_last - dy_first) over the
+ * chunks of 256 consecutive entries of `order` (the caller sorted, so it knows).  Band partial
+ * sums go to `workspace` (ltb200_masks_shifted_banded_workspace bytes; 0 = no band plan for
+ * this geometry, use ltb200_masks_shifted) and are added in band order (deterministic). */
+LTB_API size_t ltb200_masks_shifted_banded_workspace(int64_t n_frames, int sig_y, int sig_x,
+                                                     int n_masks, int max_span);
+LTB_API int ltb200_masks_shifted_banded(const void* tile, int tile_dtype, int64_t n_frames,
+                                        int sig_y, int sig_x, int64_t ld_tile, const float* masks,
+                                        int n_masks, int64_t ld_masks, const int32_t* shifts,
+                                        int per_frame, const int32_t* order, int max_span,
+                                        float* out, int64_t ld_out, int accumulate,
+                                        void* workspace, size_t workspace_bytes, void* stream);
 /* float64 masks / accumulation / result: the reference's dtype rule for float64 masks or frames
  * (result_type(input, mask), udf/masks.py:360-368); tile dtypes f32, f64, u8, u16, i16, i32 */
 LTB_API int ltb200_masks_shifted_f64(const void* tile, int tile_dtype, int64_t n_frames, int sig_y,

@@ -37,6 +37,9 @@ SIGNATURES = {
                                 _int, _vp]),
     'ltb200_masks_shifted': (_int, [_vp, _int, _i64, _int, _int, _i64, _vp, _int, _i64, _vp, _int,
                                     _vp, _i64, _int, _vp]),
+    'ltb200_masks_shifted_banded_workspace': (_sz, [_i64, _int, _int, _int, _int]),
+    'ltb200_masks_shifted_banded': (_int, [_vp, _int, _i64, _int, _int, _i64, _vp, _int, _i64, _vp,
+                                           _int, _vp, _int, _vp, _i64, _int, _vp, _sz, _vp]),
     'ltb200_masks_shifted_f64': (_int, [_vp, _int, _i64, _int, _int, _i64, _vp, _int, _i64, _vp,
                                         _int, _vp, _i64, _int, _vp]),
     'ltb200_group_masks_workspace': (_sz, []),

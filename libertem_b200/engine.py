@@ -258,9 +258,12 @@ def set_k1_variant(variant):
     check(get_lib().ltb200_set_k1_variant(int(variant)))
 
 
-def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
+def masks_shifted(tile, masks, shifts, out=None, accumulate=False, banded=None):
     """per-frame shifted masks: tile (F, sy, sx), masks (M, sy*sx) float32 or float64 (-> float64
-    accumulation and result), shifts int32 (F, 2) or (1, 2) (dy, dx) -> out (F, M)"""
+    accumulation and result), shifts int32 (F, 2) or (1, 2) (dy, dx) -> out (F, M).
+    ``banded``: None = automatic (float32 results, >= 64 frames, host-side shifts: the frames
+    are sorted by dy and streamed through a shared-memory band of the masks), False = the
+    warp-per-frame kernel."""
     lib = get_lib()
     _require_cuda(tile, 'tile')
     _require_cuda(masks, 'masks')
@@ -271,6 +274,12 @@ def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
     if masks.dtype not in (torch.float32, torch.float64):
         raise TypeError(f'masks must be float32 or float64, got {masks.dtype}')
     f64 = masks.dtype == torch.float64
+    host_shifts = None
+    if isinstance(shifts, np.ndarray):
+        host_shifts = np.ascontiguousarray(shifts, dtype=np.int32).reshape(-1, 2)
+        shifts = torch.from_numpy(host_shifts)
+    elif not shifts.is_cuda:
+        host_shifts = shifts.to(torch.int32).contiguous().numpy().reshape(-1, 2)
     shifts = shifts.to(device=tile.device, dtype=torch.int32).contiguous()
     per_frame = int(shifts.shape[0] != 1)
     if per_frame and shifts.shape[0] != F:
@@ -281,6 +290,32 @@ def masks_shifted(tile, masks, shifts, out=None, accumulate=False):
     elif out.dtype != masks.dtype or (M > 1 and out.stride(1) != 1):
         raise ValueError('out must have the dtype of the masks and unit inner stride')
     ld_out = out.stride(0) if F > 1 else max(M, 1)
+    want_banded = (banded is not False and not f64 and host_shifts is not None and F >= 64
+                   and M > 0 and tile.dtype in (torch.float32, torch.uint16, torch.uint8,
+                                                torch.int16))
+    if want_banded:
+        # sort the frames by dy: a chunk of 256 consecutive frames then spans few mask rows
+        if per_frame:
+            order = np.argsort(host_shifts[:, 0], kind='stable').astype(np.int32)
+            dys = host_shifts[order, 0]
+            starts = np.arange(0, F, 256)
+            ends = np.minimum(starts + 256, F) - 1
+            max_span = int((dys[ends] - dys[starts]).max())
+        else:
+            order = np.arange(F, dtype=np.int32)
+            max_span = 0
+        need = lib.ltb200_masks_shifted_banded_workspace(F, sy, sx, M, max_span)
+        if need:
+            ws = _workspace(tile.device, need)
+            order_t = torch.from_numpy(order).to(tile.device)
+            with torch.cuda.device(tile.device):
+                check(lib.ltb200_masks_shifted_banded(
+                    tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, sy, sx, sy * sx,
+                    masks.data_ptr(), M, masks.shape[1], shifts.data_ptr(), per_frame,
+                    order_t.data_ptr(), max_span, out.data_ptr(), ld_out,
+                    int(bool(accumulate)), ws.data_ptr(), ws.numel(),
+                    _stream_ptr(tile.device)))
+            return out
     fn = lib.ltb200_masks_shifted_f64 if f64 else lib.ltb200_masks_shifted
     with torch.cuda.device(tile.device):
         check(fn(tile.data_ptr(), _TORCH_DTYPES[tile.dtype], F, sy, sx, sy * sx, masks.data_ptr(),

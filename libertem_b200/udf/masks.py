@@ -269,7 +269,7 @@ class ApplyMasksUDF(UDF):
             out = torch.view_as_real(view).reshape(view.shape[0], -1)
         if out.dtype != rows.dtype or (out.shape[1] > 1 and out.stride(1) != 1):
             return False
-        sh = torch.from_numpy(np.ascontiguousarray(shifts, dtype=np.int32).reshape(-1, 2))
+        sh = np.ascontiguousarray(shifts, dtype=np.int32).reshape(-1, 2)
         engine.masks_shifted(tile, rows, sh, out=out, accumulate=True)
         return True
 

@@ -64,10 +64,16 @@ del data, out
 F, sy, sx, NM = 16384, 256, 256, 8
 tile = engine.synth_fill((F, sy, sx), np.float32, 5, dev)
 masks = engine.synth_fill((NM, sy * sx), np.float32, 6, dev)
-sh = (torch.randint(-12, 13, (F, 2), device=dev, dtype=torch.int32))
+sh = (torch.randint(-12, 13, (F, 2), device=dev, dtype=torch.int32))   # device shifts: warp-per-frame kernel
 out = torch.zeros((F, NM), dtype=torch.float32, device=dev)
 ms = timed(lambda: engine.masks_shifted(tile, masks, sh, out=out))
 line('K5 shifted: 16384 x 256x256 f32, 8 masks, per-frame (dy, dx) in [-12, 12]', F * sy * sx * 4, ms)
+for nm, dmax in ((8, 12), (8, 4), (3, 12), (3, 4), (4, 2)):
+    shd = torch.randint(-dmax, dmax + 1, (F, 2), dtype=torch.int32)        # host shifts: banded
+    o = torch.zeros((F, nm), dtype=torch.float32, device=dev)
+    ms = timed(lambda: engine.masks_shifted(tile, masks[:nm], shd, out=o))
+    line('K5 banded: same frames, %d masks, |dy|,|dx| <= %d' % (nm, dmax), F * sy * sx * 4, ms,
+         kernel=engine.last_kernel())
 out3 = torch.zeros((F, 3), dtype=torch.float32, device=dev)
 ms = timed(lambda: engine.masks_shifted(tile, masks[:3], sh, out=out3))
 line('K5 shifted: same, 3 masks', F * sy * sx * 4, ms)

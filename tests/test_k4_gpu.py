@@ -196,3 +196,41 @@ def test_masks_shifted_kernel(dt):
     const = engine.masks_shifted(t, torch.from_numpy(masks.reshape(M, -1)).cuda(),
                                  torch.tensor([[3, -7]])).cpu().numpy()
     assert np.abs(const - _shifted_ref(data, masks, [(3, -7)])).max() / scale <= 2e-6
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.uint16])
+@pytest.mark.parametrize('M,D', [(3, 4), (8, 15), (11, 2), (6, 40)])
+def test_masks_shifted_banded_kernel(dt, M, D):
+    """K5 banded form (mask row band + |dy| halo in shared memory, band partial sums): same
+    numbers as the float64 evaluation of the reference's shifted-mask semantics
+    (udf/masks.py:85-124), incl. frames without overlap, accumulate and ragged frame chunks"""
+    from libertem_b200 import engine
+    F, sy, sx = 300, 48, 40
+    if dt == np.float32:
+        data = synth.uniform_f32(0, F * sy * sx, 5).reshape(F, sy, sx)
+        t = torch.from_numpy(data).cuda()
+    else:
+        data = synth.poisson3_u16(0, F * sy * sx, 5).reshape(F, sy, sx)
+        t = torch.from_numpy(data.view(np.int16)).cuda().view(torch.uint16)
+    masks = synth.uniform_f32(0, M * sy * sx, 6).reshape(M, sy, sx) - 0.3
+    sh = (synth.hash_u32(0, 2 * F, 7) % (2 * D + 1)).astype(np.int64).reshape(F, 2) - D
+    sh[:, 1] = (synth.hash_u32(0, F, 8) % 61).astype(np.int64) - 30      # dx: unrestricted
+    sh[0] = (0, 0)
+    sh[1] = (D, 100)         # no overlap in x
+    sh[2] = (-D, sx - 1)     # single column
+    mt = torch.from_numpy(masks.reshape(M, -1)).cuda()
+    out = engine.masks_shifted(t, mt, torch.from_numpy(sh)).cpu().numpy()
+    assert engine.last_kernel() == 50
+    ref = _shifted_ref(data, masks, sh)
+    scale = np.abs(ref).max() + 1e-30
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    assert np.all(out[1] == 0)
+    generic = engine.masks_shifted(t, mt, torch.from_numpy(sh), banded=False).cpu().numpy()
+    assert engine.last_kernel() == 5
+    assert np.abs(out - generic).max() / scale <= 2e-6
+    acc = torch.from_numpy(out).cuda()
+    engine.masks_shifted(t, mt, torch.from_numpy(sh), out=acc, accumulate=True)
+    assert np.abs(acc.cpu().numpy() - 2 * ref).max() / scale <= 4e-6
+    const = engine.masks_shifted(t, mt, torch.tensor([[3, -7]])).cpu().numpy()
+    assert engine.last_kernel() == 50
+    assert np.abs(const - _shifted_ref(data, masks, [(3, -7)])).max() / scale <= 2e-6
