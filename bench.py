@@ -597,7 +597,7 @@ def config_legs(ctx):
         free, _total = torch.cuda.mem_get_info(device)
         nav0 = 256 if free > (80 << 30) else 32
         shape = (nav0, 256, 512, 512)
-        ds = SyntheticDataSet(shape, np.float32, seed=104, num_partitions=8)
+        ds = SyntheticDataSet(shape, np.float32, seed=104, num_partitions=1)
         a = Context().create_radial_fourier_analysis(ds, n_bins=32)
         udf = a.get_udf()
         runner = UDFRunner([udf])
@@ -621,7 +621,7 @@ def config_legs(ctx):
             worst = max(worst, float((np.abs(got - ref).reshape(16, 32, 25) / scale).max()))
         line.update(parity_max_rel_err=worst, parity_ok=bool(worst <= PARITY_TOL),
                     workload='cfg4: %dx256 nav x 512x512 sig float32%s, RadialFourierAnalysis 32 '
-                             'bins x 25 orders (800 complex masks), 8 partitions' %
+                             'bins x 25 orders (800 complex masks), one partition' %
                              (nav0, '' if nav0 == 256 else ' (nav sub-sample: not enough HBM)'),
                     bound='tensor / L2->SM fabric (group-sparse GEMM), reported against the HBM '
                           'roofline of the frame bytes')

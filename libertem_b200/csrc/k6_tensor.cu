@@ -405,9 +405,31 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
             const int n_dsub = (int)((k1 - k0 + PX - 1) / PX);
             const int n_sub = n_dsub * HALVES;
 
+            // Chain totals are summed in float32 registers (round to nearest).  Adding thousands
+            // of them into ONE running sum is what dominated this kernel's rounding error
+            // (1.4e-6 of sum|x||m| for a 256x256 signal, measured and emulated); with <= 16
+            // columns there are registers for a second level: `acc` collects 32 chains, then
+            // moves into `acc_hi` (3-4e-7, the level of the reference's blocked sgemm).
+            constexpr bool TWO_LEVEL = (NH <= 16 && HALVES == 1) || NH <= 8;   // (uint16 form: 128 regs)
             float acc[NH];
+            float acc_hi[TWO_LEVEL ? NH : 1];
 #pragma unroll
             for (int c = 0; c < NH; c++) acc[c] = 0.f;
+#pragma unroll
+            for (int c = 0; c < (TWO_LEVEL ? NH : 1); c++) acc_hi[c] = 0.f;
+            int in_block = 0;                        // chains collected in `acc` (TWO_LEVEL)
+            auto level_up = [&]() {
+                if constexpr (TWO_LEVEL) {
+                    if (++in_block == 32) {
+                        in_block = 0;
+#pragma unroll
+                        for (int c = 0; c < NH; c++) {
+                            acc_hi[c] += acc[c];
+                            acc[c] = 0.f;
+                        }
+                    }
+                }
+            };
             int next_chain = 0;                      // first chain not yet drained
             auto chain_end = [&](int c) {
                 const int e = (c + 1) * chain;
@@ -428,6 +450,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     for (int c = 0; c < NH; c++)
                         acc[c] += __uint_as_float(v[c / 16][c % 16]) +
                                   __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
+                    level_up();
                     next_chain++;
                 }
             };
@@ -529,6 +552,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                         for (int c = 0; c < NH; c++)
                             acc[c] += __uint_as_float(v[c / 16][c % 16]) +
                                       __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
+                        level_up();
                     }
                     tc_wait_st();
                     tc_fence_before();
@@ -547,6 +571,10 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
             tc_fence_after();
             if (!(p.debug & 4)) drain_upto(n_sub - 1);
             tc_fence_before();
+            if constexpr (TWO_LEVEL) {
+#pragma unroll
+                for (int c = 0; c < NH; c++) acc[c] += acc_hi[c];
+            }
 
             const int64_t f = fb * K6_FB + row;
             if (f < p.n_frames) {
