@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import walk_plan
 from ._lib import get_lib, check
 
 KT = 128          # entries per pipeline stage (K4_KT)
@@ -67,6 +68,16 @@ class GroupPlan:
         self._band_ws = None
         #: opt-in mirror-symmetric plan (dict(main=..., rest=...)) or None
         self.sym = None
+        #: dense-walk plan of K10 (device tensors of walk_plan.build_walk) or None
+        self.walk = None
+        self._walk_ws = None
+
+    def walk_workspace(self, n_frames, accumulate):
+        need = get_lib().ltb200_group_masks_walk_workspace(
+            n_frames, self.n_groups, self.n_pairs, int(bool(accumulate)))
+        if self._walk_ws is None or self._walk_ws.numel() < need:
+            self._walk_ws = torch.zeros(need, dtype=torch.uint8, device=self.entry_px.device)
+        return self._walk_ws
 
     def band_workspace(self, n_frames, which=None):
         which = self.banded if which is None else which
@@ -112,6 +123,8 @@ TC_KT = 64                        # entries per stage of the tensor-core kernel 
 #: gather / L2->SM fabric, not by the tensor work or the table bytes the symmetry saves, so it
 #: stays opt-in (build_plan(sym=True) or LTB200_K7_SYM=1); the banded plan is the default.
 SYM_PATH = os.environ.get('LTB200_K7_SYM', '0') == '1'
+#: dense-walk plan (K10): the default for stacks it accepts; LTB200_K10=0 restores K7 for A/B
+WALK_PATH = os.environ.get('LTB200_K10', '1') != '0'
 #: frame-stream bytes of one band of one 128-frame block aimed at by the band count (a handful
 #: of frame blocks x this must stay L2-resident together with the band's weight-table slices)
 BAND_TARGET_BYTES = 32 << 20
@@ -245,7 +258,8 @@ def build_sym(stack3, group_size, n_bands):
                 group_off=np.array(offs, dtype=np.int32), residual=residual)
 
 
-def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None):
+def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None,
+               walk_max_dup=1.5):
     """stack: complex (M, *sig) dense array with M = n_groups * group_size (``sig_shape`` gives
     the 2D signal shape when the stack comes flattened)"""
     M = stack.shape[0]
@@ -296,6 +310,17 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
                           group_off_dev=torch.from_numpy(b['group_off']).to(device))
     plan = GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
                      group_size, M, device, table_split=split, n_cols=n_cols, banded=banded)
+    if WALK_PATH and n_cols and n_groups > 0:
+        w = walk_plan.build_walk(flat, group_size, max_dup=walk_max_dup)
+        if w is not None:
+            plan.walk = dict(
+                n_segments=w['n_segments'], n_entries=w['n_entries'],
+                boxes=torch.from_numpy(w['boxes'].view(np.int32)).to(device),
+                ops=torch.from_numpy(w['ops'].view(np.int32)).to(device),
+                events=torch.from_numpy(w['events'].view(np.int32)).to(device),
+                table=torch.from_numpy(w['table']).to(device),
+                seg_off_host=np.ascontiguousarray(
+                    np.stack([w['visit_off'], w['op_off'], w['ev_off']]), dtype=np.int32))
     if (SYM_PATH if sym is None else sym) and banded is not None and len(sig_shape) == 2:
         plan.sym = _sym_to_device(flat, sig_shape, group_size, max(1, n_bands // 2), n_cols,
                                   device)
@@ -327,8 +352,9 @@ TC_MIN_FRAMES = 96
 def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     """out (F, n_masks) complex64 (+)= group-sparse contraction of the float32 tile.
 
-    kernel: 'auto' (tensor cores, K7, from TC_MIN_FRAMES frames: the quad / banded plan for
-    16-byte aligned frame rows, else the 4-byte ring-major gather), 'tc' (K7, 4-byte gather,
+    kernel: 'auto' (tensor cores from TC_MIN_FRAMES frames: the dense-walk kernel K10 when the
+    stack has such a plan and the frame rows are 16-byte aligned, else K7 with the quad / banded
+    plan, else K7's 4-byte ring-major gather), 'walk' (K10), 'tc' (K7, 4-byte gather,
     ring-major), 'banded' (K7, quad gather, banded schedule) or 'ffma' (K4)"""
     lib = get_lib()
     if not tile.is_cuda:
@@ -344,9 +370,9 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     real = torch.view_as_real(out).reshape(F, 2 * plan.n_masks)
     ld_tile = tile.stride(0) if F > 1 else max(K, 1)
     ld_out = real.stride(0) if F > 1 else max(2 * plan.n_masks, 1)
-    use_tc = kernel in ('tc', 'banded', 'sym') or (kernel == 'auto' and F >= TC_MIN_FRAMES)
+    use_tc = kernel in ('tc', 'banded', 'sym', 'walk') or (kernel == 'auto' and F >= TC_MIN_FRAMES)
     if use_tc and plan.table_split is None:
-        if kernel in ('tc', 'banded', 'sym'):
+        if kernel in ('tc', 'banded', 'sym', 'walk'):
             raise _lib.LTB200Error('no tensor-core table for this plan')
         use_tc = False
     if kernel == 'banded' and plan.banded is None:
@@ -354,6 +380,21 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
     aligned = tile.data_ptr() % 16 == 0 and ld_tile % 4 == 0
     if kernel == 'banded' and not aligned:
         raise _lib.LTB200Error('the banded plan needs 16-byte aligned frame rows')
+    if kernel == 'walk' and (plan.walk is None or not aligned):
+        raise _lib.LTB200Error('no dense-walk plan for this stack / tile (sig_size % 32, 16-byte '
+                               'aligned frame rows)')
+    if use_tc and plan.walk is not None and aligned and (
+            kernel == 'walk' or (kernel == 'auto' and plan.sym is None)):
+        w = plan.walk
+        ws = plan.walk_workspace(F, accumulate)
+        with torch.cuda.device(tile.device):
+            check(lib.ltb200_group_masks_walk(
+                tile.data_ptr(), F, K, ld_tile, w['boxes'].data_ptr(), w['ops'].data_ptr(),
+                w['events'].data_ptr(), w['table'].data_ptr(), w['seg_off_host'].ctypes.data,
+                w['n_segments'], plan.n_groups, plan.n_pairs, real.data_ptr(), ld_out,
+                int(bool(accumulate)), ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream(tile.device).cuda_stream))
+        return out
     if kernel == 'sym' and plan.sym is None:
         raise _lib.LTB200Error('no mirror-symmetric plan (build_plan(sym=True) and a symmetric stack)')
     if use_tc and plan.sym is not None and aligned and kernel in ('sym', 'auto'):

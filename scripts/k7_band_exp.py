@@ -1,5 +1,5 @@
 """K7 on the cfg4 geometry, ring-major vs banded schedule.
-    python scripts/k7_band_exp.py <n_bands> <kernel tc|banded|sym> [frames] [ncu]
+    python scripts/k7_band_exp.py <n_bands> <kernel tc|banded|sym|walk> [frames] [ncu]
 (sym: the experimental mirror-symmetric plan, needs LTB200_K7_SYM=1)"""
 import os
 import sys
@@ -23,7 +23,7 @@ def main():
     fac = radial_mask_factory(512, 512, 256, 256, 0, 364.0, 32, 24, use_sparse=False)
     stack = np.asarray(fac()).reshape(800, -1)
     plan = gm.build_plan(stack, 25, dev, n_bands=n_bands, sig_shape=(512, 512))
-    n_ent = (plan.n_entries if kernel == 'tc' else
+    n_ent = (plan.n_entries if kernel == 'tc' else plan.walk['n_entries'] if kernel == 'walk' else
              int((plan.sym['main'] if kernel == 'sym' else plan.banded)['group_off_host'][-1]))
     data = engine.synth_fill((F, 512 * 512), np.float32, 104, dev)
     out = gm.group_masks(data, plan, kernel=kernel)
