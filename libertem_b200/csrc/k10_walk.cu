@@ -15,21 +15,21 @@
 // follows static lists that are the same for every block of 128 frames.
 //
 // 20 warps:
-//   * warps 0..7   converters: thread <-> frame row (TMEM lane); slices alternate between the
-//     two sets of 4 warps: two LDS.128 of the row's 32 bytes, hi/lo split (hi = top 19 bits,
-//     lo = x - hi rounded to TF32), tcgen05.st of both into a ring of 8 A-operand slots;
+//   * warps 0..7   converters: thread <-> frame row (TMEM lane); the slices of a box alternate
+//     between the two sets of 4 warps: two LDS.128 of the row's 32 bytes, hi/lo split (hi = top
+//     19 bits, lo = x - hi rounded to TF32), tcgen05.st of both into the box's A-operand stage
+//     (two stages of 4 slices x (hi 8 | lo 8) columns);
 //   * warps 8..15  accumulator drain: chain totals (TMEM) -> float32 registers; groups of even
 //     / odd id go to warps 8..11 / 12..15, each thread keeps two groups (window of 4); the last
 //     chain of a group writes the result row;
 //   * warp 16      box producer (TMA, frame stream, evict_first) + work-item fetch;
 //   * warp 17      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops (the table
 //     is stored as the byte image of the swizzled stage);
-//   * warp 18      MMA issuer: per op three tcgen05.mma.kind::tf32 of M 128, N 64, K 8 into the
-//     op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi; the table rows are
-//     [hi(0..55) | lo(0..55)], the lo product reads rows 56..119);
-//   * warp 19      idle.
+//   * warps 18, 19 MMA issuers (even / odd groups): per op three tcgen05.mma.kind::tf32 of
+//     M 128, N 64, K 8 into the op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi;
+//     the table rows are [hi(0..55) | lo(0..55)], the lo product reads rows 56..119).
 // TMEM: 6 accumulator buffers of 64 columns (pool; chains of <= 8 ops, the float32 accumulate
-// of the tensor core truncates -- see k6_tensor.cu) + 8 A slots of (hi 8 | lo 8) columns.
+// of the tensor core truncates -- see k6_tensor.cu) + 2 A stages of 4 x (hi 8 | lo 8) columns.
 #include "common.cuh"
 #include <cstdlib>
 
@@ -42,7 +42,7 @@ constexpr int K10_HR = 56;                       // weight rows per half
 constexpr uint32_t K10_TAB_BYTES = 2 * K10_HR * 128;        // 14 KiB copied per stage
 constexpr uint32_t K10_TAB_STRIDE = K10_TAB_BYTES + 1024;   // + 8 zero rows (rows 112..119)
 constexpr int K10_TSTAGES = 7;
-constexpr int K10_AS = 8;                        // A-operand slots
+constexpr int K10_AS = 2;                        // A-operand stages: 4 slices x (hi 8 | lo 8)
 constexpr int K10_NBUF = 6;                      // accumulator buffers
 constexpr int K10_ACC_COLS = 64;
 constexpr int K10_A_BASE = K10_NBUF * K10_ACC_COLS;   // 384
@@ -52,7 +52,11 @@ constexpr int K10_THREADS = 640;
 constexpr int K10_TMEM_COLS = 512;
 
 constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4, K10_OP_NEW = 1u << 5,
-                   K10_OP_END = 1u << 6, K10_OP_NOP = 1u << 7;
+                   K10_OP_END = 1u << 6, K10_OP_NOP = 1u << 7;   // NEW / END: first / last op of a box
+constexpr int K10_OP_SLICE_SHIFT = 8;            // bits 8-9: slice of the box
+constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: parity of the buffer's use count
+constexpr int K10_OP_OWNER_SHIFT = 11;           // group parity = owning MMA warp
+constexpr int K10_EV_PARITY_SHIFT = 5;
 constexpr uint32_t K10_EV_SLOT = 1u << 3, K10_EV_LAST = 1u << 4;
 
 struct K10Params {
@@ -111,6 +115,17 @@ __device__ __forceinline__ void k10_mma(uint32_t d_tmem, uint32_t a_tmem, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same with the descriptor given as its two 32-bit halves (the low half is a running value)
+__device__ __forceinline__ void k10_mma2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void k10_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -209,7 +224,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    constexpr int DRAIN_WARP0 = 8, DATA_WARP = 16, TABLE_WARP = 17, MMA_WARP = 18;
+    constexpr int DRAIN_WARP0 = 8, DATA_WARP = 16, TABLE_WARP = 17, MMA_WARP = 18;   // + 19
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K10_DSTAGES; s++) {
@@ -218,11 +233,11 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         }
         for (int s = 0; s < K10_TSTAGES; s++) {
             mbar_init(&tab_full[s], 1);
-            mbar_init(&tab_free[s], 1);
+            mbar_init(&tab_free[s], 2);                // both MMA warps
         }
         for (int s = 0; s < K10_AS; s++) {
-            mbar_init(&a_full[s], 4);                  // the 4 warps of a converter set
-            mbar_init(&mma_done[s], 1);
+            mbar_init(&a_full[s], 8);                  // converter warps
+            mbar_init(&mma_done[s], 2);                // both MMA warps
         }
         for (int s = 0; s < K10_NBUF; s++) {
             mbar_init(&acc_full[s], 1);
@@ -230,7 +245,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         }
         for (int s = 0; s < K10_QLEN; s++) {
             mbar_init(&q_full[s], 1);
-            mbar_init(&q_free[s], 10);                 // table warp, MMA warp, 8 drain warps
+            mbar_init(&q_free[s], 11);                 // table warp, 2 MMA warps, 8 drain warps
         }
         fence_mbar_init();
     }
@@ -263,20 +278,21 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         const uint32_t row_off = (uint32_t)row * 128u;
         int stage = 0;
         uint32_t dphase = 0;
-        uint32_t k = 0;                                 // slices seen so far (both sets)
+        uint32_t nbox = 0;                              // boxes seen so far
         for (;;) {
             mbar_wait(&data_full[stage], dphase);
             const int m = meta[stage];
             if (m < 0) break;
             const uint8_t* dbase = smem + (size_t)stage * K10_BOX_BYTES + row_off;
-            // this set's slices of the box (at most 2 of the 4): load, then release the stage
+            // the used slices of a box alternate between the two sets (at most 2 of the 4 each):
+            // load, release the stage, then convert
             float4 x[2][2];
-            uint32_t kk[2];
-            int n_mine = 0;
+            int jj[2];
+            int n_mine = 0, c = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if ((m >> j) & 1) {
-                    if ((int)(k & 1) == set) {
+                    if ((c & 1) == set) {
                         const float4 v0 = *reinterpret_cast<const float4*>(
                             dbase + (((uint32_t)(2 * j) ^ swz) << 4));
                         const float4 v1 = *reinterpret_cast<const float4*>(
@@ -284,15 +300,15 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                         if (n_mine == 0) {
                             x[0][0] = v0;
                             x[0][1] = v1;
-                            kk[0] = k;
+                            jj[0] = j;
                         } else {
                             x[1][0] = v0;
                             x[1][1] = v1;
-                            kk[1] = k;
+                            jj[1] = j;
                         }
                         n_mine++;
                     }
-                    k++;
+                    c++;
                 }
             }
 #pragma unroll
@@ -308,6 +324,10 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 stage = 0;
                 dphase ^= 1;
             }
+            // the A stage of this box is free once the MMAs of the box two back have completed
+            const uint32_t ast = nbox & 1u;
+            mbar_wait(&mma_done[ast], ((nbox >> 1) & 1u) ^ 1u);
+            k10_fence_after();
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 if (s < n_mine) {
@@ -322,19 +342,17 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                             lo[h * 4 + t] = __float_as_uint(e[t] - __uint_as_float(hb)) + 0x1000u;
                         }
                     }
-                    const uint32_t slot = kk[s] & (K10_AS - 1);
-                    // the slot is free once the MMAs of the slice K10_AS back have completed
-                    mbar_wait(&mma_done[slot], ((kk[s] >> 3) & 1) ^ 1);
-                    k10_fence_after();
-                    const uint32_t a = tmem_base + lane_sel + (uint32_t)(K10_A_BASE + slot * 16);
+                    const uint32_t a =
+                        tmem_base + lane_sel + (uint32_t)(K10_A_BASE + ast * 64 + jj[s] * 16);
                     k10_st8(a, hi);
                     k10_st8(a + 8, lo);
-                    k10_wait_st();
-                    k10_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[slot]);
                 }
             }
+            k10_wait_st();
+            k10_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[ast]);
+            nbox++;
         }
     } else if (warp < DATA_WARP) {
         // ===== accumulator drain =====
@@ -349,7 +367,6 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         for (int s = 0; s < 2; s++)
 #pragma unroll
             for (int c = 0; c < K10_HR; c++) acc[s][c] = 0.f;
-        uint32_t duse = 0;
         for (uint32_t qn = 0;; qn++) {
             const int q = qn % K10_QLEN;
             mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
@@ -369,11 +386,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     const uint32_t ev = __shfl_sync(0xffffffffu, w, j);
                     const uint32_t buf = ev & 7u;
                     const uint32_t g = ev >> 8;
-                    if ((int)(g & 1u) != grp) {
-                        duse ^= 1u << buf;             // the other group's chain
-                        continue;
-                    }
-                    mbar_wait(&acc_full[buf], (duse >> buf) & 1u);
+                    if ((int)(g & 1u) != grp) continue;     // the other group's chain
+                    // (every buffer is used an even number of times per segment: static parity)
+                    mbar_wait(&acc_full[buf], (ev >> K10_EV_PARITY_SHIFT) & 1u);
                     k10_fence_after();
                     const uint32_t d = tmem_base + lane_sel + buf * K10_ACC_COLS;
                     const bool slot1 = (ev & K10_EV_SLOT) != 0;
@@ -409,7 +424,6 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     k10_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_free[buf]);
-                    duse ^= 1u << buf;
                     if (ev & K10_EV_LAST) {
                         // the group's sum over this segment is complete: write the row
                         float* o = p.out + f * p.ld_out + (int64_t)g * p.n_cols;
@@ -505,11 +519,24 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     }
                 }
             }
-        } else if (warp == MMA_WARP) {
-            // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        } else {
+            // ===== MMA issuers (warp-uniform loops, one elected lane issues) =====
+            // Two warps: warp 18 issues the ops of the even groups, warp 19 those of the odd
+            // groups (disjoint accumulator buffers, so the two instruction streams need no
+            // ordering); both walk the whole op list and both commit onto the barriers that
+            // release an A stage / a table stage.  One op = 96 tensor-pipe cycles, one warp
+            // cannot decode and issue an op in that time (profiles/r2_k10_*): everything an op
+            // needs is a shift / mask of its word, the descriptors are running 32-bit halves,
+            // four ops (one table stage) per unrolled round.
+            const uint32_t me = (uint32_t)(warp - MMA_WARP);
             constexpr uint32_t IDESC = k10_idesc_tf32(K10_ACC_COLS);
+            const uint32_t tb0 = smem_u32(smem + K10Smem::TABLE_OFF);
+            const uint32_t desc_hi32 = (uint32_t)(k10_desc_k_sw128(0) >> 32);
+            const uint32_t desc_lo0 = (uint32_t)k10_desc_k_sw128(tb0);
+            constexpr uint32_t DESC_STAGE = K10_TAB_STRIDE >> 4, DESC_LO_HALF = (K10_HR * 128) >> 4;
+            uint32_t desc_lo = desc_lo0;                // table stage `ts`, rows 0.., op 0
             int ts = 0;
-            uint32_t tphase = 0, cuse = 0, ka = 0;      // ka: slices consumed
+            uint32_t tphase = 0, ast = 0, aphase = 0;
             for (uint32_t qn = 0;; qn++) {
                 const int q = qn % K10_QLEN;
                 mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
@@ -523,47 +550,51 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     const uint32_t w = w_next;
                     if (base + 32 < o1)
                         w_next = base + 32 + lane < o1 ? p.ops[base + 32 + lane] : K10_OP_NOP;
-                    const int n = o1 - base < 32 ? o1 - base : 32;
-                    for (int j = 0; j < n; j++) {
-                        const uint32_t op = __shfl_sync(0xffffffffu, w, j);
-                        const int sub = j & 3;                  // base is a multiple of 4
-                        if (sub == 0) mbar_wait(&tab_full[ts], tphase);
-                        const bool nop = (op & K10_OP_NOP) != 0;
-                        const uint32_t buf = op & 7u;
-                        const uint32_t as = ka & (K10_AS - 1);
-                        if (!nop) {
-                            if (op & K10_OP_NEW) mbar_wait(&a_full[as], (ka >> 3) & 1u);
-                            if (op & K10_OP_FIRST)
-                                mbar_wait(&acc_free[buf], ((cuse >> buf) & 1u) ^ 1u);
-                        }
-                        k10_fence_after();
-                        if (k10_elect_one()) {
-                            if (!nop) {
-                                const uint32_t tb = smem_u32(smem + K10Smem::TABLE_OFF +
-                                                             (size_t)ts * K10_TAB_STRIDE);
-                                const uint64_t b_hi = k10_desc_k_sw128(tb) + (uint64_t)(sub * 2);
-                                const uint64_t b_lo =
-                                    k10_desc_k_sw128(tb + K10_HR * 128u) + (uint64_t)(sub * 2);
-                                const uint32_t a_hi = tmem_base + (uint32_t)(K10_A_BASE + as * 16);
-                                const uint32_t d = tmem_base + buf * K10_ACC_COLS;
-                                k10_mma(d, a_hi, b_hi, IDESC, (op & K10_OP_FIRST) ? 0u : 1u);
-                                k10_mma(d, a_hi, b_lo, IDESC, 1u);
-                                k10_mma(d, a_hi + 8, b_hi, IDESC, 1u);
-                                if (op & K10_OP_END) k10_commit(&mma_done[as]);
-                                if (op & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
+                    const int n = o1 - base < 32 ? o1 - base : 32;      // a multiple of 4
+                    uint32_t op_next = __shfl_sync(0xffffffffu, w, 0);
+                    for (int j = 0; j < n; j += 4) {
+                        mbar_wait(&tab_full[ts], tphase);
+#pragma unroll
+                        for (int sub = 0; sub < 4; sub++) {
+                            const uint32_t op = op_next;
+                            op_next = __shfl_sync(0xffffffffu, w, (j + sub + 1) & 31);
+                            if (op & K10_OP_NOP) continue;
+                            if (op & K10_OP_NEW) mbar_wait(&a_full[ast], aphase);
+                            if (((op >> K10_OP_OWNER_SHIFT) & 1u) == me) {
+                                const uint32_t buf = op & 7u;
+                                if (op & K10_OP_FIRST)
+                                    mbar_wait(&acc_free[buf],
+                                              ((op >> K10_OP_PARITY_SHIFT) & 1u) ^ 1u);
+                                k10_fence_after();
+                                if (k10_elect_one()) {
+                                    const uint32_t d = tmem_base + buf * K10_ACC_COLS;
+                                    const uint32_t a_hi =
+                                        tmem_base + (uint32_t)K10_A_BASE + ast * 64u +
+                                        ((op >> K10_OP_SLICE_SHIFT) & 3u) * 16u;
+                                    const uint32_t b = desc_lo + (uint32_t)(sub * 2);
+                                    k10_mma2(d, a_hi, b, desc_hi32, IDESC,
+                                             (op & K10_OP_FIRST) ? 0u : 1u);
+                                    k10_mma2(d, a_hi, b + DESC_LO_HALF, desc_hi32, IDESC, 1u);
+                                    k10_mma2(d, a_hi + 8, b, desc_hi32, IDESC, 1u);
+                                    if (op & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
+                                }
+                                __syncwarp();
                             }
-                            if (sub == 3) k10_commit(&tab_free[ts]);
+                            if (op & K10_OP_END) {
+                                // this warp's MMAs of the box (if any) release the A stage
+                                if (k10_elect_one()) k10_commit(&mma_done[ast]);
+                                __syncwarp();
+                                ast ^= 1u;
+                                aphase ^= ast ^ 1u;
+                            }
                         }
+                        if (k10_elect_one()) k10_commit(&tab_free[ts]);
                         __syncwarp();
-                        if (!nop) {
-                            if (op & K10_OP_END) ka++;
-                            if (op & K10_OP_COMMIT) cuse ^= 1u << buf;
-                        }
-                        if (sub == 3) {
-                            if (++ts == K10_TSTAGES) {
-                                ts = 0;
-                                tphase ^= 1;
-                            }
+                        desc_lo += DESC_STAGE;
+                        if (++ts == K10_TSTAGES) {
+                            ts = 0;
+                            tphase ^= 1;
+                            desc_lo = desc_lo0;
                         }
                     }
                 }

@@ -17,8 +17,8 @@ and the kernel only follows lists (the same for every block of 128 frames):
 * ``boxes``  -- per visit: first pixel of the box | 4-bit mask of the slices that are used;
 * ``ops``    -- per (slice, group): the TMEM accumulator buffer (a pool of ``NBUF``), whether the
   op starts a chain (zero-initialise, wait for the drain of the buffer's previous chain),
-  whether it ends one (hand the buffer to the drain warps), whether it opens / closes a slice
-  (A-operand slot hand-over with the converter warps);
+  whether it ends one (hand the buffer to the drain warps), its slice of the box, whether it
+  is the first / last op of its box (A-operand stage hand-over with the converter warps);
 * ``events`` -- per chain, in commit order: buffer, register slot, group (its parity selects
   the drain warps), last-chain-of-the-group (write the result);
 * ``table``  -- the split-TF32 weight blocks in op order as the byte image of the kernel's
@@ -47,12 +47,16 @@ MAX_SEGMENTS = 8
 
 OP_FIRST = 1 << 3
 OP_COMMIT = 1 << 4
-OP_NEW_SLICE = 1 << 5
-OP_END_SLICE = 1 << 6
+OP_NEW_BOX = 1 << 5
+OP_END_BOX = 1 << 6
 OP_NOP = 1 << 7
+OP_SLICE_SHIFT = 8    # bits 8-9: slice of the box (A-operand slot inside the box's stage)
+OP_PARITY_SHIFT = 10  # first op of a chain: parity of the buffer's use count in the segment
+OP_OWNER_SHIFT = 11   # group parity = MMA warp / drain group that owns the op
 
 EV_SLOT = 1 << 3
 EV_LAST = 1 << 4
+EV_PARITY_SHIFT = 5   # parity of the buffer's use count in the segment
 
 
 def tf32_round(a):
@@ -171,40 +175,64 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                 if len(gs) == 0:
                     continue
                 mask |= 1 << j
-                for gi, g in enumerate(gs):
-                    seq.append((v, j, int(lo[v] + g), gi == 0, gi == len(gs) - 1))
+                for g in gs:
+                    seq.append([v, j, int(lo[v] + g), False, False])
             boxes[v] = np.uint32(box[v] * BOX) | np.uint32(mask)
         for i, e in enumerate(seq):
             last_op_of_group[e[2]] = i
-        free = list(range(NBUF))                   # FIFO: oldest released first
+        # accumulator buffers: a pool of NBUF / 2 per group parity (the two MMA warps / drain
+        # groups are independent pipelines), FIFO = oldest released first
+        free = [list(range(NBUF // 2)), list(range(NBUF // 2, NBUF))]
+        uses = [0] * NBUF
         open_buf, open_len = {}, {}
-        for i, (v, j, g, new_slice, end_slice) in enumerate(seq):
-            word = 0
+        words = []
+        for i, (v, j, g, _, _) in enumerate(seq):
+            word = j << OP_SLICE_SHIFT
+            par = g & 1
             if g not in open_buf:
-                if not free:
+                if not free[par]:
                     raise AssertionError('walk plan: accumulator pool exhausted')
-                open_buf[g] = free.pop(0)
+                b = open_buf[g] = free[par].pop(0)
                 open_len[g] = 0
-                word |= OP_FIRST
+                word |= OP_FIRST | ((uses[b] & 1) << OP_PARITY_SHIFT)
                 if len(open_buf) > W_LIVE:
                     raise AssertionError('walk plan: more than W_LIVE live groups')
             b = open_buf[g]
-            word |= b
+            word |= b | (par << OP_OWNER_SHIFT)
             open_len[g] += 1
-            if new_slice:
-                word |= OP_NEW_SLICE
-            if end_slice:
-                word |= OP_END_SLICE
             final = last_op_of_group[g] == i
             if open_len[g] == chain or final:
                 word |= OP_COMMIT
-                ev = b | (EV_SLOT if (g >> 1) & 1 else 0) | (EV_LAST if final else 0) | (g << 8)
+                ev = (b | (EV_SLOT if (g >> 1) & 1 else 0) | (EV_LAST if final else 0) |
+                      ((uses[b] & 1) << EV_PARITY_SHIFT) | (g << 8))
                 events.append(ev)
-                free.append(b)
+                uses[b] += 1
+                free[par].append(b)
                 del open_buf[g], open_len[g]
-            ops.append(word)
+            words.append(word)
             op_slice.append(int(box[v]) * (BOX // SL) + j)
             op_group.append(g)
+        # every buffer is used an even number of times per segment, so that the mbarrier
+        # parities of a chain are static: an odd count gets one empty chain (zero weights) on
+        # the last slice of the segment
+        if seq:
+            v, j = seq[-1][0], seq[-1][1]
+            for b in range(NBUF):
+                if uses[b] & 1:
+                    par = 1 if b >= NBUF // 2 else 0
+                    words.append((j << OP_SLICE_SHIFT) | b | (par << OP_OWNER_SHIFT) | OP_FIRST |
+                                 OP_COMMIT | ((uses[b] & 1) << OP_PARITY_SHIFT))
+                    events.append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
+                    uses[b] += 1
+                    seq.append([v, j, -2, False, False])
+                    op_slice.append(int(box[v]) * (BOX // SL) + j)
+                    op_group.append(-2)
+        for i, e in enumerate(seq):                # first / last op of every visit
+            if i == 0 or seq[i - 1][0] != e[0]:
+                words[i] |= OP_NEW_BOX
+            if i == len(seq) - 1 or seq[i + 1][0] != e[0]:
+                words[i] |= OP_END_BOX
+        ops.extend(words)
         assert not open_buf
         while len(ops) % STAGE_OPS:
             ops.append(OP_NOP)
@@ -279,32 +307,41 @@ def emulate(plan, tile):
     for s in range(plan['n_segments']):
         bufs = np.zeros((NBUF, F, HR))
         busy = [False] * NBUF
+        uses = [0] * NBUF
         acc = np.zeros((2, 2, F, HR))
         slot_owner = [[None, None], [None, None]]
         evs = list(plan['events'][plan['ev_off'][s]:plan['ev_off'][s + 1]])
-        slices = []
-        for v in range(plan['visit_off'][s], plan['visit_off'][s + 1]):
-            word = int(plan['boxes'][v])
-            px0, mask = word & ~31, word & 15
-            assert mask
-            for j in range(4):
-                if mask >> j & 1:
-                    slices.append(px0 + j * SL)
-        cur = -1
+        v = plan['visit_off'][s] - 1
+        px0 = mask = 0
         open_groups = {}
         for i in range(plan['op_off'][s], plan['op_off'][s + 1]):
             word = int(plan['ops'][i])
             if word & OP_NOP:
                 continue
             g = int(plan['op_group'][i])
-            if word & OP_NEW_SLICE:
-                cur += 1
-            assert slices[cur] == plan['op_slice'][i] * SL
+            dummy = g == -2
+            if word & OP_NEW_BOX:
+                v += 1
+                px0, mask = int(plan['boxes'][v]) & ~31, int(plan['boxes'][v]) & 15
+            j = (word >> OP_SLICE_SHIFT) & 3
+            assert mask >> j & 1                   # the converters fill only the masked slices
+            assert px0 + j * SL == plan['op_slice'][i] * SL
             b = word & 7
-            x = tile[:, slices[cur]:slices[cur] + SL].astype(np.float64)       # (F, 8)
+            assert ((word >> OP_OWNER_SHIFT) & 1) == (1 if b >= NBUF // 2 else 0)
+            if dummy:
+                ev = int(evs.pop(0))
+                assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
+                assert (ev & 7) == b and not ev & EV_LAST
+                assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1) == ((ev >> EV_PARITY_SHIFT) & 1)
+                assert not np.any(w[i // STAGE_OPS, :, i % STAGE_OPS])
+                uses[b] += 1
+                continue
+            assert ((word >> OP_OWNER_SHIFT) & 1) == (g & 1)
+            x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)    # (F, 8)
             prod = x @ w[i // STAGE_OPS, :, i % STAGE_OPS].T                   # (F, HR)
             if word & OP_FIRST:
                 assert not busy[b] and g not in open_groups
+                assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1)
                 busy[b] = True
                 open_groups[g] = b
                 bufs[b] = prod
@@ -317,6 +354,8 @@ def emulate(plan, tile):
                 p = g & 1
                 ev = int(evs.pop(0))
                 assert (ev & 7) == b and (ev >> 8) == g
+                assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses[b] & 1)
+                uses[b] += 1
                 slot = 1 if ev & EV_SLOT else 0
                 assert slot == ((g >> 1) & 1)
                 assert slot_owner[p][slot] in (None, g)
@@ -329,8 +368,9 @@ def emulate(plan, tile):
                     written[g] += 1
                     acc[p, slot] = 0
                     slot_owner[p][slot] = None
-        assert cur == len(slices) - 1
+        assert v == plan['visit_off'][s + 1] - 1
         assert not any(busy) and not evs and not open_groups
+        assert not any(u & 1 for u in uses)
         assert slot_owner == [[None, None], [None, None]]
     assert written.max() <= 2
     return (out[..., 0::2] + 1j * out[..., 1::2]).reshape(F, G * gs)
