@@ -52,10 +52,11 @@ constexpr int K10_THREADS = 640;
 constexpr int K10_TMEM_COLS = 512;
 
 constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4, K10_OP_NEW = 1u << 5,
-                   K10_OP_END = 1u << 6, K10_OP_NOP = 1u << 7;   // NEW / END: first / last op of a box
+                   K10_OP_END = 1u << 6,                     // NEW / END: first / last op of a box
+                   K10_OP_NOP = 3u << 11;                    // padding: owned by no warp
 constexpr int K10_OP_SLICE_SHIFT = 8;            // bits 8-9: slice of the box
 constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: parity of the buffer's use count
-constexpr int K10_OP_OWNER_SHIFT = 11;           // group parity = owning MMA warp
+constexpr int K10_OP_OWNER_SHIFT = 11;           // bits 11-12: owning MMA warp (3: padding)
 constexpr int K10_EV_PARITY_SHIFT = 5;
 constexpr uint32_t K10_EV_SLOT = 1u << 3, K10_EV_LAST = 1u << 4;
 
@@ -551,45 +552,64 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     if (base + 32 < o1)
                         w_next = base + 32 + lane < o1 ? p.ops[base + 32 + lane] : K10_OP_NOP;
                     const int n = o1 - base < 32 ? o1 - base : 32;      // a multiple of 4
-                    uint32_t op_next = __shfl_sync(0xffffffffu, w, 0);
-                    for (int j = 0; j < n; j += 4) {
-                        mbar_wait(&tab_full[ts], tphase);
+                    // the op words of a round are shuffled out one round ahead and kept in
+                    // vector registers until the round ends (the empty asm below), so that the
+                    // move to the uniform registers never waits for the shuffle
+                    uint32_t nx[4];
 #pragma unroll
-                        for (int sub = 0; sub < 4; sub++) {
-                            const uint32_t op = op_next;
-                            op_next = __shfl_sync(0xffffffffu, w, (j + sub + 1) & 31);
-                            if (op & K10_OP_NOP) continue;
-                            if (op & K10_OP_NEW) mbar_wait(&a_full[ast], aphase);
-                            if (((op >> K10_OP_OWNER_SHIFT) & 1u) == me) {
-                                const uint32_t buf = op & 7u;
-                                if (op & K10_OP_FIRST)
-                                    mbar_wait(&acc_free[buf],
-                                              ((op >> K10_OP_PARITY_SHIFT) & 1u) ^ 1u);
-                                k10_fence_after();
-                                if (k10_elect_one()) {
+                    for (int u = 0; u < 4; u++) nx[u] = __shfl_sync(0xffffffffu, w, u);
+                    for (int j = 0; j < n; j += 4) {
+                        uint32_t op[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) op[u] = nx[u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            nx[u] = __shfl_sync(0xffffffffu, w, (j + 4 + u) & 31);
+                        mbar_wait(&tab_full[ts], tphase);
+                        if (k10_elect_one()) {
+                            uint32_t ast_l = ast, aphase_l = aphase;
+#pragma unroll
+                            for (int sub = 0; sub < 4; sub++) {
+                                const uint32_t o = op[sub];
+                                if (o & K10_OP_NEW) {
+                                    mbar_wait(&a_full[ast_l], aphase_l);
+                                    k10_fence_after();
+                                }
+                                if (((o >> K10_OP_OWNER_SHIFT) & 3u) == me) {
+                                    const uint32_t buf = o & 7u;
+                                    if (o & K10_OP_FIRST) {
+                                        mbar_wait(&acc_free[buf],
+                                                  ((o >> K10_OP_PARITY_SHIFT) & 1u) ^ 1u);
+                                        k10_fence_after();
+                                    }
                                     const uint32_t d = tmem_base + buf * K10_ACC_COLS;
                                     const uint32_t a_hi =
-                                        tmem_base + (uint32_t)K10_A_BASE + ast * 64u +
-                                        ((op >> K10_OP_SLICE_SHIFT) & 3u) * 16u;
+                                        tmem_base + (uint32_t)K10_A_BASE + ast_l * 64u +
+                                        ((o >> K10_OP_SLICE_SHIFT) & 3u) * 16u;
                                     const uint32_t b = desc_lo + (uint32_t)(sub * 2);
                                     k10_mma2(d, a_hi, b, desc_hi32, IDESC,
-                                             (op & K10_OP_FIRST) ? 0u : 1u);
+                                             (o & K10_OP_FIRST) ? 0u : 1u);
                                     k10_mma2(d, a_hi, b + DESC_LO_HALF, desc_hi32, IDESC, 1u);
                                     k10_mma2(d, a_hi + 8, b, desc_hi32, IDESC, 1u);
-                                    if (op & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
+                                    if (o & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
                                 }
-                                __syncwarp();
+                                if (o & K10_OP_END) {
+                                    // this warp's MMAs of the box (if any) release the A stage
+                                    k10_commit(&mma_done[ast_l]);
+                                    ast_l ^= 1u;
+                                    aphase_l ^= ast_l ^ 1u;
+                                }
                             }
-                            if (op & K10_OP_END) {
-                                // this warp's MMAs of the box (if any) release the A stage
-                                if (k10_elect_one()) k10_commit(&mma_done[ast]);
-                                __syncwarp();
-                                ast ^= 1u;
-                                aphase ^= ast ^ 1u;
-                            }
+                            k10_commit(&tab_free[ts]);
                         }
-                        if (k10_elect_one()) k10_commit(&tab_free[ts]);
                         __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < 4; u++) asm volatile("" : "+r"(nx[u])::"memory");
+                        // the A-stage position after the round (all lanes)
+                        const uint32_t t = ast + ((op[0] >> 6) & 1u) + ((op[1] >> 6) & 1u) +
+                                           ((op[2] >> 6) & 1u) + ((op[3] >> 6) & 1u);
+                        aphase ^= (t >> 1) & 1u;
+                        ast = t & 1u;
                         desc_lo += DESC_STAGE;
                         if (++ts == K10_TSTAGES) {
                             ts = 0;

@@ -49,10 +49,10 @@ OP_FIRST = 1 << 3
 OP_COMMIT = 1 << 4
 OP_NEW_BOX = 1 << 5
 OP_END_BOX = 1 << 6
-OP_NOP = 1 << 7
 OP_SLICE_SHIFT = 8    # bits 8-9: slice of the box (A-operand slot inside the box's stage)
 OP_PARITY_SHIFT = 10  # first op of a chain: parity of the buffer's use count in the segment
-OP_OWNER_SHIFT = 11   # group parity = MMA warp / drain group that owns the op
+OP_OWNER_SHIFT = 11   # bits 11-12: group parity = MMA warp / drain group that owns the op
+OP_NOP = 3 << OP_OWNER_SHIFT   # padding: owned by no warp
 
 EV_SLOT = 1 << 3
 EV_LAST = 1 << 4
@@ -316,7 +316,8 @@ def emulate(plan, tile):
         open_groups = {}
         for i in range(plan['op_off'][s], plan['op_off'][s + 1]):
             word = int(plan['ops'][i])
-            if word & OP_NOP:
+            if (word & OP_NOP) == OP_NOP:
+                assert word == OP_NOP
                 continue
             g = int(plan['op_group'][i])
             dummy = g == -2
