@@ -271,30 +271,37 @@ LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, in
  * ltb200_group_masks_tc (reference analysis/radialfourier.py:106-146 masks through
  * udf/masks.py:59-77), but every pixel crosses the L2 -> SM fabric once inside a dense TMA box
  * [128 frames x 32 px]; the boxes are visited sorted by the first group they touch and the
- * groups are separated by the weights.  All lists come from libertem_b200/walk_plan.py
- * (build_walk) and are the same for every block of 128 frames:
+ * groups are separated by the weights (an op = 8 consecutive pixels x one group touching
+ * them).  The groups of even / odd id form two independent pipelines (index k = 0 / 1 below).
+ * All lists come from libertem_b200/walk_plan.py (build_walk), are the same for every block of
+ * 128 frames and are final: the kernel only shifts and masks their words.
  *   boxes   (n_visits) uint32: first pixel of the box (multiple of 32) | 4-bit mask of the
- *           8-pixel slices in use;
- *   ops     (n_ops, multiple of 4 per segment) uint32 per (slice, group): bits 0-2 accumulator
- *           buffer, 3 first op of a chain, 4 last op of a chain, 5 first op of its slice,
- *           6 last op of its slice, 7 padding (no work);
- *   events  (n_chains) uint32 per accumulation chain in commit order: bits 0-2 buffer, 3
- *           register slot, 4 last chain of the group in this segment, 8.. group id;
- *   table   (n_ops / 4, 112, 32) float32: per 4 ops the byte image of a shared-memory stage --
+ *           8-pixel slices in use; a multiple of 4 visits per segment;
+ *   ops_k   uint32 per op of pipeline k in walk order (a multiple of 4 per segment): bits 0-2
+ *           accumulator buffer, 3 / 4 first / last op of an accumulation chain, 5 / 6 first /
+ *           last word of the pipeline in its box, 7 no tensor work (marker of a box without
+ *           ops of the pipeline, padding), 8-9 slice of the box, 10 mbarrier parity of the
+ *           buffer (first op), 11 A stage of the box, 12 mbarrier parity of the A stage;
+ *   events_k uint32 per accumulation chain of pipeline k: bits 0-2 buffer, 3 register slot,
+ *           4 last chain of the group in this segment, 5 mbarrier parity, 8.. group id;
+ *   table_k (n_ops_k / 4, 112, 32) float32: per 4 ops the byte image of a shared-memory stage:
  *           rows [hi(c) | lo(c)], c = 2 * pair + {0 re, 1 im} < 56, the 8 weights of op j at
  *           floats [8 j, 8 j + 8) of a row, 16-byte chunks XOR-swizzled with (row & 7);
- *   seg_off_host (3, n_segments + 1) int32 on the HOST: visit, op and event offsets of the
- *           segments (independent work items; a group receives sums from <= 2 segments).
+ *   seg_off_host (5, n_segments + 1) int32 on the HOST: visit, op_0, op_1, event_0, event_1
+ *           offsets of the segments (independent work items; a group receives sums from <= 2
+ *           segments).
  * out (n_frames, >= n_groups * n_pairs * 2) float32 = complex64 (n_groups * n_pairs), written
  * (accumulate = 0) or added to (accumulate = 1, staged through the workspace). */
 LTB_API size_t ltb200_group_masks_walk_workspace(int64_t n_frames, int n_groups, int n_pairs,
                                                  int accumulate);
 LTB_API int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int64_t sig_size,
-                                    int64_t ld_tile, const uint32_t* boxes, const uint32_t* ops,
-                                    const uint32_t* events, const float* table,
-                                    const int32_t* seg_off_host, int n_segments, int n_groups,
-                                    int n_pairs, float* out, int64_t ld_out, int accumulate,
-                                    void* workspace, size_t workspace_bytes, void* stream);
+                                    int64_t ld_tile, const uint32_t* boxes, const uint32_t* ops0,
+                                    const uint32_t* ops1, const uint32_t* events0,
+                                    const uint32_t* events1, const float* table0,
+                                    const float* table1, const int32_t* seg_off_host,
+                                    int n_segments, int n_groups, int n_pairs, float* out,
+                                    int64_t ld_out, int accumulate, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 
 /* Mirror-symmetric plan (opt-in: validated on B200, 3 % faster than the banded plan on cfg4 --
  * the kernel is gather-bound, not bound by what the symmetry saves): for stacks whose masks obey m(sy - y, x) = conj(m(y, x)) -- the

@@ -12,7 +12,9 @@
 // and the separation into groups is done by the weights: an OP is (slice of 8 consecutive
 // pixels, group touching it) with an [8 x 2G] weight block that is zero outside the group.
 // Everything order-dependent is decided on the host (libertem_b200/walk_plan.py): the kernel
-// follows static lists that are the same for every block of 128 frames.
+// interprets static lists ("microcode") that are the same for every block of 128 frames.  The
+// groups of even and odd id are two independent pipelines (MMA issuer warp, accumulator
+// buffers, drain warps, weight-table stream) that share only the boxes and their A stages.
 //
 // 20 warps:
 //   * warps 0..7   converters: thread <-> frame row (TMEM lane); the slices of a box alternate
@@ -23,9 +25,9 @@
 //     / odd id go to warps 8..11 / 12..15, each thread keeps two groups (window of 4); the last
 //     chain of a group writes the result row;
 //   * warp 16      box producer (TMA, frame stream, evict_first) + work-item fetch;
-//   * warp 17      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops (the table
-//     is stored as the byte image of the swizzled stage);
-//   * warps 18, 19 MMA issuers (even / odd groups): per op three tcgen05.mma.kind::tf32 of
+//   * warp 17      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops of a
+//     pipeline (the tables are stored as the byte image of the swizzled stage), two rings of 4;
+//   * warps 18, 19 MMA issuers (even / odd pipeline): per op three tcgen05.mma.kind::tf32 of
 //     M 128, N 64, K 8 into the op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi;
 //     the table rows are [hi(0..55) | lo(0..55)], the lo product reads rows 56..119).
 // TMEM: 6 accumulator buffers of 64 columns (pool; chains of <= 8 ops, the float32 accumulate
@@ -41,7 +43,7 @@ constexpr int K10_DSTAGES = 6;
 constexpr int K10_HR = 56;                       // weight rows per half
 constexpr uint32_t K10_TAB_BYTES = 2 * K10_HR * 128;        // 14 KiB copied per stage
 constexpr uint32_t K10_TAB_STRIDE = K10_TAB_BYTES + 1024;   // + 8 zero rows (rows 112..119)
-constexpr int K10_TSTAGES = 7;
+constexpr int K10_TSTAGES = 4;                    // per pipeline
 constexpr int K10_AS = 2;                        // A-operand stages: 4 slices x (hi 8 | lo 8)
 constexpr int K10_NBUF = 6;                      // accumulator buffers
 constexpr int K10_ACC_COLS = 64;
@@ -51,23 +53,24 @@ constexpr int K10_MAXSEG = 8;
 constexpr int K10_THREADS = 640;
 constexpr int K10_TMEM_COLS = 512;
 
-constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4, K10_OP_NEW = 1u << 5,
-                   K10_OP_END = 1u << 6,                     // NEW / END: first / last op of a box
-                   K10_OP_NOP = 3u << 11;                    // padding: owned by no warp
+constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4,
+                   K10_OP_NEW = 1u << 5, K10_OP_END = 1u << 6,   // first / last word in a box
+                   K10_OP_NOMMA = 1u << 7;                       // marker / padding
 constexpr int K10_OP_SLICE_SHIFT = 8;            // bits 8-9: slice of the box
 constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: parity of the buffer's use count
-constexpr int K10_OP_OWNER_SHIFT = 11;           // bits 11-12: owning MMA warp (3: padding)
-constexpr int K10_EV_PARITY_SHIFT = 5;
+constexpr int K10_OP_ASTAGE_SHIFT = 11;          // A stage of the box
+constexpr int K10_OP_APARITY_SHIFT = 12;         // mbarrier parity of the A stage
 constexpr uint32_t K10_EV_SLOT = 1u << 3, K10_EV_LAST = 1u << 4;
+constexpr int K10_EV_PARITY_SHIFT = 5;
 
 struct K10Params {
     const uint32_t* boxes;         // per visit: first pixel | slice mask (low 4 bits)
-    const uint32_t* ops;           // per (slice, group)
-    const uint32_t* events;        // per chain, commit order
-    const float* table;            // (n_ops / 4) stage images of K10_TAB_BYTES
-    int visit_off[K10_MAXSEG + 1];
-    int op_off[K10_MAXSEG + 1];    // multiples of 4
-    int ev_off[K10_MAXSEG + 1];
+    const uint32_t* ops[2];        // per pipeline: one word per op / marker
+    const uint32_t* events[2];     // per pipeline: one word per chain
+    const float* table[2];         // per pipeline: (n_ops / 4) stage images of K10_TAB_BYTES
+    int visit_off[K10_MAXSEG + 1]; // multiples of 4 visits per segment
+    int op_off[2][K10_MAXSEG + 1]; // multiples of 4
+    int ev_off[2][K10_MAXSEG + 1];
     int n_seg;
     int n_cols;                    // 2 * n_pairs real columns per group
     float* out;
@@ -199,7 +202,7 @@ __device__ __forceinline__ void k10_bulk_load(void* dst, const void* src, uint32
 
 struct K10Smem {
     static constexpr uint32_t TABLE_OFF = K10_DSTAGES * K10_BOX_BYTES;
-    static constexpr uint32_t BAR_OFF = TABLE_OFF + K10_TSTAGES * K10_TAB_STRIDE;
+    static constexpr uint32_t BAR_OFF = TABLE_OFF + 2 * K10_TSTAGES * K10_TAB_STRIDE;
     static constexpr uint32_t TOTAL = BAR_OFF + 1024 + 1024;            // + alignment slack
 };
 
@@ -211,9 +214,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 
     uint64_t* data_full = reinterpret_cast<uint64_t*>(smem + K10Smem::BAR_OFF);   // [DSTAGES]
     uint64_t* data_free = data_full + K10_DSTAGES;                                // [DSTAGES]
-    uint64_t* tab_full = data_free + K10_DSTAGES;                                 // [TSTAGES]
-    uint64_t* tab_free = tab_full + K10_TSTAGES;                                  // [TSTAGES]
-    uint64_t* a_full = tab_free + K10_TSTAGES;                                    // [AS]
+    uint64_t* tab_full = data_free + K10_DSTAGES;                                 // [2][TSTAGES]
+    uint64_t* tab_free = tab_full + 2 * K10_TSTAGES;                              // [2][TSTAGES]
+    uint64_t* a_full = tab_free + 2 * K10_TSTAGES;                                // [AS]
     uint64_t* mma_done = a_full + K10_AS;                                         // [AS]
     uint64_t* acc_full = mma_done + K10_AS;                                       // [NBUF]
     uint64_t* acc_free = acc_full + K10_NBUF;                                     // [NBUF]
@@ -232,9 +235,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             mbar_init(&data_full[s], 1);
             mbar_init(&data_free[s], 8);               // converter warps
         }
-        for (int s = 0; s < K10_TSTAGES; s++) {
+        for (int s = 0; s < 2 * K10_TSTAGES; s++) {
             mbar_init(&tab_full[s], 1);
-            mbar_init(&tab_free[s], 2);                // both MMA warps
+            mbar_init(&tab_free[s], 1);
         }
         for (int s = 0; s < K10_AS; s++) {
             mbar_init(&a_full[s], 8);                  // converter warps
@@ -251,7 +254,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         fence_mbar_init();
     }
     // rows 112..119 of every table stage (read by the lo product, N = 64 from row 56) stay zero
-    for (int i = threadIdx.x; i < K10_TSTAGES * 256; i += K10_THREADS) {
+    for (int i = threadIdx.x; i < 2 * K10_TSTAGES * 256; i += K10_THREADS) {
         const int s = i >> 8, w = i & 255;
         reinterpret_cast<uint32_t*>(smem + K10Smem::TABLE_OFF + (size_t)s * K10_TAB_STRIDE +
                                     K10_TAB_BYTES)[w] = 0u;
@@ -375,19 +378,19 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_free[q]);
             if (qi.item < 0) break;
-            const int e0 = p.ev_off[qi.seg], e1 = p.ev_off[qi.seg + 1];
+            const int e0 = p.ev_off[grp][qi.seg], e1 = p.ev_off[grp][qi.seg + 1];
+            const uint32_t* __restrict__ events = p.events[grp];
             const int64_t f = (int64_t)qi.fb * K10_FB + row;
-            uint32_t w_next = e0 + lane < e1 ? p.events[e0 + lane] : 0u;
+            uint32_t w_next = e0 + lane < e1 ? events[e0 + lane] : 0u;
             for (int base = e0; base < e1; base += 32) {
                 const uint32_t w = w_next;
                 if (base + 32 < e1)
-                    w_next = base + 32 + lane < e1 ? p.events[base + 32 + lane] : 0u;
+                    w_next = base + 32 + lane < e1 ? events[base + 32 + lane] : 0u;
                 const int n = e1 - base < 32 ? e1 - base : 32;
                 for (int j = 0; j < n; j++) {
                     const uint32_t ev = __shfl_sync(0xffffffffu, w, j);
                     const uint32_t buf = ev & 7u;
                     const uint32_t g = ev >> 8;
-                    if ((int)(g & 1u) != grp) continue;     // the other group's chain
                     // (every buffer is used an even number of times per segment: static parity)
                     mbar_wait(&acc_full[buf], (ev >> K10_EV_PARITY_SHIFT) & 1u);
                     k10_fence_after();
@@ -495,49 +498,60 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 }
             }
         } else if (warp == TABLE_WARP) {
-            // ===== weight-table producer =====
+            // ===== weight-table producer: one ring of K10_TSTAGES stages per pipeline, served
+            // by one lane that polls whichever ring has a free stage =====
             if (lane == 0) {
                 const uint64_t pol_keep = l2_policy_evict_last();
-                int ts = 0;
-                uint32_t tphase = 0;
+                int ts[2] = {0, 0};
+                uint32_t tphase[2] = {0, 0};
                 for (uint32_t qn = 0;; qn++) {
                     const int q = qn % K10_QLEN;
                     mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
                     const K10QItem qi = queue[q];
                     mbar_arrive(&q_free[q]);
                     if (qi.item < 0) break;
-                    const int t0 = p.op_off[qi.seg] >> 2, t1 = p.op_off[qi.seg + 1] >> 2;
-                    for (int t = t0; t < t1; t++) {
-                        mbar_wait(&tab_free[ts], tphase ^ 1);
-                        mbar_arrive_expect_tx(&tab_full[ts], K10_TAB_BYTES);
-                        k10_bulk_load(smem + K10Smem::TABLE_OFF + (size_t)ts * K10_TAB_STRIDE,
-                                      p.table + (size_t)t * (K10_TAB_BYTES / 4), K10_TAB_BYTES,
-                                      &tab_full[ts], pol_keep);
-                        if (++ts == K10_TSTAGES) {
-                            ts = 0;
-                            tphase ^= 1;
+                    int t[2] = {p.op_off[0][qi.seg] >> 2, p.op_off[1][qi.seg] >> 2};
+                    const int t1[2] = {p.op_off[0][qi.seg + 1] >> 2, p.op_off[1][qi.seg + 1] >> 2};
+                    while (t[0] < t1[0] || t[1] < t1[1]) {
+#pragma unroll
+                        for (int s = 0; s < 2; s++) {
+                            if (t[s] >= t1[s]) continue;
+                            const int slot = s * K10_TSTAGES + ts[s];
+                            if (!mbar_try_wait(&tab_free[slot], tphase[s] ^ 1)) continue;
+                            mbar_arrive_expect_tx(&tab_full[slot], K10_TAB_BYTES);
+                            k10_bulk_load(smem + K10Smem::TABLE_OFF + (size_t)slot * K10_TAB_STRIDE,
+                                          p.table[s] + (size_t)t[s] * (K10_TAB_BYTES / 4),
+                                          K10_TAB_BYTES, &tab_full[slot], pol_keep);
+                            t[s]++;
+                            if (++ts[s] == K10_TSTAGES) {
+                                ts[s] = 0;
+                                tphase[s] ^= 1;
+                            }
                         }
                     }
                 }
             }
         } else {
-            // ===== MMA issuers (warp-uniform loops, one elected lane issues) =====
-            // Two warps: warp 18 issues the ops of the even groups, warp 19 those of the odd
-            // groups (disjoint accumulator buffers, so the two instruction streams need no
-            // ordering); both walk the whole op list and both commit onto the barriers that
-            // release an A stage / a table stage.  One op = 96 tensor-pipe cycles, one warp
-            // cannot decode and issue an op in that time (profiles/r2_k10_*): everything an op
-            // needs is a shift / mask of its word, the descriptors are running 32-bit halves,
-            // four ops (one table stage) per unrolled round.
-            const uint32_t me = (uint32_t)(warp - MMA_WARP);
+            // ===== MMA issuers (one per pipeline; warp-uniform loop, one elected lane issues)
+            // One op = 96 tensor-pipe cycles and a single thread retires an instruction every
+            // 6-8 cycles here (profiles/r2_k10_*), so the issue loop must be short: every word
+            // of the list is final (buffer, A stage, parities are static), four words (one
+            // table stage) per round, the words of the next round are shuffled out while this
+            // one runs, the descriptor is a running 32-bit half.
+            const int me = warp - MMA_WARP;
             constexpr uint32_t IDESC = k10_idesc_tf32(K10_ACC_COLS);
-            const uint32_t tb0 = smem_u32(smem + K10Smem::TABLE_OFF);
+            const uint32_t tb0 =
+                smem_u32(smem + K10Smem::TABLE_OFF + (size_t)me * K10_TSTAGES * K10_TAB_STRIDE);
             const uint32_t desc_hi32 = (uint32_t)(k10_desc_k_sw128(0) >> 32);
             const uint32_t desc_lo0 = (uint32_t)k10_desc_k_sw128(tb0);
             constexpr uint32_t DESC_STAGE = K10_TAB_STRIDE >> 4, DESC_LO_HALF = (K10_HR * 128) >> 4;
+            uint64_t* my_tab_full = tab_full + me * K10_TSTAGES;
+            uint64_t* my_tab_free = tab_free + me * K10_TSTAGES;
+            const uint32_t* __restrict__ ops = p.ops[me];
+            const uint32_t a_base = tmem_base + (uint32_t)K10_A_BASE;
             uint32_t desc_lo = desc_lo0;                // table stage `ts`, rows 0.., op 0
             int ts = 0;
-            uint32_t tphase = 0, ast = 0, aphase = 0;
+            uint32_t tphase = 0;
             for (uint32_t qn = 0;; qn++) {
                 const int q = qn % K10_QLEN;
                 mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
@@ -545,16 +559,13 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_free[q]);
                 if (qi.item < 0) break;
-                const int o0 = p.op_off[qi.seg], o1 = p.op_off[qi.seg + 1];
-                uint32_t w_next = o0 + lane < o1 ? p.ops[o0 + lane] : K10_OP_NOP;
+                const int o0 = p.op_off[me][qi.seg], o1 = p.op_off[me][qi.seg + 1];
+                uint32_t w_next = o0 + lane < o1 ? ops[o0 + lane] : K10_OP_NOMMA;
                 for (int base = o0; base < o1; base += 32) {
                     const uint32_t w = w_next;
                     if (base + 32 < o1)
-                        w_next = base + 32 + lane < o1 ? p.ops[base + 32 + lane] : K10_OP_NOP;
+                        w_next = base + 32 + lane < o1 ? ops[base + 32 + lane] : K10_OP_NOMMA;
                     const int n = o1 - base < 32 ? o1 - base : 32;      // a multiple of 4
-                    // the op words of a round are shuffled out one round ahead and kept in
-                    // vector registers until the round ends (the empty asm below), so that the
-                    // move to the uniform registers never waits for the shuffle
                     uint32_t nx[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) nx[u] = __shfl_sync(0xffffffffu, w, u);
@@ -565,17 +576,17 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 #pragma unroll
                         for (int u = 0; u < 4; u++)
                             nx[u] = __shfl_sync(0xffffffffu, w, (j + 4 + u) & 31);
-                        mbar_wait(&tab_full[ts], tphase);
+                        mbar_wait(&my_tab_full[ts], tphase);
                         if (k10_elect_one()) {
-                            uint32_t ast_l = ast, aphase_l = aphase;
 #pragma unroll
                             for (int sub = 0; sub < 4; sub++) {
                                 const uint32_t o = op[sub];
+                                const uint32_t ast = (o >> K10_OP_ASTAGE_SHIFT) & 1u;
                                 if (o & K10_OP_NEW) {
-                                    mbar_wait(&a_full[ast_l], aphase_l);
+                                    mbar_wait(&a_full[ast], (o >> K10_OP_APARITY_SHIFT) & 1u);
                                     k10_fence_after();
                                 }
-                                if (((o >> K10_OP_OWNER_SHIFT) & 3u) == me) {
+                                if (!(o & K10_OP_NOMMA)) {
                                     const uint32_t buf = o & 7u;
                                     if (o & K10_OP_FIRST) {
                                         mbar_wait(&acc_free[buf],
@@ -584,8 +595,8 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                                     }
                                     const uint32_t d = tmem_base + buf * K10_ACC_COLS;
                                     const uint32_t a_hi =
-                                        tmem_base + (uint32_t)K10_A_BASE + ast_l * 64u +
-                                        ((o >> K10_OP_SLICE_SHIFT) & 3u) * 16u;
+                                        a_base + ((o >> (K10_OP_ASTAGE_SHIFT - 6)) & 64u) +
+                                        ((o >> (K10_OP_SLICE_SHIFT - 4)) & 48u);
                                     const uint32_t b = desc_lo + (uint32_t)(sub * 2);
                                     k10_mma2(d, a_hi, b, desc_hi32, IDESC,
                                              (o & K10_OP_FIRST) ? 0u : 1u);
@@ -593,23 +604,14 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                                     k10_mma2(d, a_hi + 8, b, desc_hi32, IDESC, 1u);
                                     if (o & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
                                 }
-                                if (o & K10_OP_END) {
-                                    // this warp's MMAs of the box (if any) release the A stage
-                                    k10_commit(&mma_done[ast_l]);
-                                    ast_l ^= 1u;
-                                    aphase_l ^= ast_l ^ 1u;
-                                }
+                                // this pipeline's MMAs of the box (if any) release the A stage
+                                if (o & K10_OP_END) k10_commit(&mma_done[ast]);
                             }
-                            k10_commit(&tab_free[ts]);
+                            k10_commit(&my_tab_free[ts]);
                         }
                         __syncwarp();
 #pragma unroll
                         for (int u = 0; u < 4; u++) asm volatile("" : "+r"(nx[u])::"memory");
-                        // the A-stage position after the round (all lanes)
-                        const uint32_t t = ast + ((op[0] >> 6) & 1u) + ((op[1] >> 6) & 1u) +
-                                           ((op[2] >> 6) & 1u) + ((op[3] >> 6) & 1u);
-                        aphase ^= (t >> 1) & 1u;
-                        ast = t & 1u;
                         desc_lo += DESC_STAGE;
                         if (++ts == K10_TSTAGES) {
                             ts = 0;
@@ -659,8 +661,10 @@ extern "C" size_t ltb200_group_masks_walk_workspace(int64_t n_frames, int n_grou
 
 extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int64_t sig_size,
                                        int64_t ld_tile, const uint32_t* boxes,
-                                       const uint32_t* ops, const uint32_t* events,
-                                       const float* table, const int32_t* seg_off_host,
+                                       const uint32_t* ops0, const uint32_t* ops1,
+                                       const uint32_t* events0, const uint32_t* events1,
+                                       const float* table0, const float* table1,
+                                       const int32_t* seg_off_host,
                                        int n_segments, int n_groups, int n_pairs, float* out,
                                        int64_t ld_out, int accumulate, void* workspace,
                                        size_t workspace_bytes, void* stream) {
@@ -670,13 +674,15 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     LTB_REQUIRE(n_segments >= 1 && n_segments <= K10_MAXSEG,
                 "group_masks_walk: 1..%d segments", K10_MAXSEG);
     if (n_frames == 0) return LTB_OK;
-    LTB_REQUIRE(tile && boxes && ops && events && table && seg_off_host && out,
+    LTB_REQUIRE(tile && boxes && ops0 && ops1 && events0 && events1 && table0 && table1 &&
+                    seg_off_host && out,
                 "group_masks_walk: NULL pointer");
     LTB_REQUIRE(sig_size % 32 == 0 && sig_size < (1ll << 31),
                 "group_masks_walk: sig_size must be a multiple of 32");
     LTB_REQUIRE((uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0 && ld_tile >= sig_size,
                 "group_masks_walk: frame rows must be 16-byte aligned");
-    LTB_REQUIRE((uintptr_t)table % 16 == 0, "group_masks_walk: table must be 16 B aligned");
+    LTB_REQUIRE((uintptr_t)table0 % 16 == 0 && (uintptr_t)table1 % 16 == 0,
+                "group_masks_walk: tables must be 16 B aligned");
     LTB_REQUIRE(ld_out >= (int64_t)n_groups * n_pairs * 2, "group_masks_walk: ld_out too small");
     const size_t need = ltb200_group_masks_walk_workspace(n_frames, n_groups, n_pairs, accumulate);
     LTB_REQUIRE(workspace != nullptr && workspace_bytes >= need,
@@ -685,15 +691,24 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     cudaStream_t st = (cudaStream_t)stream;
     K10Params p;
     p.boxes = boxes;
-    p.ops = ops;
-    p.events = events;
-    p.table = table;
+    p.ops[0] = ops0;
+    p.ops[1] = ops1;
+    p.events[0] = events0;
+    p.events[1] = events1;
+    p.table[0] = table0;
+    p.table[1] = table1;
+    const int ns1 = n_segments + 1;
     for (int s = 0; s <= K10_MAXSEG; s++) {
         const int t = s <= n_segments ? s : n_segments;
         p.visit_off[s] = seg_off_host[t];
-        p.op_off[s] = seg_off_host[(n_segments + 1) + t];
-        p.ev_off[s] = seg_off_host[2 * (n_segments + 1) + t];
-        LTB_REQUIRE(p.op_off[s] % 4 == 0, "group_masks_walk: op offsets must be multiples of 4");
+        for (int k = 0; k < 2; k++) {
+            p.op_off[k][s] = seg_off_host[(1 + k) * ns1 + t];
+            p.ev_off[k][s] = seg_off_host[(3 + k) * ns1 + t];
+            LTB_REQUIRE(p.op_off[k][s] % 4 == 0,
+                        "group_masks_walk: op offsets must be multiples of 4");
+        }
+        LTB_REQUIRE(p.visit_off[s] % 4 == 0,
+                    "group_masks_walk: visit offsets must be multiples of 4");
     }
     p.n_seg = n_segments;
     p.n_cols = 2 * n_pairs;

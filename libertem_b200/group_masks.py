@@ -313,14 +313,18 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
     if WALK_PATH and n_cols and n_groups > 0:
         w = walk_plan.build_walk(flat, group_size, max_dup=walk_max_dup)
         if w is not None:
+            def dev_u32(a):
+                return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(device)
             plan.walk = dict(
                 n_segments=w['n_segments'], n_entries=w['n_entries'],
-                boxes=torch.from_numpy(w['boxes'].view(np.int32)).to(device),
-                ops=torch.from_numpy(w['ops'].view(np.int32)).to(device),
-                events=torch.from_numpy(w['events'].view(np.int32)).to(device),
-                table=torch.from_numpy(w['table']).to(device),
+                boxes=dev_u32(w['boxes']),
+                ops=[dev_u32(w['ops0']), dev_u32(w['ops1'])],
+                events=[dev_u32(w['events0']), dev_u32(w['events1'])],
+                table=[torch.from_numpy(w['table0']).to(device),
+                       torch.from_numpy(w['table1']).to(device)],
                 seg_off_host=np.ascontiguousarray(
-                    np.stack([w['visit_off'], w['op_off'], w['ev_off']]), dtype=np.int32))
+                    np.stack([w['visit_off'], w['op_off0'], w['op_off1'], w['ev_off0'],
+                              w['ev_off1']]), dtype=np.int32))
     if (SYM_PATH if sym is None else sym) and banded is not None and len(sig_shape) == 2:
         plan.sym = _sym_to_device(flat, sig_shape, group_size, max(1, n_bands // 2), n_cols,
                                   device)
@@ -389,8 +393,10 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
         ws = plan.walk_workspace(F, accumulate)
         with torch.cuda.device(tile.device):
             check(lib.ltb200_group_masks_walk(
-                tile.data_ptr(), F, K, ld_tile, w['boxes'].data_ptr(), w['ops'].data_ptr(),
-                w['events'].data_ptr(), w['table'].data_ptr(), w['seg_off_host'].ctypes.data,
+                tile.data_ptr(), F, K, ld_tile, w['boxes'].data_ptr(), w['ops'][0].data_ptr(),
+                w['ops'][1].data_ptr(), w['events'][0].data_ptr(), w['events'][1].data_ptr(),
+                w['table'][0].data_ptr(), w['table'][1].data_ptr(),
+                w['seg_off_host'].ctypes.data,
                 w['n_segments'], plan.n_groups, plan.n_pairs, real.data_ptr(), ld_out,
                 int(bool(accumulate)), ws.data_ptr(), ws.numel(),
                 torch.cuda.current_stream(tile.device).cuda_stream))

@@ -11,22 +11,30 @@ What makes this possible is the ORDER of the boxes: they are visited sorted by t
 they touch.  The groups of the reference's ``radial_mask_factory``
 (src/libertem/analysis/radialfourier.py:106-146) are concentric rings, a box touches <= 4
 adjacent ones, so at any time only a window of ``W_LIVE`` = 4 groups has an open accumulator in
-tensor memory.  Everything that depends on that order is decided HERE, once per mask stack,
-and the kernel only follows lists (the same for every block of 128 frames):
+tensor memory.  Everything that depends on that order is decided HERE, once per mask stack:
+the kernel is an interpreter of static lists ("microcode", the same for every block of 128
+frames) and computes nothing but shifts and masks of their words.
 
-* ``boxes``  -- per visit: first pixel of the box | 4-bit mask of the slices that are used;
-* ``ops``    -- per (slice, group): the TMEM accumulator buffer (a pool of ``NBUF``), whether the
-  op starts a chain (zero-initialise, wait for the drain of the buffer's previous chain),
-  whether it ends one (hand the buffer to the drain warps), its slice of the box, whether it
-  is the first / last op of its box (A-operand stage hand-over with the converter warps);
-* ``events`` -- per chain, in commit order: buffer, register slot, group (its parity selects
-  the drain warps), last-chain-of-the-group (write the result);
-* ``table``  -- the split-TF32 weight blocks in op order as the byte image of the kernel's
+The groups of even and odd id form two independent pipelines (an MMA issuer warp, a pool of
+``NBUF / 2`` accumulator buffers, four drain warps and a weight-table stream each) that share
+only the boxes and their A-operand stages:
+
+* ``boxes``   -- per visit: first pixel of the box | 4-bit mask of the slices that are used;
+  every segment holds a multiple of 4 visits (padded with empty ones), so that the A stage and
+  the mbarrier parity of a box are static;
+* ``ops[p]``  -- per op of pipeline p, in walk order: accumulator buffer, first / last op of an
+  accumulation chain (+ the static mbarrier parity), slice and A stage of the box, first / last
+  op of the pipeline in its box (A-stage hand-over with the converter warps; a box without ops
+  of the pipeline gets an empty marker word);
+* ``events[p]`` -- per chain: buffer, register slot, group, last-chain-of-the-group (write the
+  result), mbarrier parity;
+* ``table[p]`` -- the split-TF32 weight blocks of ``ops[p]`` as the byte image of the kernel's
   shared-memory stages (4 ops = 32 entries per stage, rows [hi | lo], 128-byte swizzle applied
   on the host so that the kernel issues one contiguous bulk copy per stage).
 
 The accumulate of the tensor core truncates, so chains are cut after ``CHAIN``
-ops and summed in float32 registers by the drain warps, as in K6 / K7.
+ops and summed in float32 registers by the drain warps, as in K6 / K7.  Every buffer is used an
+even number of times per segment (an empty chain is added otherwise): all parities are static.
 
 Boxes whose groups span more than ``W_LIVE`` are visited once per window (generic stacks);
 segments (contiguous runs of the visit order, at least ``W_LIVE`` groups apart) are independent
@@ -47,17 +55,19 @@ MAX_SEGMENTS = 8
 
 OP_FIRST = 1 << 3
 OP_COMMIT = 1 << 4
-OP_NEW_BOX = 1 << 5
-OP_END_BOX = 1 << 6
-OP_SLICE_SHIFT = 8    # bits 8-9: slice of the box (A-operand slot inside the box's stage)
-OP_PARITY_SHIFT = 10  # first op of a chain: parity of the buffer's use count in the segment
-OP_OWNER_SHIFT = 11   # bits 11-12: group parity = MMA warp / drain group that owns the op
-OP_NOP = 3 << OP_OWNER_SHIFT   # padding: owned by no warp
+OP_NEW_BOX = 1 << 5     # first word of the pipeline in its box: wait for the converters
+OP_END_BOX = 1 << 6     # last word of the pipeline in its box: release the A stage
+OP_NOMMA = 1 << 7       # marker / padding: no tensor work
+OP_SLICE_SHIFT = 8      # bits 8-9: slice of the box
+OP_PARITY_SHIFT = 10    # first op of a chain: parity of the buffer's use count in the segment
+OP_ASTAGE_SHIFT = 11    # A stage of the box (box index & 1)
+OP_APARITY_SHIFT = 12   # mbarrier parity of the A stage ((box index >> 1) & 1)
+OP_NOP = OP_NOMMA       # padding word
 
 EV_SLOT = 1 << 3
 EV_LAST = 1 << 4
-EV_PARITY_SHIFT = 5   # parity of the buffer's use count in the segment
-
+EV_PARITY_SHIFT = 5     # parity of the buffer's use count in the segment
+BOX_PAD = 4             # visits per segment are padded to a multiple of this
 
 def tf32_round(a):
     bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
@@ -147,7 +157,6 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
         return None
     if n_visits > max_dup * max(1, int(bx.any(axis=0).sum())):
         return None
-    # ops of every visit: (slice, group) pairs, slices ascending, groups ascending inside
     sl4 = sl.reshape(n_groups, K // BOX, BOX // SL)
     n_ops_visit = np.zeros(n_visits, dtype=np.int64)
     for v in range(n_visits):
@@ -157,16 +166,16 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
     bounds = _segment_bounds(key, n_ops_visit, n_segments)
     n_seg = len(bounds) - 1
 
-    boxes = np.zeros(n_visits, dtype=np.uint32)
-    ops, op_slice, op_group = [], [], []
-    events = []
-    visit_off, op_off, ev_off = [0], [0], [0]
-    # last visit index per group (a group's final op closes its chain and writes the result);
-    # per segment, so that a segment is self-contained
+    boxes = []
+    ops = ([], [])                 # per pipeline
+    op_slice = ([], [])            # global slice index of every word (-1: no weights)
+    op_group = ([], [])            # group of every word (-1 marker / padding, -2 empty chain)
+    events = ([], [])
+    visit_off, op_off, ev_off = [0], ([0], [0]), ([0], [0])
     for s in range(n_seg):
         v0, v1 = bounds[s], bounds[s + 1]
-        last_op_of_group = {}
-        seq = []                                   # (visit, slice, group)
+        seq = []                                   # [box index in the segment, slice, group]
+        seg_boxes = []
         for v in range(v0, v1):
             m = sl4[lo[v]:hi[v] + 1, box[v]]       # (groups in window, 4)
             mask = 0
@@ -176,19 +185,21 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                     continue
                 mask |= 1 << j
                 for g in gs:
-                    seq.append([v, j, int(lo[v] + g), False, False])
-            boxes[v] = np.uint32(box[v] * BOX) | np.uint32(mask)
+                    seq.append([v - v0, j, int(lo[v] + g)])
+            seg_boxes.append((int(box[v]) * BOX) | mask)
+        while len(seg_boxes) % BOX_PAD:            # empty visits: the box is loaded, not used
+            seg_boxes.append(seg_boxes[-1] & ~15)
+        last_op_of_group = {}
         for i, e in enumerate(seq):
             last_op_of_group[e[2]] = i
-        # accumulator buffers: a pool of NBUF / 2 per group parity (the two MMA warps / drain
-        # groups are independent pipelines), FIFO = oldest released first
+        # accumulator buffers: a pool of NBUF / 2 per pipeline, FIFO = oldest released first
         free = [list(range(NBUF // 2)), list(range(NBUF // 2, NBUF))]
         uses = [0] * NBUF
         open_buf, open_len = {}, {}
-        words = []
-        for i, (v, j, g, _, _) in enumerate(seq):
-            word = j << OP_SLICE_SHIFT
+        words = ([], [])                           # per pipeline: [word, box, slice, group]
+        for i, (b_i, j, g) in enumerate(seq):
             par = g & 1
+            word = j << OP_SLICE_SHIFT
             if g not in open_buf:
                 if not free[par]:
                     raise AssertionError('walk plan: accumulator pool exhausted')
@@ -198,63 +209,74 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                 if len(open_buf) > W_LIVE:
                     raise AssertionError('walk plan: more than W_LIVE live groups')
             b = open_buf[g]
-            word |= b | (par << OP_OWNER_SHIFT)
+            word |= b
             open_len[g] += 1
             final = last_op_of_group[g] == i
             if open_len[g] == chain or final:
                 word |= OP_COMMIT
-                ev = (b | (EV_SLOT if (g >> 1) & 1 else 0) | (EV_LAST if final else 0) |
-                      ((uses[b] & 1) << EV_PARITY_SHIFT) | (g << 8))
-                events.append(ev)
+                events[par].append(b | (EV_SLOT if (g >> 1) & 1 else 0) |
+                                   (EV_LAST if final else 0) |
+                                   ((uses[b] & 1) << EV_PARITY_SHIFT) | (g << 8))
                 uses[b] += 1
                 free[par].append(b)
                 del open_buf[g], open_len[g]
-            words.append(word)
-            op_slice.append(int(box[v]) * (BOX // SL) + j)
-            op_group.append(g)
-        # every buffer is used an even number of times per segment, so that the mbarrier
-        # parities of a chain are static: an odd count gets one empty chain (zero weights) on
-        # the last slice of the segment
+            words[par].append([word, b_i, j, g])
+        assert not open_buf
+        # every buffer is used an even number of times per segment (static mbarrier parities):
+        # an odd count gets one empty chain (zero weights) on the last op's slice
         if seq:
-            v, j = seq[-1][0], seq[-1][1]
+            b_i, j = seq[-1][0], seq[-1][1]
             for b in range(NBUF):
                 if uses[b] & 1:
                     par = 1 if b >= NBUF // 2 else 0
-                    words.append((j << OP_SLICE_SHIFT) | b | (par << OP_OWNER_SHIFT) | OP_FIRST |
-                                 OP_COMMIT | ((uses[b] & 1) << OP_PARITY_SHIFT))
-                    events.append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
+                    words[par].append([(j << OP_SLICE_SHIFT) | b | OP_FIRST | OP_COMMIT |
+                                       ((uses[b] & 1) << OP_PARITY_SHIFT), b_i, j, -2])
+                    events[par].append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
                     uses[b] += 1
-                    seq.append([v, j, -2, False, False])
-                    op_slice.append(int(box[v]) * (BOX // SL) + j)
-                    op_group.append(-2)
-        for i, e in enumerate(seq):                # first / last op of every visit
-            if i == 0 or seq[i - 1][0] != e[0]:
-                words[i] |= OP_NEW_BOX
-            if i == len(seq) - 1 or seq[i + 1][0] != e[0]:
-                words[i] |= OP_END_BOX
-        ops.extend(words)
-        assert not open_buf
-        while len(ops) % STAGE_OPS:
-            ops.append(OP_NOP)
-            op_slice.append(-1)
-            op_group.append(-1)
-        visit_off.append(v1)
-        op_off.append(len(ops))
-        ev_off.append(len(events))
+        # per pipeline: box hand-over flags; a box without ops of the pipeline gets a marker
+        for par in range(2):
+            by_box = {}
+            for w in words[par]:
+                by_box.setdefault(w[1], []).append(w)
+            for b_i in range(len(seg_boxes)):
+                ws = by_box.get(b_i)
+                if not ws:
+                    ws = [[OP_NOMMA, b_i, 0, -1]]
+                ws[0][0] |= OP_NEW_BOX
+                ws[-1][0] |= OP_END_BOX
+                for w in ws:
+                    w[0] |= ((b_i & 1) << OP_ASTAGE_SHIFT) | (((b_i >> 1) & 1) << OP_APARITY_SHIFT)
+                    ops[par].append(w[0])
+                    op_group[par].append(w[3])
+                    op_slice[par].append(
+                        (seg_boxes[b_i] & ~31) // SL + w[2] if w[3] != -1 else -1)
+            while len(ops[par]) % STAGE_OPS:
+                ops[par].append(OP_NOP)
+                op_group[par].append(-1)
+                op_slice[par].append(-1)
+            op_off[par].append(len(ops[par]))
+            ev_off[par].append(len(events[par]))
+        boxes.extend(seg_boxes)
+        visit_off.append(len(boxes))
 
-    ops = np.array(ops, dtype=np.uint32)
-    op_slice = np.array(op_slice, dtype=np.int64)
-    op_group = np.array(op_group, dtype=np.int64)
-    table = _table_image(flat, group_size, op_slice, op_group)
-    return dict(
+    plan = dict(
         n_groups=n_groups, group_size=group_size, sig_size=K, n_segments=n_seg, chain=chain,
-        boxes=boxes, ops=ops,
-        events=np.array(events, dtype=np.uint32),
-        visit_off=np.array(visit_off, dtype=np.int32), op_off=np.array(op_off, dtype=np.int32),
-        ev_off=np.array(ev_off, dtype=np.int32),
-        table=table, n_entries=int(len(ops)) * SL, op_slice=op_slice, op_group=op_group,
-        n_real_ops=int((op_group >= 0).sum()),
+        boxes=np.array(boxes, dtype=np.uint32),
+        visit_off=np.array(visit_off, dtype=np.int32),
+        n_real_ops=sum(int((np.array(op_group[p]) >= 0).sum()) for p in range(2)),
+        n_entries=sum(len(ops[p]) for p in range(2)) * SL,
     )
+    for p in range(2):
+        sl_p = np.array(op_slice[p], dtype=np.int64)
+        gr_p = np.array(op_group[p], dtype=np.int64)
+        plan[f'ops{p}'] = np.array(ops[p], dtype=np.uint32)
+        plan[f'events{p}'] = np.array(events[p], dtype=np.uint32)
+        plan[f'op_off{p}'] = np.array(op_off[p], dtype=np.int32)
+        plan[f'ev_off{p}'] = np.array(ev_off[p], dtype=np.int32)
+        plan[f'op_slice{p}'] = sl_p
+        plan[f'op_group{p}'] = gr_p
+        plan[f'table{p}'] = _table_image(flat, group_size, sl_p, gr_p)
+    return plan
 
 
 def _table_image(flat, group_size, op_slice, op_group):
@@ -301,77 +323,89 @@ def emulate(plan, tile):
     F = tile.shape[0]
     G, gs = plan['n_groups'], plan['group_size']
     out = np.zeros((F, G, 2 * gs), dtype=np.float64)
-    w = unswizzle_table(plan['table']).astype(np.float64)
-    w = w[:, :HR] + w[:, HR:]                                        # (stages, HR, 4, 8)
     written = np.zeros(G, dtype=np.int64)
-    for s in range(plan['n_segments']):
-        bufs = np.zeros((NBUF, F, HR))
-        busy = [False] * NBUF
-        uses = [0] * NBUF
-        acc = np.zeros((2, 2, F, HR))
-        slot_owner = [[None, None], [None, None]]
-        evs = list(plan['events'][plan['ev_off'][s]:plan['ev_off'][s + 1]])
-        v = plan['visit_off'][s] - 1
-        px0 = mask = 0
-        open_groups = {}
-        for i in range(plan['op_off'][s], plan['op_off'][s + 1]):
-            word = int(plan['ops'][i])
-            if (word & OP_NOP) == OP_NOP:
-                assert word == OP_NOP
-                continue
-            g = int(plan['op_group'][i])
-            dummy = g == -2
-            if word & OP_NEW_BOX:
-                v += 1
-                px0, mask = int(plan['boxes'][v]) & ~31, int(plan['boxes'][v]) & 15
-            j = (word >> OP_SLICE_SHIFT) & 3
-            assert mask >> j & 1                   # the converters fill only the masked slices
-            assert px0 + j * SL == plan['op_slice'][i] * SL
-            b = word & 7
-            assert ((word >> OP_OWNER_SHIFT) & 1) == (1 if b >= NBUF // 2 else 0)
-            if dummy:
-                ev = int(evs.pop(0))
-                assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
-                assert (ev & 7) == b and not ev & EV_LAST
-                assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1) == ((ev >> EV_PARITY_SHIFT) & 1)
-                assert not np.any(w[i // STAGE_OPS, :, i % STAGE_OPS])
-                uses[b] += 1
-                continue
-            assert ((word >> OP_OWNER_SHIFT) & 1) == (g & 1)
-            x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)    # (F, 8)
-            prod = x @ w[i // STAGE_OPS, :, i % STAGE_OPS].T                   # (F, HR)
-            if word & OP_FIRST:
-                assert not busy[b] and g not in open_groups
-                assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1)
-                busy[b] = True
-                open_groups[g] = b
-                bufs[b] = prod
-            else:
-                assert busy[b] and open_groups[g] == b
-                bufs[b] += prod
-            assert len(open_groups) <= W_LIVE
-            assert max(open_groups) - min(open_groups) < W_LIVE
-            if word & OP_COMMIT:
-                p = g & 1
-                ev = int(evs.pop(0))
-                assert (ev & 7) == b and (ev >> 8) == g
-                assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses[b] & 1)
-                uses[b] += 1
-                slot = 1 if ev & EV_SLOT else 0
-                assert slot == ((g >> 1) & 1)
-                assert slot_owner[p][slot] in (None, g)
-                slot_owner[p][slot] = g
-                acc[p, slot] += bufs[b]
-                busy[b] = False
-                del open_groups[g]
-                if ev & EV_LAST:
-                    out[:, g] += acc[p, slot][:, :2 * gs]
-                    written[g] += 1
-                    acc[p, slot] = 0
-                    slot_owner[p][slot] = None
-        assert v == plan['visit_off'][s + 1] - 1
-        assert not any(busy) and not evs and not open_groups
-        assert not any(u & 1 for u in uses)
-        assert slot_owner == [[None, None], [None, None]]
+    for p in range(2):
+        w = unswizzle_table(plan[f'table{p}']).astype(np.float64)
+        w = w[:, :HR] + w[:, HR:]                                    # (stages, HR, 4, 8)
+        ops, events = plan[f'ops{p}'], plan[f'events{p}']
+        for s in range(plan['n_segments']):
+            v0, v1 = plan['visit_off'][s], plan['visit_off'][s + 1]
+            assert (v1 - v0) % BOX_PAD == 0
+            bufs = np.zeros((NBUF, F, HR))
+            busy = [False] * NBUF
+            uses = [0] * NBUF
+            acc = np.zeros((2, F, HR))
+            slot_owner = [None, None]
+            evs = list(events[plan[f'ev_off{p}'][s]:plan[f'ev_off{p}'][s + 1]])
+            b_i = -1                                   # box of the segment
+            in_box = False
+            open_groups = {}
+            o0, o1 = plan[f'op_off{p}'][s], plan[f'op_off{p}'][s + 1]
+            assert o0 % STAGE_OPS == 0 and o1 % STAGE_OPS == 0
+            for i in range(o0, o1):
+                word = int(ops[i])
+                if word == OP_NOP:
+                    assert not in_box
+                    continue
+                if word & OP_NEW_BOX:
+                    assert not in_box
+                    b_i += 1
+                    in_box = True
+                assert in_box
+                assert ((word >> OP_ASTAGE_SHIFT) & 1) == (b_i & 1)
+                assert ((word >> OP_APARITY_SHIFT) & 1) == ((b_i >> 1) & 1)
+                box_word = int(plan['boxes'][v0 + b_i])
+                px0, mask = box_word & ~31, box_word & 15
+                if not word & OP_NOMMA:
+                    g = int(plan[f'op_group{p}'][i])
+                    j = (word >> OP_SLICE_SHIFT) & 3
+                    assert mask >> j & 1               # the converters fill only masked slices
+                    assert px0 + j * SL == plan[f'op_slice{p}'][i] * SL
+                    b = word & 7
+                    assert (b >= NBUF // 2) == bool(p)
+                    x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)
+                    prod = x @ w[i // STAGE_OPS, :, i % STAGE_OPS].T               # (F, HR)
+                    if g == -2:                        # empty chain
+                        assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
+                        assert not np.any(prod)
+                    else:
+                        assert (g & 1) == p
+                    if word & OP_FIRST:
+                        assert not busy[b] and g not in open_groups
+                        assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1)
+                        busy[b] = True
+                        open_groups[g] = b
+                        bufs[b] = prod
+                    else:
+                        assert busy[b] and open_groups[g] == b
+                        bufs[b] += prod
+                    live = [q for q in open_groups if q >= 0]
+                    assert len(live) <= W_LIVE // 2
+                    if word & OP_COMMIT:
+                        ev = int(evs.pop(0))
+                        assert (ev & 7) == b
+                        assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses[b] & 1)
+                        uses[b] += 1
+                        busy[b] = False
+                        del open_groups[g]
+                        if g == -2:
+                            assert not ev & EV_LAST
+                        else:
+                            assert (ev >> 8) == g
+                            slot = 1 if ev & EV_SLOT else 0
+                            assert slot == ((g >> 1) & 1)
+                            assert slot_owner[slot] in (None, g)
+                            slot_owner[slot] = g
+                            acc[slot] += bufs[b]
+                            if ev & EV_LAST:
+                                out[:, g] += acc[slot][:, :2 * gs]
+                                written[g] += 1
+                                acc[slot] = 0
+                                slot_owner[slot] = None
+                if word & OP_END_BOX:
+                    in_box = False
+            assert b_i == v1 - v0 - 1 and not in_box
+            assert not any(busy) and not evs and not open_groups
+            assert not any(u & 1 for u in uses) and slot_owner == [None, None]
     assert written.max() <= 2
     return (out[..., 0::2] + 1j * out[..., 1::2]).reshape(F, G * gs)
