@@ -277,7 +277,10 @@ LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, in
  * 128 frames and are final: the kernel only shifts and masks their words.
  *   boxes   (n_visits) uint32: first pixel of the box (multiple of 32) | 4-bit mask of the
  *           8-pixel slices in use; a multiple of 4 visits per segment;
- *   ops_k   uint32 per op of pipeline k in walk order (a multiple of 4 per segment): bits 0-2
+ *   ops_c   uint32 lists of the four MMA issuers c = group id % 4 (issuers c and c + 2 share
+ *           pipeline c % 2); a list is aligned with the op stream of its pipeline (walk order,
+ *           a multiple of 4 per segment) and holds the issuer's own ops, empty words (bit 7)
+ *           for the other issuer's, and ITS box hand-over flags: bits 0-2
  *           accumulator buffer, 3 / 4 first / last op of an accumulation chain, 5 / 6 first /
  *           last word of the pipeline in its box, 7 no tensor work (marker of a box without
  *           ops of the pipeline, padding), 8-9 slice of the box, 10 mbarrier parity of the
@@ -296,7 +299,8 @@ LTB_API size_t ltb200_group_masks_walk_workspace(int64_t n_frames, int n_groups,
                                                  int accumulate);
 LTB_API int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int64_t sig_size,
                                     int64_t ld_tile, const uint32_t* boxes, const uint32_t* ops0,
-                                    const uint32_t* ops1, const uint32_t* events0,
+                                    const uint32_t* ops1, const uint32_t* ops2,
+                                    const uint32_t* ops3, const uint32_t* events0,
                                     const uint32_t* events1, const float* table0,
                                     const float* table1, const int32_t* seg_off_host,
                                     int n_segments, int n_groups, int n_pairs, float* out,

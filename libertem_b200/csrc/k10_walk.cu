@@ -16,7 +16,7 @@
 // groups of even and odd id are two independent pipelines (MMA issuer warp, accumulator
 // buffers, drain warps, weight-table stream) that share only the boxes and their A stages.
 //
-// 20 warps:
+// 24 warps (22 with a role):
 //   * warps 0..7   converters: thread <-> frame row (TMEM lane); the slices of a box alternate
 //     between the two sets of 4 warps: two LDS.128 of the row's 32 bytes, hi/lo split (hi = top
 //     19 bits, lo = x - hi rounded to TF32), tcgen05.st of both into the box's A-operand stage
@@ -24,10 +24,10 @@
 //   * warps 8..15  accumulator drain: chain totals (TMEM) -> float32 registers; groups of even
 //     / odd id go to warps 8..11 / 12..15, each thread keeps two groups (window of 4); the last
 //     chain of a group writes the result row;
-//   * warp 16      box producer (TMA, frame stream, evict_first) + work-item fetch;
-//   * warp 17      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops of a
+//   * warp 20      box producer (TMA, frame stream, evict_first) + work-item fetch;
+//   * warp 21      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops of a
 //     pipeline (the tables are stored as the byte image of the swizzled stage), two rings of 4;
-//   * warps 18, 19 MMA issuers (even / odd pipeline): per op three tcgen05.mma.kind::tf32 of
+//   * warps 16..19 MMA issuers (groups g % 4; two per pipeline): per op three tcgen05.mma.kind::tf32 of
 //     M 128, N 64, K 8 into the op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi;
 //     the table rows are [hi(0..55) | lo(0..55)], the lo product reads rows 56..119).
 // TMEM: 6 accumulator buffers of 64 columns (pool; chains of <= 8 ops, the float32 accumulate
@@ -50,7 +50,7 @@ constexpr int K10_ACC_COLS = 64;
 constexpr int K10_A_BASE = K10_NBUF * K10_ACC_COLS;   // 384
 constexpr int K10_QLEN = 4;
 constexpr int K10_MAXSEG = 8;
-constexpr int K10_THREADS = 640;
+constexpr int K10_THREADS = 768;                  // 24 warps (22 with a role)
 constexpr int K10_TMEM_COLS = 512;
 
 constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4,
@@ -65,7 +65,7 @@ constexpr int K10_EV_PARITY_SHIFT = 5;
 
 struct K10Params {
     const uint32_t* boxes;         // per visit: first pixel | slice mask (low 4 bits)
-    const uint32_t* ops[2];        // per pipeline: one word per op / marker
+    const uint32_t* ops[4];        // per MMA issuer (g % 4): aligned with its pipeline's stream
     const uint32_t* events[2];     // per pipeline: one word per chain
     const float* table[2];         // per pipeline: (n_ops / 4) stage images of K10_TAB_BYTES
     int visit_off[K10_MAXSEG + 1]; // multiples of 4 visits per segment
@@ -228,7 +228,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    constexpr int DRAIN_WARP0 = 8, DATA_WARP = 16, TABLE_WARP = 17, MMA_WARP = 18;   // + 19
+    constexpr int DRAIN_WARP0 = 8, MMA_WARP = 16, DATA_WARP = 20, TABLE_WARP = 21;   // MMA: 16..19
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K10_DSTAGES; s++) {
@@ -237,11 +237,11 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         }
         for (int s = 0; s < 2 * K10_TSTAGES; s++) {
             mbar_init(&tab_full[s], 1);
-            mbar_init(&tab_free[s], 1);
+            mbar_init(&tab_free[s], 2);                // the two issuers of the pipeline
         }
         for (int s = 0; s < K10_AS; s++) {
             mbar_init(&a_full[s], 8);                  // converter warps
-            mbar_init(&mma_done[s], 2);                // both MMA warps
+            mbar_init(&mma_done[s], 4);                // the four MMA issuers
         }
         for (int s = 0; s < K10_NBUF; s++) {
             mbar_init(&acc_full[s], 1);
@@ -249,7 +249,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         }
         for (int s = 0; s < K10_QLEN; s++) {
             mbar_init(&q_full[s], 1);
-            mbar_init(&q_free[s], 11);                 // table warp, 2 MMA warps, 8 drain warps
+            mbar_init(&q_free[s], 13);                 // table warp, 4 MMA warps, 8 drain warps
         }
         fence_mbar_init();
     }
@@ -274,7 +274,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 
     if (warp < DRAIN_WARP0) {
         // ===== converters =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const int set = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
@@ -358,11 +358,11 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             if (lane == 0) mbar_arrive(&a_full[ast]);
             nbox++;
         }
-    } else if (warp < DATA_WARP) {
+    } else if (warp < MMA_WARP) {
         // ===== accumulator drain =====
-        // the CTA owns 640 x 96 registers: 8 x 32 x 152 here + 8 x 32 x 64 (converters) +
-        // 4 x 32 x 40 (producers, MMA) = 60 416 <= 61 440
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // the CTA owns 768 x 80 = 61 440 registers (what the launch allocates: see -Xptxas -v):
+        // 8 x 32 x 144 here + 8 x 32 x 56 (converters) + 8 x 32 x 40 (warps 16..23)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int grp = (warp - DRAIN_WARP0) >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
@@ -456,6 +456,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             }
         }
     } else {
+        // (whole warpgroups 16..19 and 20..23: setmaxnreg is a warpgroup-wide instruction)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == DATA_WARP) {
             // ===== box producer + work-item fetch =====
@@ -531,22 +532,26 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     }
                 }
             }
-        } else {
-            // ===== MMA issuers (one per pipeline; warp-uniform loop, one elected lane issues)
+        } else if (warp < DATA_WARP) {
+            // ===== MMA issuers (two per pipeline: groups g % 4 = warp - 16; warp-uniform loop,
+            // one elected lane issues) -- each walks the whole op stream of its pipeline (its
+            // list has empty words for the other issuer's ops) and both release every table
+            // stage; all four release every A stage
             // One op = 96 tensor-pipe cycles and a single thread retires an instruction every
             // 6-8 cycles here (profiles/r2_k10_*), so the issue loop must be short: every word
             // of the list is final (buffer, A stage, parities are static), four words (one
             // table stage) per round, the words of the next round are shuffled out while this
             // one runs, the descriptor is a running 32-bit half.
-            const int me = warp - MMA_WARP;
+            const int me = warp - MMA_WARP;             // issuer 0..3
+            const int pipe = me & 1;
             constexpr uint32_t IDESC = k10_idesc_tf32(K10_ACC_COLS);
             const uint32_t tb0 =
-                smem_u32(smem + K10Smem::TABLE_OFF + (size_t)me * K10_TSTAGES * K10_TAB_STRIDE);
+                smem_u32(smem + K10Smem::TABLE_OFF + (size_t)pipe * K10_TSTAGES * K10_TAB_STRIDE);
             const uint32_t desc_hi32 = (uint32_t)(k10_desc_k_sw128(0) >> 32);
             const uint32_t desc_lo0 = (uint32_t)k10_desc_k_sw128(tb0);
             constexpr uint32_t DESC_STAGE = K10_TAB_STRIDE >> 4, DESC_LO_HALF = (K10_HR * 128) >> 4;
-            uint64_t* my_tab_full = tab_full + me * K10_TSTAGES;
-            uint64_t* my_tab_free = tab_free + me * K10_TSTAGES;
+            uint64_t* my_tab_full = tab_full + pipe * K10_TSTAGES;
+            uint64_t* my_tab_free = tab_free + pipe * K10_TSTAGES;
             const uint32_t* __restrict__ ops = p.ops[me];
             const uint32_t a_base = tmem_base + (uint32_t)K10_A_BASE;
             uint32_t desc_lo = desc_lo0;                // table stage `ts`, rows 0.., op 0
@@ -559,7 +564,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_free[q]);
                 if (qi.item < 0) break;
-                const int o0 = p.op_off[me][qi.seg], o1 = p.op_off[me][qi.seg + 1];
+                const int o0 = p.op_off[pipe][qi.seg], o1 = p.op_off[pipe][qi.seg + 1];
                 uint32_t w_next = o0 + lane < o1 ? ops[o0 + lane] : K10_OP_NOMMA;
                 for (int base = o0; base < o1; base += 32) {
                     const uint32_t w = w_next;
@@ -582,13 +587,13 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                             for (int sub = 0; sub < 4; sub++) {
                                 const uint32_t o = op[sub];
                                 const uint32_t ast = (o >> K10_OP_ASTAGE_SHIFT) & 1u;
-                                if (o & K10_OP_NEW) {
+                                if (__builtin_expect((o & K10_OP_NEW) != 0, 0)) {
                                     mbar_wait(&a_full[ast], (o >> K10_OP_APARITY_SHIFT) & 1u);
                                     k10_fence_after();
                                 }
-                                if (!(o & K10_OP_NOMMA)) {
+                                if (__builtin_expect(!(o & K10_OP_NOMMA), 1)) {
                                     const uint32_t buf = o & 7u;
-                                    if (o & K10_OP_FIRST) {
+                                    if (__builtin_expect((o & K10_OP_FIRST) != 0, 0)) {
                                         mbar_wait(&acc_free[buf],
                                                   ((o >> K10_OP_PARITY_SHIFT) & 1u) ^ 1u);
                                         k10_fence_after();
@@ -662,6 +667,7 @@ extern "C" size_t ltb200_group_masks_walk_workspace(int64_t n_frames, int n_grou
 extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int64_t sig_size,
                                        int64_t ld_tile, const uint32_t* boxes,
                                        const uint32_t* ops0, const uint32_t* ops1,
+                                       const uint32_t* ops2, const uint32_t* ops3,
                                        const uint32_t* events0, const uint32_t* events1,
                                        const float* table0, const float* table1,
                                        const int32_t* seg_off_host,
@@ -674,7 +680,7 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     LTB_REQUIRE(n_segments >= 1 && n_segments <= K10_MAXSEG,
                 "group_masks_walk: 1..%d segments", K10_MAXSEG);
     if (n_frames == 0) return LTB_OK;
-    LTB_REQUIRE(tile && boxes && ops0 && ops1 && events0 && events1 && table0 && table1 &&
+    LTB_REQUIRE(tile && boxes && ops0 && ops1 && ops2 && ops3 && events0 && events1 && table0 && table1 &&
                     seg_off_host && out,
                 "group_masks_walk: NULL pointer");
     LTB_REQUIRE(sig_size % 32 == 0 && sig_size < (1ll << 31),
@@ -693,6 +699,8 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     p.boxes = boxes;
     p.ops[0] = ops0;
     p.ops[1] = ops1;
+    p.ops[2] = ops2;
+    p.ops[3] = ops3;
     p.events[0] = events0;
     p.events[1] = events1;
     p.table[0] = table0;

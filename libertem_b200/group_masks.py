@@ -318,7 +318,7 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
             plan.walk = dict(
                 n_segments=w['n_segments'], n_entries=w['n_entries'],
                 boxes=dev_u32(w['boxes']),
-                ops=[dev_u32(w['ops0']), dev_u32(w['ops1'])],
+                ops=[dev_u32(w[f'ops{c}']) for c in range(4)],
                 events=[dev_u32(w['events0']), dev_u32(w['events1'])],
                 table=[torch.from_numpy(w['table0']).to(device),
                        torch.from_numpy(w['table1']).to(device)],
@@ -394,7 +394,8 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
         with torch.cuda.device(tile.device):
             check(lib.ltb200_group_masks_walk(
                 tile.data_ptr(), F, K, ld_tile, w['boxes'].data_ptr(), w['ops'][0].data_ptr(),
-                w['ops'][1].data_ptr(), w['events'][0].data_ptr(), w['events'][1].data_ptr(),
+                w['ops'][1].data_ptr(), w['ops'][2].data_ptr(), w['ops'][3].data_ptr(),
+                w['events'][0].data_ptr(), w['events'][1].data_ptr(),
                 w['table'][0].data_ptr(), w['table'][1].data_ptr(),
                 w['seg_off_host'].ctypes.data,
                 w['n_segments'], plan.n_groups, plan.n_pairs, real.data_ptr(), ld_out,

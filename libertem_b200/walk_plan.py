@@ -22,7 +22,8 @@ only the boxes and their A-operand stages:
 * ``boxes``   -- per visit: first pixel of the box | 4-bit mask of the slices that are used;
   every segment holds a multiple of 4 visits (padded with empty ones), so that the A stage and
   the mbarrier parity of a box are static;
-* ``ops[p]``  -- per op of pipeline p, in walk order: accumulator buffer, first / last op of an
+* ``ops[c]``  -- per issuer warp c = g % 4 (two per pipeline), a list aligned with the op
+  stream of its pipeline (own ops, empty words for the other issuer's); per op, in walk order: accumulator buffer, first / last op of an
   accumulation chain (+ the static mbarrier parity), slice and A stage of the box, first / last
   op of the pipeline in its box (A-stage hand-over with the converter warps; a box without ops
   of the pipeline gets an empty marker word);
@@ -167,7 +168,7 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
     n_seg = len(bounds) - 1
 
     boxes = []
-    ops = ([], [])                 # per pipeline
+    ops = ([], [], [], [])         # per issuer (g % 4): aligned with its pipeline's stream
     op_slice = ([], [])            # global slice index of every word (-1: no weights)
     op_group = ([], [])            # group of every word (-1 marker / padding, -2 empty chain)
     events = ([], [])
@@ -233,7 +234,12 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                                        ((uses[b] & 1) << OP_PARITY_SHIFT), b_i, j, -2])
                     events[par].append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
                     uses[b] += 1
-        # per pipeline: box hand-over flags; a box without ops of the pipeline gets a marker
+        # per pipeline: the op stream (= table slot order); a box without ops of the pipeline
+        # gets a marker slot.  Per ISSUER (two per pipeline, groups g % 4 = par and par + 2):
+        # a word list aligned with the stream -- its own ops, empty words for the other
+        # issuer's -- with ITS box hand-over flags (wait for the converters before its first
+        # op of a box, release the A stage after its last one; in a box without own ops both
+        # flags sit on the first word of the box)
         for par in range(2):
             by_box = {}
             for w in words[par]:
@@ -242,19 +248,29 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                 ws = by_box.get(b_i)
                 if not ws:
                     ws = [[OP_NOMMA, b_i, 0, -1]]
-                ws[0][0] |= OP_NEW_BOX
-                ws[-1][0] |= OP_END_BOX
+                stage_bits = ((b_i & 1) << OP_ASTAGE_SHIFT) | (((b_i >> 1) & 1) << OP_APARITY_SHIFT)
+                for k in range(2):
+                    cls = par + 2 * k
+                    own = [n for n, w in enumerate(ws)
+                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 and k == 0]
+                    first, last = (own[0], own[-1]) if own else (0, 0)
+                    for n, w in enumerate(ws):
+                        word = (w[0] if n in own else OP_NOMMA) | stage_bits
+                        if n == first:
+                            word |= OP_NEW_BOX
+                        if n == last:
+                            word |= OP_END_BOX
+                        ops[cls].append(word)
                 for w in ws:
-                    w[0] |= ((b_i & 1) << OP_ASTAGE_SHIFT) | (((b_i >> 1) & 1) << OP_APARITY_SHIFT)
-                    ops[par].append(w[0])
                     op_group[par].append(w[3])
                     op_slice[par].append(
                         (seg_boxes[b_i] & ~31) // SL + w[2] if w[3] != -1 else -1)
-            while len(ops[par]) % STAGE_OPS:
-                ops[par].append(OP_NOP)
+            while len(op_group[par]) % STAGE_OPS:
+                for k in range(2):
+                    ops[par + 2 * k].append(OP_NOP)
                 op_group[par].append(-1)
                 op_slice[par].append(-1)
-            op_off[par].append(len(ops[par]))
+            op_off[par].append(len(op_group[par]))
             ev_off[par].append(len(events[par]))
         boxes.extend(seg_boxes)
         visit_off.append(len(boxes))
@@ -264,12 +280,13 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
         boxes=np.array(boxes, dtype=np.uint32),
         visit_off=np.array(visit_off, dtype=np.int32),
         n_real_ops=sum(int((np.array(op_group[p]) >= 0).sum()) for p in range(2)),
-        n_entries=sum(len(ops[p]) for p in range(2)) * SL,
+        n_entries=sum(len(op_group[p]) for p in range(2)) * SL,
     )
     for p in range(2):
         sl_p = np.array(op_slice[p], dtype=np.int64)
         gr_p = np.array(op_group[p], dtype=np.int64)
-        plan[f'ops{p}'] = np.array(ops[p], dtype=np.uint32)
+        for k in range(2):
+            plan[f'ops{p + 2 * k}'] = np.array(ops[p + 2 * k], dtype=np.uint32)
         plan[f'events{p}'] = np.array(events[p], dtype=np.uint32)
         plan[f'op_off{p}'] = np.array(op_off[p], dtype=np.int32)
         plan[f'ev_off{p}'] = np.array(ev_off[p], dtype=np.int32)
@@ -317,6 +334,39 @@ def unswizzle_table(table):
     return t[:, np.arange(STAGE_ROWS)[:, None], chunk].reshape(n_stages, STAGE_ROWS, STAGE_OPS, SL)
 
 
+def _merge_issuers(plan, p):
+    """the op stream of pipeline p from its two issuer lists (checks their box flags)"""
+    a, b = plan[f'ops{p}'].astype(np.int64), plan[f'ops{p + 2}'].astype(np.int64)
+    assert len(a) == len(b) == len(plan[f'op_group{p}'])
+    own_a, own_b = (a & OP_NOMMA) == 0, (b & OP_NOMMA) == 0
+    assert not np.any(own_a & own_b)
+    g = plan[f'op_group{p}']
+    assert np.all((g[own_a] & 3) == p) or np.all((g[own_a][g[own_a] >= 0] & 3) == p)
+    assert np.all((g[own_b] & 3) == p + 2)
+    stage_mask = (1 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
+    real = (a != OP_NOP) | (b != OP_NOP)
+    assert np.all((a & stage_mask)[real] == (b & stage_mask)[real])
+    merged = np.where(own_b, b, a) & ~(OP_NEW_BOX | OP_END_BOX)
+    # per issuer: exactly one NEW and one END per box, NEW not after its first own op, END not
+    # before its last one; the stream's box boundaries = where the A stage / parity bits change
+    key = (a & stage_mask)
+    box_id = np.concatenate([[0], np.cumsum(key[1:] != key[:-1])])
+    box_id[~real] = -1
+    for lst, own in ((a, own_a), (b, own_b)):
+        for bid in np.unique(box_id[box_id >= 0]):
+            idx = np.nonzero(box_id == bid)[0]
+            new = idx[(lst[idx] & OP_NEW_BOX) != 0]
+            end = idx[(lst[idx] & OP_END_BOX) != 0]
+            assert len(new) == 1 and len(end) == 1 and new[0] <= end[0]
+            mine = idx[own[idx]]
+            if len(mine):
+                assert new[0] <= mine[0] and end[0] >= mine[-1]
+    first = np.concatenate([[True], box_id[1:] != box_id[:-1]]) & real
+    last = np.concatenate([box_id[1:] != box_id[:-1], [True]]) & real
+    merged = merged | np.where(first, OP_NEW_BOX, 0) | np.where(last, OP_END_BOX, 0)
+    return merged
+
+
 def emulate(plan, tile):
     """numpy model of what the kernel does with the lists (float64 arithmetic; checks the
     invariants the kernel relies on).  tile: (F, K) -> (F, n_groups * group_size) complex128"""
@@ -327,7 +377,7 @@ def emulate(plan, tile):
     for p in range(2):
         w = unswizzle_table(plan[f'table{p}']).astype(np.float64)
         w = w[:, :HR] + w[:, HR:]                                    # (stages, HR, 4, 8)
-        ops, events = plan[f'ops{p}'], plan[f'events{p}']
+        ops, events = _merge_issuers(plan, p), plan[f'events{p}']
         for s in range(plan['n_segments']):
             v0, v1 = plan['visit_off'][s], plan['visit_off'][s + 1]
             assert (v1 - v0) % BOX_PAD == 0
@@ -344,8 +394,9 @@ def emulate(plan, tile):
             assert o0 % STAGE_OPS == 0 and o1 % STAGE_OPS == 0
             for i in range(o0, o1):
                 word = int(ops[i])
-                if word == OP_NOP:
-                    assert not in_box
+                if (word & ~((1 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT))) == OP_NOP \
+                        and plan[f'op_group{p}'][i] == -1 and not in_box \
+                        and not word & (OP_NEW_BOX | OP_END_BOX):
                     continue
                 if word & OP_NEW_BOX:
                     assert not in_box
