@@ -286,7 +286,8 @@ LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, in
  *           ops of the pipeline, padding), 8-9 slice of the box, 10 mbarrier parity of the
  *           buffer (first op), 11 A stage of the box, 12 mbarrier parity of the A stage;
  *   events_k uint32 per accumulation chain of pipeline k: bits 0-2 buffer, 3 register slot,
- *           4 last chain of the group in this segment, 5 mbarrier parity, 8.. group id;
+ *           4 last chain of the group in this segment, 5 mbarrier parity, 6 which issuer of
+ *           the pipeline uses the buffer next, 8.. group id;
  *   table_k (n_ops_k / 4, 112, 32) float32: per 4 ops the byte image of a shared-memory stage:
  *           rows [hi(c) | lo(c)], c = 2 * pair + {0 re, 1 im} < 56, the 8 weights of op j at
  *           floats [8 j, 8 j + 8) of a row, 16-byte chunks XOR-swizzled with (row & 7);

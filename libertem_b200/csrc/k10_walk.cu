@@ -57,11 +57,12 @@ constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4,
                    K10_OP_NEW = 1u << 5, K10_OP_END = 1u << 6,   // first / last word in a box
                    K10_OP_NOMMA = 1u << 7;                       // marker / padding
 constexpr int K10_OP_SLICE_SHIFT = 8;            // bits 8-9: slice of the box
-constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: parity of the buffer's use count
+constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: mbarrier parity of the wait for the drain
 constexpr int K10_OP_ASTAGE_SHIFT = 11;          // A stage of the box
 constexpr int K10_OP_APARITY_SHIFT = 12;         // mbarrier parity of the A stage
 constexpr uint32_t K10_EV_SLOT = 1u << 3, K10_EV_LAST = 1u << 4;
 constexpr int K10_EV_PARITY_SHIFT = 5;
+constexpr int K10_EV_NEXT_SHIFT = 6;             // issuer of the pipeline that uses the buffer next
 
 struct K10Params {
     const uint32_t* boxes;         // per visit: first pixel | slice mask (low 4 bits)
@@ -219,8 +220,8 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
     uint64_t* a_full = tab_free + 2 * K10_TSTAGES;                                // [AS]
     uint64_t* mma_done = a_full + K10_AS;                                         // [AS]
     uint64_t* acc_full = mma_done + K10_AS;                                       // [NBUF]
-    uint64_t* acc_free = acc_full + K10_NBUF;                                     // [NBUF]
-    uint64_t* q_full = acc_free + K10_NBUF;                                       // [QLEN]
+    uint64_t* acc_free = acc_full + K10_NBUF;                                     // [NBUF][2]
+    uint64_t* q_full = acc_free + 2 * K10_NBUF;                                   // [QLEN]
     uint64_t* q_free = q_full + K10_QLEN;                                         // [QLEN]
     int* meta = reinterpret_cast<int*>(q_free + K10_QLEN);                        // [DSTAGES]
     K10QItem* queue = reinterpret_cast<K10QItem*>(meta + 8);                      // [QLEN]
@@ -245,7 +246,12 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         }
         for (int s = 0; s < K10_NBUF; s++) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_free[s], 4);                // the 4 warps of a drain group
+            // "drained": one barrier per buffer and WAITING issuer of the pipeline (the two
+            // issuers share the pool and can be a short chain apart: on a common barrier the
+            // parity of one's wait could be satisfied by the other's phase).  The drain of a
+            // chain arrives on the barrier of the issuer that uses the buffer next.
+            mbar_init(&acc_free[2 * s], 4);            // the 4 warps of a drain group
+            mbar_init(&acc_free[2 * s + 1], 4);
         }
         for (int s = 0; s < K10_QLEN; s++) {
             mbar_init(&q_full[s], 1);
@@ -427,7 +433,8 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     }
                     k10_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_free[buf]);
+                    if (lane == 0)
+                        mbar_arrive(&acc_free[2 * buf + ((ev >> K10_EV_NEXT_SHIFT) & 1u)]);
                     if (ev & K10_EV_LAST) {
                         // the group's sum over this segment is complete: write the row
                         float* o = p.out + f * p.ld_out + (int64_t)g * p.n_cols;
@@ -594,8 +601,8 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                                 if (__builtin_expect(!(o & K10_OP_NOMMA), 1)) {
                                     const uint32_t buf = o & 7u;
                                     if (__builtin_expect((o & K10_OP_FIRST) != 0, 0)) {
-                                        mbar_wait(&acc_free[buf],
-                                                  ((o >> K10_OP_PARITY_SHIFT) & 1u) ^ 1u);
+                                        mbar_wait(&acc_free[2 * buf + (uint32_t)(me >> 1)],
+                                                  (o >> K10_OP_PARITY_SHIFT) & 1u);
                                         k10_fence_after();
                                     }
                                     const uint32_t d = tmem_base + buf * K10_ACC_COLS;

@@ -60,7 +60,8 @@ OP_NEW_BOX = 1 << 5     # first word of the pipeline in its box: wait for the co
 OP_END_BOX = 1 << 6     # last word of the pipeline in its box: release the A stage
 OP_NOMMA = 1 << 7       # marker / padding: no tensor work
 OP_SLICE_SHIFT = 8      # bits 8-9: slice of the box
-OP_PARITY_SHIFT = 10    # first op of a chain: parity of the buffer's use count in the segment
+OP_PARITY_SHIFT = 10    # first op of a chain: mbarrier parity of the issuer's wait for the drain
+#                         of the buffer's previous chain
 OP_ASTAGE_SHIFT = 11    # A stage of the box (box index & 1)
 OP_APARITY_SHIFT = 12   # mbarrier parity of the A stage ((box index >> 1) & 1)
 OP_NOP = OP_NOMMA       # padding word
@@ -68,6 +69,7 @@ OP_NOP = OP_NOMMA       # padding word
 EV_SLOT = 1 << 3
 EV_LAST = 1 << 4
 EV_PARITY_SHIFT = 5     # parity of the buffer's use count in the segment
+EV_NEXT_SHIFT = 6       # which issuer of the pipeline (0 / 1) uses the buffer next
 BOX_PAD = 4             # visits per segment are padded to a multiple of this
 
 def tf32_round(a):
@@ -137,10 +139,16 @@ def _segment_bounds(key, n_ops_visit, n_segments):
     return bounds
 
 
-def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
+def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_per_slice=2):
     """flat: (M, K) complex stack, M = n_groups * group_size.  Returns the plan as a dict of
-    numpy arrays or None when the stack does not fit this form (K % 32, group_size > HR / 2, or
-    boxes that would have to be visited more than ``max_dup`` times on average)."""
+    numpy arrays or None when the stack does not fit this form: K % 32, group_size > HR / 2,
+    boxes that would have to be visited more than ``max_dup`` times on average (groups narrower
+    than a quarter of a box), or more than ``max_per_slice`` groups on one 8-pixel slice.  The
+    defaults admit what the kernel is validated for on hardware -- every box visited once, at
+    most two (adjacent) groups per slice, i.e. rings at least ~11 pixels wide; generic stacks
+    (``max_dup=inf, max_per_slice=inf``) are handled by the same lists and pass the numerical
+    tests, but one narrow-ring geometry showed a rare data race under stress (NEXT.md), so
+    such stacks stay on K7."""
     M, K = flat.shape
     if group_size < 1 or M % group_size or K % BOX or 2 * group_size > HR or K >= (1 << 31):
         return None
@@ -158,12 +166,16 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
         return None
     if n_visits > max_dup * max(1, int(bx.any(axis=0).sum())):
         return None
+    if int(sl.sum(axis=0).max()) > max_per_slice:
+        return None
     sl4 = sl.reshape(n_groups, K // BOX, BOX // SL)
     n_ops_visit = np.zeros(n_visits, dtype=np.int64)
     for v in range(n_visits):
         n_ops_visit[v] = sl4[lo[v]:hi[v] + 1, box[v]].sum()
     if n_segments is None:
-        n_segments = max(1, min(MAX_SEGMENTS, n_groups // W_LIVE))
+        import os
+        n_segments = int(os.environ.get('LTB200_K10_SEGS', 0)) or \
+            max(1, min(MAX_SEGMENTS, n_groups // W_LIVE))
     bounds = _segment_bounds(key, n_ops_visit, n_segments)
     n_seg = len(bounds) - 1
 
@@ -193,47 +205,78 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
         last_op_of_group = {}
         for i, e in enumerate(seq):
             last_op_of_group[e[2]] = i
-        # accumulator buffers: a pool of NBUF / 2 per pipeline, FIFO = oldest released first
+        # accumulator buffers: a pool of NBUF / 2 per pipeline, FIFO = oldest released first.
+        # The two issuers of a pipeline share its pool and may be a (short) chain apart, so the
+        # "buffer drained" barriers are per buffer AND waiting issuer: the drain of a chain
+        # arrives on the barrier of the issuer that uses the buffer NEXT (a static fact), and
+        # each barrier is waited on by one thread in a fixed order -- no parity can alias.
         free = [list(range(NBUF // 2)), list(range(NBUF // 2, NBUF))]
         uses = [0] * NBUF
+        chains = [[] for _ in range(NBUF)]         # per buffer: [issuer k, pipeline, event, word]
         open_buf, open_len = {}, {}
         words = ([], [])                           # per pipeline: [word, box, slice, group]
+
+        def empty_chain(b, k, b_i, j):
+            """a chain without weights on buffer b, issued by issuer k of its pipeline"""
+            par = 1 if b >= NBUF // 2 else 0
+            w = [(j << OP_SLICE_SHIFT) | b | OP_FIRST | OP_COMMIT, b_i, j, -2 - k]
+            words[par].append(w)
+            events[par].append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
+            chains[b].append([k, par, len(events[par]) - 1, w])
+            uses[b] += 1
+
+        if seq:
+            # every segment starts with an empty chain of issuer 0 on every buffer: the last
+            # drain of an item can then always be addressed to issuer 0
+            for b in range(NBUF):
+                empty_chain(b, 0, seq[0][0], seq[0][1])
         for i, (b_i, j, g) in enumerate(seq):
             par = g & 1
-            word = j << OP_SLICE_SHIFT
+            w = [j << OP_SLICE_SHIFT, b_i, j, g]
             if g not in open_buf:
                 if not free[par]:
                     raise AssertionError('walk plan: accumulator pool exhausted')
                 b = open_buf[g] = free[par].pop(0)
                 open_len[g] = 0
-                word |= OP_FIRST | ((uses[b] & 1) << OP_PARITY_SHIFT)
+                w[0] |= OP_FIRST
+                chains[b].append([(g >> 1) & 1, par, None, w])
                 if len(open_buf) > W_LIVE:
                     raise AssertionError('walk plan: more than W_LIVE live groups')
             b = open_buf[g]
-            word |= b
+            w[0] |= b
             open_len[g] += 1
             final = last_op_of_group[g] == i
             if open_len[g] == chain or final:
-                word |= OP_COMMIT
+                w[0] |= OP_COMMIT
                 events[par].append(b | (EV_SLOT if (g >> 1) & 1 else 0) |
                                    (EV_LAST if final else 0) |
                                    ((uses[b] & 1) << EV_PARITY_SHIFT) | (g << 8))
+                chains[b][-1][2] = len(events[par]) - 1
                 uses[b] += 1
                 free[par].append(b)
                 del open_buf[g], open_len[g]
-            words[par].append([word, b_i, j, g])
+            words[par].append(w)
         assert not open_buf
-        # every buffer is used an even number of times per segment (static mbarrier parities):
-        # an odd count gets one empty chain (zero weights) on the last op's slice
         if seq:
+            # every buffer is used an even number of times per segment by EITHER issuer of its
+            # pipeline (static mbarrier parities): odd counts get one more empty chain
             b_i, j = seq[-1][0], seq[-1][1]
             for b in range(NBUF):
-                if uses[b] & 1:
-                    par = 1 if b >= NBUF // 2 else 0
-                    words[par].append([(j << OP_SLICE_SHIFT) | b | OP_FIRST | OP_COMMIT |
-                                       ((uses[b] & 1) << OP_PARITY_SHIFT), b_i, j, -2])
-                    events[par].append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
-                    uses[b] += 1
+                for k in range(2):
+                    if sum(1 for c in chains[b] if c[0] == k) & 1:
+                        empty_chain(b, k, b_i, j)
+            for b in range(NBUF):
+                n_before = [0, 0]
+                for n, (k, par, ev, w) in enumerate(chains[b]):
+                    # the issuer's wait for "drained": the parity of the phase of ITS barrier
+                    # that the drain before this chain completes.  Issuer 0 consumes one
+                    # arrival that precedes the segment (the last drain of the previous item;
+                    # none in the first item, where the fresh barrier lets parity 1 pass)
+                    w[0] |= ((n_before[k] & 1) ^ (1 if k == 0 else 0)) << OP_PARITY_SHIFT
+                    n_before[k] += 1
+                    nxt = chains[b][n + 1][0] if n + 1 < len(chains[b]) else 0
+                    events[par][ev] |= nxt << EV_NEXT_SHIFT
+                assert chains[b][0][0] == 0 and not n_before[0] & 1 and not n_before[1] & 1
         # per pipeline: the op stream (= table slot order); a box without ops of the pipeline
         # gets a marker slot.  Per ISSUER (two per pipeline, groups g % 4 = par and par + 2):
         # a word list aligned with the stream -- its own ops, empty words for the other
@@ -252,7 +295,7 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.5):
                 for k in range(2):
                     cls = par + 2 * k
                     own = [n for n, w in enumerate(ws)
-                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 and k == 0]
+                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 - k]
                     first, last = (own[0], own[-1]) if own else (0, 0)
                     for n, w in enumerate(ws):
                         word = (w[0] if n in own else OP_NOMMA) | stage_bits
@@ -341,8 +384,8 @@ def _merge_issuers(plan, p):
     own_a, own_b = (a & OP_NOMMA) == 0, (b & OP_NOMMA) == 0
     assert not np.any(own_a & own_b)
     g = plan[f'op_group{p}']
-    assert np.all((g[own_a] & 3) == p) or np.all((g[own_a][g[own_a] >= 0] & 3) == p)
-    assert np.all((g[own_b] & 3) == p + 2)
+    assert np.all((g[own_a][g[own_a] >= 0] & 3) == p) and np.all(g[own_a][g[own_a] < 0] == -2)
+    assert np.all((g[own_b][g[own_b] >= 0] & 3) == p + 2) and np.all(g[own_b][g[own_b] < 0] == -3)
     stage_mask = (1 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
     real = (a != OP_NOP) | (b != OP_NOP)
     assert np.all((a & stage_mask)[real] == (b & stage_mask)[real])
@@ -384,6 +427,8 @@ def emulate(plan, tile):
             bufs = np.zeros((NBUF, F, HR))
             busy = [False] * NBUF
             uses = [0] * NBUF
+            uses_k = [[0, 0] for _ in range(NBUF)]
+            next_user = [0] * NBUF                     # an item starts with issuer 0 everywhere
             acc = np.zeros((2, F, HR))
             slot_owner = [None, None]
             evs = list(events[plan[f'ev_off{p}'][s]:plan[f'ev_off{p}'][s + 1]])
@@ -416,14 +461,19 @@ def emulate(plan, tile):
                     assert (b >= NBUF // 2) == bool(p)
                     x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)
                     prod = x @ w[i // STAGE_OPS, :, i % STAGE_OPS].T               # (F, HR)
-                    if g == -2:                        # empty chain
+                    if g <= -2:                        # empty chain
                         assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
                         assert not np.any(prod)
                     else:
                         assert (g & 1) == p
+                    k_iss = ((g >> 1) & 1) if g >= 0 else -2 - g      # issuer of the pipeline
                     if word & OP_FIRST:
                         assert not busy[b] and g not in open_groups
-                        assert ((word >> OP_PARITY_SHIFT) & 1) == (uses[b] & 1)
+                        assert ((word >> OP_PARITY_SHIFT) & 1) == \
+                            (uses_k[b][k_iss] & 1) ^ (1 if k_iss == 0 else 0)
+                        # the drain of the previous chain was addressed to this issuer
+                        assert next_user[b] == k_iss
+                        uses_k[b][k_iss] += 1
                         busy[b] = True
                         open_groups[g] = b
                         bufs[b] = prod
@@ -436,10 +486,11 @@ def emulate(plan, tile):
                         ev = int(evs.pop(0))
                         assert (ev & 7) == b
                         assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses[b] & 1)
+                        next_user[b] = (ev >> EV_NEXT_SHIFT) & 1
                         uses[b] += 1
                         busy[b] = False
                         del open_groups[g]
-                        if g == -2:
+                        if g <= -2:
                             assert not ev & EV_LAST
                         else:
                             assert (ev >> 8) == g
@@ -458,5 +509,7 @@ def emulate(plan, tile):
             assert b_i == v1 - v0 - 1 and not in_box
             assert not any(busy) and not evs and not open_groups
             assert not any(u & 1 for u in uses) and slot_owner == [None, None]
+            assert not any(u[0] & 1 or u[1] & 1 for u in uses_k)
+            assert all(next_user[b] == 0 for b in range(NBUF) if uses[b])
     assert written.max() <= 2
     return (out[..., 0::2] + 1j * out[..., 1::2]).reshape(F, G * gs)
