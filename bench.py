@@ -65,6 +65,7 @@ KERNEL_NAMES = {
     7: 'k7_group_tensor_kernel (tcgen05, ring-major plan)',
     70: 'k7_group_tensor_kernel (tcgen05, quad / banded plan)',
     71: 'k7_group_tensor_kernel (tcgen05, mirror-symmetric plan)',
+    10: 'k10_walk_kernel (tcgen05, dense-walk plan: TMA boxes in ring order)',
     8: 'k8_int_kernel (tcgen05 kind::i8, exact integer path)', 20: 'k2_csc_kernel',
 }
 
@@ -623,8 +624,8 @@ def config_legs(ctx):
                     workload='cfg4: %dx256 nav x 512x512 sig float32%s, RadialFourierAnalysis 32 '
                              'bins x 25 orders (800 complex masks), one partition' %
                              (nav0, '' if nav0 == 256 else ' (nav sub-sample: not enough HBM)'),
-                    bound='tensor / L2->SM fabric (group-sparse GEMM), reported against the HBM '
-                          'roofline of the frame bytes')
+                    bound='tensor pipe / A-operand hand-over (group-sparse GEMM on dense TMA '
+                          'boxes), reported against the HBM roofline of the frame bytes')
         out['cfg4'] = line
         del ds, runner, udf, a
         torch.cuda.empty_cache()

@@ -234,3 +234,85 @@ def test_masks_shifted_banded_kernel(dt, M, D):
     const = engine.masks_shifted(t, mt, torch.tensor([[3, -7]])).cpu().numpy()
     assert engine.last_kernel() == 50
     assert np.abs(const - _shifted_ref(data, masks, [(3, -7)])).max() / scale <= 2e-6
+
+
+def _radial_flat(S, n_bins, max_order, **kw):
+    from libertem_b200 import masks as M
+    from libertem_b200.analysis.radialfourier import radial_mask_factory
+    cx, cy = kw.get('cx', S / 2), kw.get('cy', S / 2)
+    ro = kw.get('ro', M.bounding_radius(cx, cy, S, S))
+    st = np.asarray(radial_mask_factory(S, S, cx, cy, kw.get('ri', 0), ro, n_bins, max_order,
+                                        use_sparse=False)())
+    return st.reshape(st.shape[0], -1).astype(np.complex64)
+
+
+@pytest.mark.parametrize('S,n_bins,max_order,F,kw', [
+    (64, 4, 6, 128, {}), (128, 8, 24, 300, {}), (128, 8, 24, 1000, {}), (256, 16, 24, 257, {}),
+    (128, 5, 12, 500, dict(cx=60.5, cy=70.25, ri=6.0, ro=50.0)), (128, 8, 7, 2000, {})])
+def test_group_masks_walk(S, n_bins, max_order, F, kw):
+    """K10 (dense-walk plan, ltb200_group_masks_walk) on the reference's radial masks: numpy
+    float64, the banded K7 plan, accumulate, strided tiles, ragged last frame block; the result
+    does not depend on the launch (atomics with <= 2 addends per element)"""
+    from libertem_b200 import engine, group_masks as gm
+    flat = _radial_flat(S, n_bins, max_order, **kw)
+    plan = gm.build_plan(flat, max_order + 1, torch.device('cuda'))
+    assert plan.walk is not None
+    data = synth.uniform_f32(0, F * S * S, 21).reshape(F, S * S)
+    t = torch.from_numpy(data).cuda()
+    out = gm.group_masks(t, plan, kernel='auto').cpu().numpy()
+    assert engine.last_kernel() == (10 if F >= gm.TC_MIN_FRAMES else 4)
+    out = gm.group_masks(t, plan, kernel='walk').cpu().numpy()
+    assert engine.last_kernel() == 10
+    ref = data.astype(np.float64) @ flat.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(flat).astype(np.float64).T).max() + 1e-30
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    assert np.abs(out - ref).max() / scale <= 2e-6
+    banded = gm.group_masks(t, plan, kernel='banded').cpu().numpy()
+    assert np.abs(out - banded).max() / scale <= 3e-6
+    out2 = gm.group_masks(t, plan, out=torch.from_numpy(out).cuda(), accumulate=True,
+                          kernel='walk').cpu().numpy()
+    assert np.abs(out2 - 2 * ref).max() / scale <= 4e-6
+    big = torch.zeros((F, S * S + 24), device='cuda')
+    big[:, 8:8 + S * S] = t
+    for _ in range(3):
+        out3 = gm.group_masks(big[:, 8:8 + S * S], plan, kernel='walk').cpu().numpy()
+        assert np.array_equal(out3, out)
+
+
+@pytest.mark.parametrize('n_groups,size,K,F', [(3, 25, 512, 200), (8, 7, 2048, 129),
+                                               (12, 4, 4096, 1000), (1, 5, 256, 128)])
+def test_group_masks_walk_bands(n_groups, size, K, F):
+    """K10 on stacks that are not rings (overlapping pixel bands; empty first group)"""
+    from libertem_b200 import engine, group_masks as gm
+    rng = np.random.default_rng(K)
+    stack = np.zeros((n_groups * size, K), dtype=np.complex64)
+    width = 96
+    step = (K - width) // max(1, n_groups - 1) if n_groups > 1 else 0
+    for g in range(n_groups):
+        if g == 0 and n_groups > 4:
+            continue
+        a = g * step
+        b = min(K, a + width)
+        stack[g * size:(g + 1) * size, a:b] = (rng.random((size, b - a)) - 0.5 +
+                                               1j * (rng.random((size, b - a)) - 0.5))
+    plan = gm.build_plan(stack, size, torch.device('cuda'))
+    assert plan.walk is not None
+    data = synth.uniform_f32(0, F * K, 22).reshape(F, K)
+    t = torch.from_numpy(data).cuda()
+    out = gm.group_masks(t, plan, kernel='walk').cpu().numpy()
+    assert engine.last_kernel() == 10
+    ref = data.astype(np.float64) @ stack.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(stack).astype(np.float64).T).max() + 1e-30
+    assert np.abs(out - ref).max() / scale <= 2e-6
+
+
+def test_group_masks_walk_rejects():
+    from libertem_b200 import _lib, group_masks as gm
+    flat = _radial_flat(128, 16, 6)              # narrow rings: no walk plan by default
+    plan = gm.build_plan(flat, 7, torch.device('cuda'))
+    assert plan.walk is None and plan.banded is not None
+    t = torch.zeros((128, 128 * 128), device='cuda')
+    with pytest.raises(_lib.LTB200Error):
+        gm.group_masks(t, plan, kernel='walk')
+    out = gm.group_masks(t, plan, kernel='auto')
+    assert float(out.abs().max()) == 0.0

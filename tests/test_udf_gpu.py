@@ -666,11 +666,12 @@ def test_corrections_do_not_leak_between_runs(lt):
 
 
 @pytest.mark.parametrize('name', ['centre', 'offcentre'])
-@pytest.mark.parametrize('kernel', ['auto', 'banded', 'ffma'])
+@pytest.mark.parametrize('kernel', ['auto', 'walk', 'banded', 'ffma'])
 def test_cfg4_k7_radial_fourier_golden(lt, name, kernel, monkeypatch):
-    """RadialFourierAnalysis vs the unmodified reference at a size where the DEFAULT kernel
-    (K7: tcgen05 group-sparse, >= 96 frames per tile) runs: 256 frames, one partition
-    (reference analysis/radialfourier.py:106-146,184-194).  'auto' must pick K7."""
+    """RadialFourierAnalysis vs the unmodified reference at a size where the DEFAULT kernels
+    (tcgen05 group-sparse, >= 96 frames per tile) run: 256 frames, one partition
+    (reference analysis/radialfourier.py:106-146,184-194).  'auto' must pick K10 (dense walk)
+    when the stack has such a plan, else K7; 'walk' / 'banded' force K10 / K7."""
     from libertem_b200 import engine, group_masks as gm
     meta, g = load_golden('cfg4_k7_' + name)
     data = synth.dataset(meta['shape'], np.float32, meta['data_seed'])
@@ -684,7 +685,7 @@ def test_cfg4_k7_radial_fourier_golden(lt, name, kernel, monkeypatch):
         monkeypatch.setattr(gm, 'group_masks',
                             lambda *args, **kw: orig(*args, **{**kw, 'kernel': kernel}))
     res = ctx.run(a)
-    want_kernel = {'auto': (70, 71), 'banded': (70,), 'ffma': (4,)}[kernel]
+    want_kernel = {'auto': (10, 70, 71), 'walk': (10,), 'banded': (70,), 'ffma': (4,)}[kernel]
     assert engine.last_kernel() in want_kernel, engine.last_kernel()
     raw = res.raw_results
     ref = g['raw_results']
@@ -717,7 +718,7 @@ def test_radial_fourier_symmetries_known_answer(lt, kernel, monkeypatch):
         monkeypatch.setattr(gm, 'group_masks',
                             lambda *args, **kw: orig(*args, **{**kw, 'kernel': kernel}))
     res = ctx.run(a)
-    assert engine.last_kernel() in ((70, 71, 7) if kernel == 'auto' else (4,))
+    assert engine.last_kernel() in ((10, 70, 71, 7) if kernel == 'auto' else (4,))
     raw = res.raw_results
     ref = g['raw_results']
     tot = float(g['frame_sums'].max())
