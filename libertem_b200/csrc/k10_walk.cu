@@ -30,8 +30,11 @@
 //   * warps 16..19 MMA issuers (groups g % 4; two per pipeline): per op three tcgen05.mma.kind::tf32 of
 //     M 128, N 64, K 8 into the op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi;
 //     the table rows are [hi(0..55) | lo(0..55)], the lo product reads rows 56..119).
-// TMEM: 6 accumulator buffers of 64 columns (pool; chains of <= 8 ops, the float32 accumulate
-// of the tensor core truncates -- see k6_tensor.cu) + 2 A stages of 4 x (hi 8 | lo 8) columns.
+// TMEM: 5 accumulator buffers of 64 columns (one pool; chains of <= 8 ops, the float32
+// accumulate of the tensor core truncates -- see k6_tensor.cu) + 3 A stages of 4 x (hi 8 | lo 8)
+// columns: the hand-over of an A stage (MMAs complete -> converters store -> MMA issuers)
+// takes about as long as the tensor pipe needs for two boxes, so with two stages the pipe sat
+// idle half the time.
 #include "common.cuh"
 #include <cstdlib>
 
@@ -44,10 +47,10 @@ constexpr int K10_HR = 56;                       // weight rows per half
 constexpr uint32_t K10_TAB_BYTES = 2 * K10_HR * 128;        // 14 KiB copied per stage
 constexpr uint32_t K10_TAB_STRIDE = K10_TAB_BYTES + 1024;   // + 8 zero rows (rows 112..119)
 constexpr int K10_TSTAGES = 4;                    // per pipeline
-constexpr int K10_AS = 2;                        // A-operand stages: 4 slices x (hi 8 | lo 8)
-constexpr int K10_NBUF = 6;                      // accumulator buffers
+constexpr int K10_AS = 3;                        // A-operand stages: 4 slices x (hi 8 | lo 8)
+constexpr int K10_NBUF = 5;                      // accumulator buffers: one pool (4 live + 1 in drain)
 constexpr int K10_ACC_COLS = 64;
-constexpr int K10_A_BASE = K10_NBUF * K10_ACC_COLS;   // 384
+constexpr int K10_A_BASE = K10_NBUF * K10_ACC_COLS;   // 320
 constexpr int K10_QLEN = 4;
 constexpr int K10_MAXSEG = 8;
 constexpr int K10_THREADS = 768;                  // 24 warps (22 with a role)
@@ -58,11 +61,11 @@ constexpr uint32_t K10_OP_FIRST = 1u << 3, K10_OP_COMMIT = 1u << 4,
                    K10_OP_NOMMA = 1u << 7;                       // marker / padding
 constexpr int K10_OP_SLICE_SHIFT = 8;            // bits 8-9: slice of the box
 constexpr int K10_OP_PARITY_SHIFT = 10;          // FIRST: mbarrier parity of the wait for the drain
-constexpr int K10_OP_ASTAGE_SHIFT = 11;          // A stage of the box
-constexpr int K10_OP_APARITY_SHIFT = 12;         // mbarrier parity of the A stage
+constexpr int K10_OP_ASTAGE_SHIFT = 11;          // bits 11-12: A stage of the box
+constexpr int K10_OP_APARITY_SHIFT = 13;         // mbarrier parity of the A stage
 constexpr uint32_t K10_EV_SLOT = 1u << 3, K10_EV_LAST = 1u << 4;
 constexpr int K10_EV_PARITY_SHIFT = 5;
-constexpr int K10_EV_NEXT_SHIFT = 6;             // issuer of the pipeline that uses the buffer next
+constexpr int K10_EV_NEXT_SHIFT = 6;             // bits 6-7: issuer (g % 4) that uses the buffer next
 
 struct K10Params {
     const uint32_t* boxes;         // per visit: first pixel | slice mask (low 4 bits)
@@ -219,9 +222,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
     uint64_t* tab_free = tab_full + 2 * K10_TSTAGES;                              // [2][TSTAGES]
     uint64_t* a_full = tab_free + 2 * K10_TSTAGES;                                // [AS]
     uint64_t* mma_done = a_full + K10_AS;                                         // [AS]
-    uint64_t* acc_full = mma_done + K10_AS;                                       // [NBUF]
-    uint64_t* acc_free = acc_full + K10_NBUF;                                     // [NBUF][2]
-    uint64_t* q_full = acc_free + 2 * K10_NBUF;                                   // [QLEN]
+    uint64_t* acc_full = mma_done + K10_AS;                                       // [NBUF][2]
+    uint64_t* acc_free = acc_full + 2 * K10_NBUF;                                 // [NBUF][4]
+    uint64_t* q_full = acc_free + 4 * K10_NBUF;                                   // [QLEN]
     uint64_t* q_free = q_full + K10_QLEN;                                         // [QLEN]
     int* meta = reinterpret_cast<int*>(q_free + K10_QLEN);                        // [DSTAGES]
     K10QItem* queue = reinterpret_cast<K10QItem*>(meta + 8);                      // [QLEN]
@@ -245,13 +248,14 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             mbar_init(&mma_done[s], 4);                // the four MMA issuers
         }
         for (int s = 0; s < K10_NBUF; s++) {
-            mbar_init(&acc_full[s], 1);
-            // "drained": one barrier per buffer and WAITING issuer of the pipeline (the two
-            // issuers share the pool and can be a short chain apart: on a common barrier the
-            // parity of one's wait could be satisfied by the other's phase).  The drain of a
-            // chain arrives on the barrier of the issuer that uses the buffer next.
-            mbar_init(&acc_free[2 * s], 4);            // the 4 warps of a drain group
-            mbar_init(&acc_free[2 * s + 1], 4);
+            // The buffers are ONE pool for both pipelines and all four issuers, which can be
+            // a (short) chain apart: on a common barrier the parity of one's wait could be
+            // satisfied by another's phase.  So "chain complete" has one barrier per buffer
+            // and drain group, and "drained" one per buffer and WAITING issuer: the drain of a
+            // chain arrives on the barrier of the issuer that uses the buffer next (static).
+            mbar_init(&acc_full[2 * s], 1);
+            mbar_init(&acc_full[2 * s + 1], 1);
+            for (int c = 0; c < 4; c++) mbar_init(&acc_free[4 * s + c], 4);   // a drain group
         }
         for (int s = 0; s < K10_QLEN; s++) {
             mbar_init(&q_full[s], 1);
@@ -288,7 +292,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         const uint32_t row_off = (uint32_t)row * 128u;
         int stage = 0;
         uint32_t dphase = 0;
-        uint32_t nbox = 0;                              // boxes seen so far
+        uint32_t ast = 0, aphase = 0;                   // A stage of the next box and its parity
         for (;;) {
             mbar_wait(&data_full[stage], dphase);
             const int m = meta[stage];
@@ -334,9 +338,8 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 stage = 0;
                 dphase ^= 1;
             }
-            // the A stage of this box is free once the MMAs of the box two back have completed
-            const uint32_t ast = nbox & 1u;
-            mbar_wait(&mma_done[ast], ((nbox >> 1) & 1u) ^ 1u);
+            // the A stage of this box is free once the MMAs of the box K10_AS back have completed
+            mbar_wait(&mma_done[ast], aphase ^ 1u);
             k10_fence_after();
 #pragma unroll
             for (int s = 0; s < 2; s++) {
@@ -362,7 +365,10 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             k10_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[ast]);
-            nbox++;
+            if (++ast == K10_AS) {
+                ast = 0;
+                aphase ^= 1u;
+            }
         }
     } else if (warp < MMA_WARP) {
         // ===== accumulator drain =====
@@ -398,7 +404,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     const uint32_t buf = ev & 7u;
                     const uint32_t g = ev >> 8;
                     // (every buffer is used an even number of times per segment: static parity)
-                    mbar_wait(&acc_full[buf], (ev >> K10_EV_PARITY_SHIFT) & 1u);
+                    mbar_wait(&acc_full[2 * buf + grp], (ev >> K10_EV_PARITY_SHIFT) & 1u);
                     k10_fence_after();
                     const uint32_t d = tmem_base + lane_sel + buf * K10_ACC_COLS;
                     const bool slot1 = (ev & K10_EV_SLOT) != 0;
@@ -434,7 +440,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     k10_fence_before();
                     __syncwarp();
                     if (lane == 0)
-                        mbar_arrive(&acc_free[2 * buf + ((ev >> K10_EV_NEXT_SHIFT) & 1u)]);
+                        mbar_arrive(&acc_free[4 * buf + ((ev >> K10_EV_NEXT_SHIFT) & 3u)]);
                     if (ev & K10_EV_LAST) {
                         // the group's sum over this segment is complete: write the row
                         float* o = p.out + f * p.ld_out + (int64_t)g * p.n_cols;
@@ -593,7 +599,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 #pragma unroll
                             for (int sub = 0; sub < 4; sub++) {
                                 const uint32_t o = op[sub];
-                                const uint32_t ast = (o >> K10_OP_ASTAGE_SHIFT) & 1u;
+                                const uint32_t ast = (o >> K10_OP_ASTAGE_SHIFT) & 3u;
                                 if (__builtin_expect((o & K10_OP_NEW) != 0, 0)) {
                                     mbar_wait(&a_full[ast], (o >> K10_OP_APARITY_SHIFT) & 1u);
                                     k10_fence_after();
@@ -601,20 +607,20 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                                 if (__builtin_expect(!(o & K10_OP_NOMMA), 1)) {
                                     const uint32_t buf = o & 7u;
                                     if (__builtin_expect((o & K10_OP_FIRST) != 0, 0)) {
-                                        mbar_wait(&acc_free[2 * buf + (uint32_t)(me >> 1)],
+                                        mbar_wait(&acc_free[4 * buf + (uint32_t)me],
                                                   (o >> K10_OP_PARITY_SHIFT) & 1u);
                                         k10_fence_after();
                                     }
                                     const uint32_t d = tmem_base + buf * K10_ACC_COLS;
                                     const uint32_t a_hi =
-                                        a_base + ((o >> (K10_OP_ASTAGE_SHIFT - 6)) & 64u) +
+                                        a_base + ((o >> (K10_OP_ASTAGE_SHIFT - 6)) & 192u) +
                                         ((o >> (K10_OP_SLICE_SHIFT - 4)) & 48u);
                                     const uint32_t b = desc_lo + (uint32_t)(sub * 2);
                                     k10_mma2(d, a_hi, b, desc_hi32, IDESC,
                                              (o & K10_OP_FIRST) ? 0u : 1u);
                                     k10_mma2(d, a_hi, b + DESC_LO_HALF, desc_hi32, IDESC, 1u);
                                     k10_mma2(d, a_hi + 8, b, desc_hi32, IDESC, 1u);
-                                    if (o & K10_OP_COMMIT) k10_commit(&acc_full[buf]);
+                                    if (o & K10_OP_COMMIT) k10_commit(&acc_full[2 * buf + pipe]);
                                 }
                                 // this pipeline's MMAs of the box (if any) release the A stage
                                 if (o & K10_OP_END) k10_commit(&mma_done[ast]);
@@ -722,8 +728,8 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
             LTB_REQUIRE(p.op_off[k][s] % 4 == 0,
                         "group_masks_walk: op offsets must be multiples of 4");
         }
-        LTB_REQUIRE(p.visit_off[s] % 4 == 0,
-                    "group_masks_walk: visit offsets must be multiples of 4");
+        LTB_REQUIRE(p.visit_off[s] % (2 * K10_AS) == 0,
+                    "group_masks_walk: visit offsets must be multiples of %d", 2 * K10_AS);
     }
     p.n_seg = n_segments;
     p.n_cols = 2 * n_pairs;

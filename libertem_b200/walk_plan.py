@@ -44,8 +44,9 @@ work items, so a group receives partial sums from at most two of them.
 import numpy as np
 
 W_LIVE = 4        # groups with an open accumulator (window of consecutive group ids)
-NBUF = 6          # TMEM accumulator buffers of 64 columns
+NBUF = 5          # TMEM accumulator buffers of 64 columns: ONE pool (4 live groups + 1 in drain)
 CHAIN = 8         # ops per accumulation chain
+A_STAGES = 3      # A-operand stages (boxes in flight between converters and MMA issuers)
 BOX = 32          # pixels per TMA box (128 bytes)
 SL = 8            # pixels per slice (K of one tf32 MMA)
 HR = 56           # weight rows per half ([hi | lo]): 2 * group_size <= HR
@@ -62,15 +63,15 @@ OP_NOMMA = 1 << 7       # marker / padding: no tensor work
 OP_SLICE_SHIFT = 8      # bits 8-9: slice of the box
 OP_PARITY_SHIFT = 10    # first op of a chain: mbarrier parity of the issuer's wait for the drain
 #                         of the buffer's previous chain
-OP_ASTAGE_SHIFT = 11    # A stage of the box (box index & 1)
-OP_APARITY_SHIFT = 12   # mbarrier parity of the A stage ((box index >> 1) & 1)
+OP_ASTAGE_SHIFT = 11    # bits 11-12: A stage of the box (box index % A_STAGES)
+OP_APARITY_SHIFT = 13   # mbarrier parity of the A stage ((box index // A_STAGES) & 1)
 OP_NOP = OP_NOMMA       # padding word
 
 EV_SLOT = 1 << 3
 EV_LAST = 1 << 4
 EV_PARITY_SHIFT = 5     # parity of the buffer's use count in the segment
-EV_NEXT_SHIFT = 6       # which issuer of the pipeline (0 / 1) uses the buffer next
-BOX_PAD = 4             # visits per segment are padded to a multiple of this
+EV_NEXT_SHIFT = 6       # bits 6-7: which issuer (g % 4) uses the buffer next
+BOX_PAD = 2 * A_STAGES  # visits per segment are padded to a multiple of this
 
 def tf32_round(a):
     bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
@@ -182,7 +183,8 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
     boxes = []
     ops = ([], [], [], [])         # per issuer (g % 4): aligned with its pipeline's stream
     op_slice = ([], [])            # global slice index of every word (-1: no weights)
-    op_group = ([], [])            # group of every word (-1 marker / padding, -2 empty chain)
+    op_group = ([], [])            # group of every word (-1 marker / padding, <= -2 empty chain)
+    op_seq = ([], [])              # position of every op in the walk order (emulator only)
     events = ([], [])
     visit_off, op_off, ev_off = [0], ([0], [0]), ([0], [0])
     for s in range(n_seg):
@@ -205,25 +207,29 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
         last_op_of_group = {}
         for i, e in enumerate(seq):
             last_op_of_group[e[2]] = i
-        # accumulator buffers: a pool of NBUF / 2 per pipeline, FIFO = oldest released first.
-        # The two issuers of a pipeline share its pool and may be a (short) chain apart, so the
-        # "buffer drained" barriers are per buffer AND waiting issuer: the drain of a chain
-        # arrives on the barrier of the issuer that uses the buffer NEXT (a static fact), and
-        # each barrier is waited on by one thread in a fixed order -- no parity can alias.
-        free = [list(range(NBUF // 2)), list(range(NBUF // 2, NBUF))]
-        uses = [0] * NBUF
-        chains = [[] for _ in range(NBUF)]         # per buffer: [issuer k, pipeline, event, word]
+        # accumulator buffers: ONE pool for both pipelines, FIFO = oldest released first (TMEM
+        # holds 5 buffers next to 3 A stages; 4 groups are live, so one buffer is in drain).
+        # Any of the four issuers may use a buffer next and they may be a (short) chain apart,
+        # so the "buffer drained" barriers are per buffer AND waiting issuer: the drain of a
+        # chain arrives on the barrier of the issuer that uses the buffer NEXT (a static fact),
+        # and each barrier is waited on by one thread in a fixed order -- no parity can alias.
+        # For the same reason "chain complete" has one barrier per buffer and drain group.
+        free = list(range(NBUF))
+        uses_p = [[0, 0] for _ in range(NBUF)]     # chains per buffer and pipeline (drain group)
+        chains = [[] for _ in range(NBUF)]         # per buffer: [issuer, pipeline, event, word]
         open_buf, open_len = {}, {}
-        words = ([], [])                           # per pipeline: [word, box, slice, group]
+        words = ([], [])                           # per pipeline: [word, box, slice, group, seq]
+        n_seq = [0]
 
-        def empty_chain(b, k, b_i, j):
-            """a chain without weights on buffer b, issued by issuer k of its pipeline"""
-            par = 1 if b >= NBUF // 2 else 0
-            w = [(j << OP_SLICE_SHIFT) | b | OP_FIRST | OP_COMMIT, b_i, j, -2 - k]
+        def empty_chain(b, cls, b_i, j):
+            """a chain without weights on buffer b, issued by issuer cls"""
+            par = cls & 1
+            w = [(j << OP_SLICE_SHIFT) | b | OP_FIRST | OP_COMMIT, b_i, j, -2 - cls, n_seq[0]]
+            n_seq[0] += 1
             words[par].append(w)
-            events[par].append(b | ((uses[b] & 1) << EV_PARITY_SHIFT) | (par << 8))
-            chains[b].append([k, par, len(events[par]) - 1, w])
-            uses[b] += 1
+            events[par].append(b | ((uses_p[b][par] & 1) << EV_PARITY_SHIFT) | (par << 8))
+            chains[b].append([cls, par, len(events[par]) - 1, w])
+            uses_p[b][par] += 1
 
         if seq:
             # every segment starts with an empty chain of issuer 0 on every buffer: the last
@@ -232,14 +238,15 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
                 empty_chain(b, 0, seq[0][0], seq[0][1])
         for i, (b_i, j, g) in enumerate(seq):
             par = g & 1
-            w = [j << OP_SLICE_SHIFT, b_i, j, g]
+            w = [j << OP_SLICE_SHIFT, b_i, j, g, n_seq[0]]
+            n_seq[0] += 1
             if g not in open_buf:
-                if not free[par]:
+                if not free:
                     raise AssertionError('walk plan: accumulator pool exhausted')
-                b = open_buf[g] = free[par].pop(0)
+                b = open_buf[g] = free.pop(0)
                 open_len[g] = 0
                 w[0] |= OP_FIRST
-                chains[b].append([(g >> 1) & 1, par, None, w])
+                chains[b].append([g & 3, par, None, w])
                 if len(open_buf) > W_LIVE:
                     raise AssertionError('walk plan: more than W_LIVE live groups')
             b = open_buf[g]
@@ -250,33 +257,34 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
                 w[0] |= OP_COMMIT
                 events[par].append(b | (EV_SLOT if (g >> 1) & 1 else 0) |
                                    (EV_LAST if final else 0) |
-                                   ((uses[b] & 1) << EV_PARITY_SHIFT) | (g << 8))
+                                   ((uses_p[b][par] & 1) << EV_PARITY_SHIFT) | (g << 8))
                 chains[b][-1][2] = len(events[par]) - 1
-                uses[b] += 1
-                free[par].append(b)
+                uses_p[b][par] += 1
+                free.append(b)
                 del open_buf[g], open_len[g]
             words[par].append(w)
         assert not open_buf
         if seq:
-            # every buffer is used an even number of times per segment by EITHER issuer of its
-            # pipeline (static mbarrier parities): odd counts get one more empty chain
+            # every buffer is used an even number of times per segment by EVERY issuer (static
+            # mbarrier parities): odd counts get one more empty chain
             b_i, j = seq[-1][0], seq[-1][1]
             for b in range(NBUF):
-                for k in range(2):
-                    if sum(1 for c in chains[b] if c[0] == k) & 1:
-                        empty_chain(b, k, b_i, j)
+                for cls in range(4):
+                    if sum(1 for c in chains[b] if c[0] == cls) & 1:
+                        empty_chain(b, cls, b_i, j)
             for b in range(NBUF):
-                n_before = [0, 0]
-                for n, (k, par, ev, w) in enumerate(chains[b]):
+                n_before = [0, 0, 0, 0]
+                for n, (cls, par, ev, w) in enumerate(chains[b]):
                     # the issuer's wait for "drained": the parity of the phase of ITS barrier
                     # that the drain before this chain completes.  Issuer 0 consumes one
                     # arrival that precedes the segment (the last drain of the previous item;
                     # none in the first item, where the fresh barrier lets parity 1 pass)
-                    w[0] |= ((n_before[k] & 1) ^ (1 if k == 0 else 0)) << OP_PARITY_SHIFT
-                    n_before[k] += 1
+                    w[0] |= ((n_before[cls] & 1) ^ (1 if cls == 0 else 0)) << OP_PARITY_SHIFT
+                    n_before[cls] += 1
                     nxt = chains[b][n + 1][0] if n + 1 < len(chains[b]) else 0
                     events[par][ev] |= nxt << EV_NEXT_SHIFT
-                assert chains[b][0][0] == 0 and not n_before[0] & 1 and not n_before[1] & 1
+                assert chains[b][0][0] == 0 and not any(v & 1 for v in n_before)
+                assert not uses_p[b][0] & 1 and not uses_p[b][1] & 1
         # per pipeline: the op stream (= table slot order); a box without ops of the pipeline
         # gets a marker slot.  Per ISSUER (two per pipeline, groups g % 4 = par and par + 2):
         # a word list aligned with the stream -- its own ops, empty words for the other
@@ -290,12 +298,13 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
             for b_i in range(len(seg_boxes)):
                 ws = by_box.get(b_i)
                 if not ws:
-                    ws = [[OP_NOMMA, b_i, 0, -1]]
-                stage_bits = ((b_i & 1) << OP_ASTAGE_SHIFT) | (((b_i >> 1) & 1) << OP_APARITY_SHIFT)
+                    ws = [[OP_NOMMA, b_i, 0, -1, -1]]
+                stage_bits = (((b_i % A_STAGES) << OP_ASTAGE_SHIFT) |
+                              (((b_i // A_STAGES) & 1) << OP_APARITY_SHIFT))
                 for k in range(2):
                     cls = par + 2 * k
                     own = [n for n, w in enumerate(ws)
-                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 - k]
+                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 - cls]
                     first, last = (own[0], own[-1]) if own else (0, 0)
                     for n, w in enumerate(ws):
                         word = (w[0] if n in own else OP_NOMMA) | stage_bits
@@ -305,6 +314,7 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
                             word |= OP_END_BOX
                         ops[cls].append(word)
                 for w in ws:
+                    op_seq[par].append(w[4])
                     op_group[par].append(w[3])
                     op_slice[par].append(
                         (seg_boxes[b_i] & ~31) // SL + w[2] if w[3] != -1 else -1)
@@ -313,6 +323,7 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
                     ops[par + 2 * k].append(OP_NOP)
                 op_group[par].append(-1)
                 op_slice[par].append(-1)
+                op_seq[par].append(-1)
             op_off[par].append(len(op_group[par]))
             ev_off[par].append(len(events[par]))
         boxes.extend(seg_boxes)
@@ -335,6 +346,7 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
         plan[f'ev_off{p}'] = np.array(ev_off[p], dtype=np.int32)
         plan[f'op_slice{p}'] = sl_p
         plan[f'op_group{p}'] = gr_p
+        plan[f'op_seq{p}'] = np.array(op_seq[p], dtype=np.int64)
         plan[f'table{p}'] = _table_image(flat, group_size, sl_p, gr_p)
     return plan
 
@@ -384,9 +396,10 @@ def _merge_issuers(plan, p):
     own_a, own_b = (a & OP_NOMMA) == 0, (b & OP_NOMMA) == 0
     assert not np.any(own_a & own_b)
     g = plan[f'op_group{p}']
-    assert np.all((g[own_a][g[own_a] >= 0] & 3) == p) and np.all(g[own_a][g[own_a] < 0] == -2)
-    assert np.all((g[own_b][g[own_b] >= 0] & 3) == p + 2) and np.all(g[own_b][g[own_b] < 0] == -3)
-    stage_mask = (1 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
+    assert np.all((g[own_a][g[own_a] >= 0] & 3) == p) and np.all(g[own_a][g[own_a] < 0] == -2 - p)
+    assert np.all((g[own_b][g[own_b] >= 0] & 3) == p + 2) and \
+        np.all(g[own_b][g[own_b] < 0] == -4 - p)
+    stage_mask = (3 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
     real = (a != OP_NOP) | (b != OP_NOP)
     assert np.all((a & stage_mask)[real] == (b & stage_mask)[real])
     merged = np.where(own_b, b, a) & ~(OP_NEW_BOX | OP_END_BOX)
@@ -412,104 +425,114 @@ def _merge_issuers(plan, p):
 
 def emulate(plan, tile):
     """numpy model of what the kernel does with the lists (float64 arithmetic; checks the
-    invariants the kernel relies on).  tile: (F, K) -> (F, n_groups * group_size) complex128"""
+    invariants the kernel relies on).  The two pipelines are replayed in the walk order of the
+    plan (any interleaving that respects the mbarrier waits gives the same result).
+    tile: (F, K) -> (F, n_groups * group_size) complex128"""
     F = tile.shape[0]
     G, gs = plan['n_groups'], plan['group_size']
     out = np.zeros((F, G, 2 * gs), dtype=np.float64)
     written = np.zeros(G, dtype=np.int64)
+    w = []
     for p in range(2):
-        w = unswizzle_table(plan[f'table{p}']).astype(np.float64)
-        w = w[:, :HR] + w[:, HR:]                                    # (stages, HR, 4, 8)
-        ops, events = _merge_issuers(plan, p), plan[f'events{p}']
-        for s in range(plan['n_segments']):
-            v0, v1 = plan['visit_off'][s], plan['visit_off'][s + 1]
-            assert (v1 - v0) % BOX_PAD == 0
-            bufs = np.zeros((NBUF, F, HR))
-            busy = [False] * NBUF
-            uses = [0] * NBUF
-            uses_k = [[0, 0] for _ in range(NBUF)]
-            next_user = [0] * NBUF                     # an item starts with issuer 0 everywhere
-            acc = np.zeros((2, F, HR))
-            slot_owner = [None, None]
-            evs = list(events[plan[f'ev_off{p}'][s]:plan[f'ev_off{p}'][s + 1]])
-            b_i = -1                                   # box of the segment
-            in_box = False
-            open_groups = {}
+        t = unswizzle_table(plan[f'table{p}']).astype(np.float64)
+        w.append(t[:, :HR] + t[:, HR:])                              # (stages, HR, 4, 8)
+    streams = [_merge_issuers(plan, p) for p in range(2)]
+    stage_mask = (3 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
+    for s in range(plan['n_segments']):
+        v0, v1 = plan['visit_off'][s], plan['visit_off'][s + 1]
+        assert (v1 - v0) % BOX_PAD == 0
+        bufs = np.zeros((NBUF, F, HR))
+        busy = [False] * NBUF
+        uses_p = [[0, 0] for _ in range(NBUF)]     # chains per buffer and drain group
+        uses_c = [[0] * 4 for _ in range(NBUF)]    # chains per buffer and issuer
+        next_user = [0] * NBUF                     # an item starts with issuer 0 everywhere
+        acc = np.zeros((2, 2, F, HR))
+        slot_owner = [[None, None], [None, None]]
+        evs = [list(plan[f'events{p}'][plan[f'ev_off{p}'][s]:plan[f'ev_off{p}'][s + 1]])
+               for p in range(2)]
+        open_groups = {}
+        order = []
+        for p in range(2):
             o0, o1 = plan[f'op_off{p}'][s], plan[f'op_off{p}'][s + 1]
             assert o0 % STAGE_OPS == 0 and o1 % STAGE_OPS == 0
+            b_i, in_box = -1, False
             for i in range(o0, o1):
-                word = int(ops[i])
-                if (word & ~((1 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT))) == OP_NOP \
-                        and plan[f'op_group{p}'][i] == -1 and not in_box \
-                        and not word & (OP_NEW_BOX | OP_END_BOX):
-                    continue
+                word = int(streams[p][i])
+                if (word & ~stage_mask) == OP_NOP and plan[f'op_group{p}'][i] == -1 \
+                        and not in_box and not word & (OP_NEW_BOX | OP_END_BOX):
+                    continue                           # padding of the last table stage
                 if word & OP_NEW_BOX:
                     assert not in_box
                     b_i += 1
                     in_box = True
                 assert in_box
-                assert ((word >> OP_ASTAGE_SHIFT) & 1) == (b_i & 1)
-                assert ((word >> OP_APARITY_SHIFT) & 1) == ((b_i >> 1) & 1)
-                box_word = int(plan['boxes'][v0 + b_i])
-                px0, mask = box_word & ~31, box_word & 15
+                assert ((word >> OP_ASTAGE_SHIFT) & 3) == b_i % A_STAGES
+                assert ((word >> OP_APARITY_SHIFT) & 1) == ((b_i // A_STAGES) & 1)
                 if not word & OP_NOMMA:
-                    g = int(plan[f'op_group{p}'][i])
-                    j = (word >> OP_SLICE_SHIFT) & 3
-                    assert mask >> j & 1               # the converters fill only masked slices
-                    assert px0 + j * SL == plan[f'op_slice{p}'][i] * SL
-                    b = word & 7
-                    assert (b >= NBUF // 2) == bool(p)
-                    x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)
-                    prod = x @ w[i // STAGE_OPS, :, i % STAGE_OPS].T               # (F, HR)
-                    if g <= -2:                        # empty chain
-                        assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
-                        assert not np.any(prod)
-                    else:
-                        assert (g & 1) == p
-                    k_iss = ((g >> 1) & 1) if g >= 0 else -2 - g      # issuer of the pipeline
-                    if word & OP_FIRST:
-                        assert not busy[b] and g not in open_groups
-                        assert ((word >> OP_PARITY_SHIFT) & 1) == \
-                            (uses_k[b][k_iss] & 1) ^ (1 if k_iss == 0 else 0)
-                        # the drain of the previous chain was addressed to this issuer
-                        assert next_user[b] == k_iss
-                        uses_k[b][k_iss] += 1
-                        busy[b] = True
-                        open_groups[g] = b
-                        bufs[b] = prod
-                    else:
-                        assert busy[b] and open_groups[g] == b
-                        bufs[b] += prod
-                    live = [q for q in open_groups if q >= 0]
-                    assert len(live) <= W_LIVE // 2
-                    if word & OP_COMMIT:
-                        ev = int(evs.pop(0))
-                        assert (ev & 7) == b
-                        assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses[b] & 1)
-                        next_user[b] = (ev >> EV_NEXT_SHIFT) & 1
-                        uses[b] += 1
-                        busy[b] = False
-                        del open_groups[g]
-                        if g <= -2:
-                            assert not ev & EV_LAST
-                        else:
-                            assert (ev >> 8) == g
-                            slot = 1 if ev & EV_SLOT else 0
-                            assert slot == ((g >> 1) & 1)
-                            assert slot_owner[slot] in (None, g)
-                            slot_owner[slot] = g
-                            acc[slot] += bufs[b]
-                            if ev & EV_LAST:
-                                out[:, g] += acc[slot][:, :2 * gs]
-                                written[g] += 1
-                                acc[slot] = 0
-                                slot_owner[slot] = None
+                    order.append((int(plan[f'op_seq{p}'][i]), p, i, b_i))
                 if word & OP_END_BOX:
                     in_box = False
             assert b_i == v1 - v0 - 1 and not in_box
-            assert not any(busy) and not evs and not open_groups
-            assert not any(u & 1 for u in uses) and slot_owner == [None, None]
-            assert not any(u[0] & 1 or u[1] & 1 for u in uses_k)
-            assert all(next_user[b] == 0 for b in range(NBUF) if uses[b])
+        order.sort()
+        last_seq = [-1, -1]
+        for seq_no, p, i, b_i in order:
+            assert seq_no > last_seq[p]                # a pipeline keeps the walk order
+            last_seq[p] = seq_no
+            word = int(streams[p][i])
+            box_word = int(plan['boxes'][v0 + b_i])
+            px0, mask = box_word & ~31, box_word & 15
+            g = int(plan[f'op_group{p}'][i])
+            cls = (g & 3) if g >= 0 else -2 - g        # issuer
+            assert (cls & 1) == p
+            j = (word >> OP_SLICE_SHIFT) & 3
+            assert mask >> j & 1                       # the converters fill only masked slices
+            assert px0 + j * SL == plan[f'op_slice{p}'][i] * SL
+            b = word & 7
+            assert b < NBUF
+            x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)
+            prod = x @ w[p][i // STAGE_OPS, :, i % STAGE_OPS].T                    # (F, HR)
+            if g <= -2:                                # empty chain
+                assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
+                assert not np.any(prod)
+            if word & OP_FIRST:
+                assert not busy[b] and g not in open_groups
+                assert ((word >> OP_PARITY_SHIFT) & 1) == \
+                    (uses_c[b][cls] & 1) ^ (1 if cls == 0 else 0)
+                assert next_user[b] == cls             # the last drain was addressed to it
+                uses_c[b][cls] += 1
+                busy[b] = True
+                open_groups[g] = b
+                bufs[b] = prod
+            else:
+                assert busy[b] and open_groups[g] == b
+                bufs[b] += prod
+            live = [q for q in open_groups if q >= 0]
+            assert len(live) <= W_LIVE and (not live or max(live) - min(live) < W_LIVE)
+            if word & OP_COMMIT:
+                ev = int(evs[p].pop(0))
+                assert (ev & 7) == b
+                assert ((ev >> EV_PARITY_SHIFT) & 1) == (uses_p[b][p] & 1)
+                next_user[b] = (ev >> EV_NEXT_SHIFT) & 3
+                uses_p[b][p] += 1
+                busy[b] = False
+                del open_groups[g]
+                if g <= -2:
+                    assert not ev & EV_LAST
+                else:
+                    assert (ev >> 8) == g
+                    slot = 1 if ev & EV_SLOT else 0
+                    assert slot == ((g >> 1) & 1)
+                    assert slot_owner[p][slot] in (None, g)
+                    slot_owner[p][slot] = g
+                    acc[p, slot] += bufs[b]
+                    if ev & EV_LAST:
+                        out[:, g] += acc[p, slot][:, :2 * gs]
+                        written[g] += 1
+                        acc[p, slot] = 0
+                        slot_owner[p][slot] = None
+        assert not any(busy) and not evs[0] and not evs[1] and not open_groups
+        assert slot_owner == [[None, None], [None, None]]
+        assert not any(v & 1 for u in uses_p for v in u) and not any(v & 1 for u in uses_c for v in u)
+        assert all(n == 0 for n in next_user)
     assert written.max() <= 2
     return (out[..., 0::2] + 1j * out[..., 1::2]).reshape(F, G * gs)
