@@ -277,23 +277,24 @@ LTB_API int ltb200_group_masks_tc_banded(const float* tile, int64_t n_frames, in
  * 128 frames and are final: the kernel only shifts and masks their words.
  *   boxes   (n_visits) uint32: first pixel of the box (multiple of 32) | 4-bit mask of the
  *           8-pixel slices in use; a multiple of 4 visits per segment;
- *   ops_c   uint32 lists of the four MMA issuers c = group id % 4 (issuers c and c + 2 share
- *           pipeline c % 2); a list is aligned with the op stream of its pipeline (walk order,
- *           a multiple of 4 per segment) and holds the issuer's own ops, empty words (bit 7)
- *           for the other issuer's, and ITS box hand-over flags: bits 0-2
- *           accumulator buffer, 3 / 4 first / last op of an accumulation chain, 5 / 6 first /
- *           last word of the pipeline in its box, 7 no tensor work (marker of a box without
- *           ops of the pipeline, padding), 8-9 slice of the box, 10 mbarrier parity of the
- *           buffer (first op), 11 A stage of the box, 12 mbarrier parity of the A stage;
+ *   ops_c   uint32 word lists of the four MMA issuers c = group id % 4 (issuers c and c + 2
+ *           belong to pipeline c % 2), in walk order, a multiple of 4 words per segment; a
+ *           word is an op of the issuer or the marker of a box without ops of the issuer:
+ *           bits 0-2 accumulator buffer, 3 / 4 first / last op of an accumulation chain, 5 / 6
+ *           first / last word of the issuer in its box, 7 no tensor work (marker, padding),
+ *           8-9 slice of the box, 10 mbarrier parity of the issuer's wait for the drain of the
+ *           buffer (first op), 11-12 A stage of the box, 13 mbarrier parity of the A stage;
  *   events_k uint32 per accumulation chain of pipeline k: bits 0-2 buffer, 3 register slot,
- *           4 last chain of the group in this segment, 5 mbarrier parity, 6 which issuer of
- *           the pipeline uses the buffer next, 8.. group id;
- *   table_k (n_ops_k / 4, 112, 32) float32: per 4 ops the byte image of a shared-memory stage:
- *           rows [hi(c) | lo(c)], c = 2 * pair + {0 re, 1 im} < 56, the 8 weights of op j at
- *           floats [8 j, 8 j + 8) of a row, 16-byte chunks XOR-swizzled with (row & 7);
- *   seg_off_host (5, n_segments + 1) int32 on the HOST: visit, op_0, op_1, event_0, event_1
- *           offsets of the segments (independent work items; a group receives sums from <= 2
- *           segments).
+ *           4 last chain of the group in this segment, 5 mbarrier parity, 6-7 the issuer that
+ *           uses the buffer next, 8.. group id;
+ *   table_c (n_stages_c, 112, 32) float32: the weight blocks of the ops of issuer c in list
+ *           order, 4 per stage (markers take no slot; a segment starts on a new stage), as the
+ *           byte image of a shared-memory stage: rows [hi(r) | lo(r)], r = 2 * pair + {0 re,
+ *           1 im} < 56, the 8 weights of op j at floats [8 j, 8 j + 8) of a row, 16-byte
+ *           chunks XOR-swizzled with (row & 7);
+ *   seg_off_host (11, n_segments + 1) int32 on the HOST: visit, word_0..3, table-stage_0..3,
+ *           event_0..1 offsets of the segments (independent work items; a group receives sums
+ *           from <= 2 segments).
  * out (n_frames, >= n_groups * n_pairs * 2) float32 = complex64 (n_groups * n_pairs), written
  * (accumulate = 0) or added to (accumulate = 1, staged through the workspace). */
 LTB_API size_t ltb200_group_masks_walk_workspace(int64_t n_frames, int n_groups, int n_pairs,
@@ -303,7 +304,8 @@ LTB_API int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int64_t
                                     const uint32_t* ops1, const uint32_t* ops2,
                                     const uint32_t* ops3, const uint32_t* events0,
                                     const uint32_t* events1, const float* table0,
-                                    const float* table1, const int32_t* seg_off_host,
+                                    const float* table1, const float* table2,
+                                    const float* table3, const int32_t* seg_off_host,
                                     int n_segments, int n_groups, int n_pairs, float* out,
                                     int64_t ld_out, int accumulate, void* workspace,
                                     size_t workspace_bytes, void* stream);

@@ -55,8 +55,8 @@ SIGNATURES = {
                                          _int, _vp, _i64, _int, _int, _vp, _sz, _vp]),
     'ltb200_group_masks_walk_workspace': (_sz, [_i64, _int, _int, _int]),
     'ltb200_group_masks_walk': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       _vp, _vp, _vp, _int, _int, _int, _vp, _i64, _int, _vp,
-                                       _sz, _vp]),
+                                       _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _i64,
+                                       _int, _vp, _sz, _vp]),
     'ltb200_synth_fill': (_int, [_vp, _int, _i64, _i64, _u32, _vp]),
     'ltb200_probe_read': (_int, [_vp, _sz, _int, _vp, _vp]),
     'ltb200_com_workspace': (_sz, [_int, _int]),

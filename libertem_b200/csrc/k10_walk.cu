@@ -25,8 +25,8 @@
 //     / odd id go to warps 8..11 / 12..15, each thread keeps two groups (window of 4); the last
 //     chain of a group writes the result row;
 //   * warp 20      box producer (TMA, frame stream, evict_first) + work-item fetch;
-//   * warp 21      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops of a
-//     pipeline (the tables are stored as the byte image of the swizzled stage), two rings of 4;
+//   * warp 21      weight-table producer: one contiguous 14 KiB bulk copy per 4 ops of an
+//     issuer (the tables are stored as the byte image of the swizzled stage), four rings of 2;
 //   * warps 16..19 MMA issuers (groups g % 4; two per pipeline): per op three tcgen05.mma.kind::tf32 of
 //     M 128, N 64, K 8 into the op's accumulator buffer (x_hi.m_hi + x_hi.m_lo + x_lo.m_hi;
 //     the table rows are [hi(0..55) | lo(0..55)], the lo product reads rows 56..119).
@@ -46,7 +46,7 @@ constexpr int K10_DSTAGES = 6;
 constexpr int K10_HR = 56;                       // weight rows per half
 constexpr uint32_t K10_TAB_BYTES = 2 * K10_HR * 128;        // 14 KiB copied per stage
 constexpr uint32_t K10_TAB_STRIDE = K10_TAB_BYTES + 1024;   // + 8 zero rows (rows 112..119)
-constexpr int K10_TSTAGES = 4;                    // per pipeline
+constexpr int K10_TSTAGES = 2;                    // per issuer (4 rings)
 constexpr int K10_AS = 3;                        // A-operand stages: 4 slices x (hi 8 | lo 8)
 constexpr int K10_NBUF = 5;                      // accumulator buffers: one pool (4 live + 1 in drain)
 constexpr int K10_ACC_COLS = 64;
@@ -69,11 +69,12 @@ constexpr int K10_EV_NEXT_SHIFT = 6;             // bits 6-7: issuer (g % 4) tha
 
 struct K10Params {
     const uint32_t* boxes;         // per visit: first pixel | slice mask (low 4 bits)
-    const uint32_t* ops[4];        // per MMA issuer (g % 4): aligned with its pipeline's stream
+    const uint32_t* ops[4];        // per MMA issuer (g % 4): its words (ops / box markers)
     const uint32_t* events[2];     // per pipeline: one word per chain
-    const float* table[2];         // per pipeline: (n_ops / 4) stage images of K10_TAB_BYTES
-    int visit_off[K10_MAXSEG + 1]; // multiples of 4 visits per segment
-    int op_off[2][K10_MAXSEG + 1]; // multiples of 4
+    const float* table[4];         // per issuer: stage images of K10_TAB_BYTES (4 ops each)
+    int visit_off[K10_MAXSEG + 1]; // multiples of 6 visits per segment
+    int op_off[4][K10_MAXSEG + 1]; // multiples of 4 words
+    int tab_off[4][K10_MAXSEG + 1];   // table stages
     int ev_off[2][K10_MAXSEG + 1];
     int n_seg;
     int n_cols;                    // 2 * n_pairs real columns per group
@@ -206,7 +207,7 @@ __device__ __forceinline__ void k10_bulk_load(void* dst, const void* src, uint32
 
 struct K10Smem {
     static constexpr uint32_t TABLE_OFF = K10_DSTAGES * K10_BOX_BYTES;
-    static constexpr uint32_t BAR_OFF = TABLE_OFF + 2 * K10_TSTAGES * K10_TAB_STRIDE;
+    static constexpr uint32_t BAR_OFF = TABLE_OFF + 4 * K10_TSTAGES * K10_TAB_STRIDE;
     static constexpr uint32_t TOTAL = BAR_OFF + 1024 + 1024;            // + alignment slack
 };
 
@@ -218,9 +219,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 
     uint64_t* data_full = reinterpret_cast<uint64_t*>(smem + K10Smem::BAR_OFF);   // [DSTAGES]
     uint64_t* data_free = data_full + K10_DSTAGES;                                // [DSTAGES]
-    uint64_t* tab_full = data_free + K10_DSTAGES;                                 // [2][TSTAGES]
-    uint64_t* tab_free = tab_full + 2 * K10_TSTAGES;                              // [2][TSTAGES]
-    uint64_t* a_full = tab_free + 2 * K10_TSTAGES;                                // [AS]
+    uint64_t* tab_full = data_free + K10_DSTAGES;                                 // [4][TSTAGES]
+    uint64_t* tab_free = tab_full + 4 * K10_TSTAGES;                              // [4][TSTAGES]
+    uint64_t* a_full = tab_free + 4 * K10_TSTAGES;                                // [AS]
     uint64_t* mma_done = a_full + K10_AS;                                         // [AS]
     uint64_t* acc_full = mma_done + K10_AS;                                       // [NBUF][2]
     uint64_t* acc_free = acc_full + 2 * K10_NBUF;                                 // [NBUF][4]
@@ -239,9 +240,9 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             mbar_init(&data_full[s], 1);
             mbar_init(&data_free[s], 8);               // converter warps
         }
-        for (int s = 0; s < 2 * K10_TSTAGES; s++) {
+        for (int s = 0; s < 4 * K10_TSTAGES; s++) {
             mbar_init(&tab_full[s], 1);
-            mbar_init(&tab_free[s], 2);                // the two issuers of the pipeline
+            mbar_init(&tab_free[s], 1);
         }
         for (int s = 0; s < K10_AS; s++) {
             mbar_init(&a_full[s], 8);                  // converter warps
@@ -264,7 +265,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
         fence_mbar_init();
     }
     // rows 112..119 of every table stage (read by the lo product, N = 64 from row 56) stay zero
-    for (int i = threadIdx.x; i < 2 * K10_TSTAGES * 256; i += K10_THREADS) {
+    for (int i = threadIdx.x; i < 4 * K10_TSTAGES * 256; i += K10_THREADS) {
         const int s = i >> 8, w = i & 255;
         reinterpret_cast<uint32_t*>(smem + K10Smem::TABLE_OFF + (size_t)s * K10_TAB_STRIDE +
                                     K10_TAB_BYTES)[w] = 0u;
@@ -512,23 +513,27 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 }
             }
         } else if (warp == TABLE_WARP) {
-            // ===== weight-table producer: one ring of K10_TSTAGES stages per pipeline, served
-            // by one lane that polls whichever ring has a free stage =====
+            // ===== weight-table producer: one ring of K10_TSTAGES stages per issuer, served by
+            // one lane that polls whichever ring has a free stage =====
             if (lane == 0) {
                 const uint64_t pol_keep = l2_policy_evict_last();
-                int ts[2] = {0, 0};
-                uint32_t tphase[2] = {0, 0};
+                int ts[4] = {0, 0, 0, 0};
+                uint32_t tphase[4] = {0, 0, 0, 0};
                 for (uint32_t qn = 0;; qn++) {
                     const int q = qn % K10_QLEN;
                     mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
                     const K10QItem qi = queue[q];
                     mbar_arrive(&q_free[q]);
                     if (qi.item < 0) break;
-                    int t[2] = {p.op_off[0][qi.seg] >> 2, p.op_off[1][qi.seg] >> 2};
-                    const int t1[2] = {p.op_off[0][qi.seg + 1] >> 2, p.op_off[1][qi.seg + 1] >> 2};
-                    while (t[0] < t1[0] || t[1] < t1[1]) {
+                    int t[4], t1[4];
 #pragma unroll
-                        for (int s = 0; s < 2; s++) {
+                    for (int s = 0; s < 4; s++) {
+                        t[s] = p.tab_off[s][qi.seg];
+                        t1[s] = p.tab_off[s][qi.seg + 1];
+                    }
+                    while (t[0] < t1[0] || t[1] < t1[1] || t[2] < t1[2] || t[3] < t1[3]) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
                             if (t[s] >= t1[s]) continue;
                             const int slot = s * K10_TSTAGES + ts[s];
                             if (!mbar_try_wait(&tab_free[slot], tphase[s] ^ 1)) continue;
@@ -546,29 +551,30 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 }
             }
         } else if (warp < DATA_WARP) {
-            // ===== MMA issuers (two per pipeline: groups g % 4 = warp - 16; warp-uniform loop,
-            // one elected lane issues) -- each walks the whole op stream of its pipeline (its
-            // list has empty words for the other issuer's ops) and both release every table
-            // stage; all four release every A stage
-            // One op = 96 tensor-pipe cycles and a single thread retires an instruction every
-            // 6-8 cycles here (profiles/r2_k10_*), so the issue loop must be short: every word
-            // of the list is final (buffer, A stage, parities are static), four words (one
-            // table stage) per round, the words of the next round are shuffled out while this
-            // one runs, the descriptor is a running 32-bit half.
+            // ===== MMA issuers (one per group class g % 4 = warp - 16; two per pipeline) =====
+            // One op = 96 tensor-pipe cycles, but a single thread retires an instruction only
+            // every 6-8 cycles in this code and cannot issue a tcgen05.mma more often than every
+            // 44.5 cycles (scripts/ubench/mma_rate_probe.cu), so the op stream is split over
+            // four issuers with PRIVATE word lists and weight-table streams: nothing is walked
+            // that is not the issuer's own, every word is final (buffer, A stage, all mbarrier
+            // parities are static), four words per unrolled round, the words of the next round
+            // are shuffled out while this one runs; the position in the table ring (stage,
+            // slot of 4) lives in the elected lane's registers.
             const int me = warp - MMA_WARP;             // issuer 0..3
             const int pipe = me & 1;
             constexpr uint32_t IDESC = k10_idesc_tf32(K10_ACC_COLS);
             const uint32_t tb0 =
-                smem_u32(smem + K10Smem::TABLE_OFF + (size_t)pipe * K10_TSTAGES * K10_TAB_STRIDE);
+                smem_u32(smem + K10Smem::TABLE_OFF + (size_t)me * K10_TSTAGES * K10_TAB_STRIDE);
             const uint32_t desc_hi32 = (uint32_t)(k10_desc_k_sw128(0) >> 32);
             const uint32_t desc_lo0 = (uint32_t)k10_desc_k_sw128(tb0);
             constexpr uint32_t DESC_STAGE = K10_TAB_STRIDE >> 4, DESC_LO_HALF = (K10_HR * 128) >> 4;
-            uint64_t* my_tab_full = tab_full + pipe * K10_TSTAGES;
-            uint64_t* my_tab_free = tab_free + pipe * K10_TSTAGES;
+            uint64_t* my_tab_full = tab_full + me * K10_TSTAGES;
+            uint64_t* my_tab_free = tab_free + me * K10_TSTAGES;
             const uint32_t* __restrict__ ops = p.ops[me];
             const uint32_t a_base = tmem_base + (uint32_t)K10_A_BASE;
-            uint32_t desc_lo = desc_lo0;                // table stage `ts`, rows 0.., op 0
-            int ts = 0;
+            // state of the elected lane (the same lane every time: the warp is converged)
+            uint32_t desc = desc_lo0;                   // table stage `ts`, rows 0.., op `slot`
+            int ts = 0, slot = 0;
             uint32_t tphase = 0;
             for (uint32_t qn = 0;; qn++) {
                 const int q = qn % K10_QLEN;
@@ -577,7 +583,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_free[q]);
                 if (qi.item < 0) break;
-                const int o0 = p.op_off[pipe][qi.seg], o1 = p.op_off[pipe][qi.seg + 1];
+                const int o0 = p.op_off[me][qi.seg], o1 = p.op_off[me][qi.seg + 1];
                 uint32_t w_next = o0 + lane < o1 ? ops[o0 + lane] : K10_OP_NOMMA;
                 for (int base = o0; base < o1; base += 32) {
                     const uint32_t w = w_next;
@@ -594,48 +600,63 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
 #pragma unroll
                         for (int u = 0; u < 4; u++)
                             nx[u] = __shfl_sync(0xffffffffu, w, (j + 4 + u) & 31);
-                        mbar_wait(&my_tab_full[ts], tphase);
+                        const bool last_round = base + j + 4 >= o1;
                         if (k10_elect_one()) {
 #pragma unroll
                             for (int sub = 0; sub < 4; sub++) {
                                 const uint32_t o = op[sub];
                                 const uint32_t ast = (o >> K10_OP_ASTAGE_SHIFT) & 3u;
-                                if (__builtin_expect((o & K10_OP_NEW) != 0, 0)) {
+                                if (o & K10_OP_NEW) {
                                     mbar_wait(&a_full[ast], (o >> K10_OP_APARITY_SHIFT) & 1u);
                                     k10_fence_after();
                                 }
-                                if (__builtin_expect(!(o & K10_OP_NOMMA), 1)) {
+                                if (!(o & K10_OP_NOMMA)) {
                                     const uint32_t buf = o & 7u;
-                                    if (__builtin_expect((o & K10_OP_FIRST) != 0, 0)) {
+                                    if (o & K10_OP_FIRST) {
                                         mbar_wait(&acc_free[4 * buf + (uint32_t)me],
                                                   (o >> K10_OP_PARITY_SHIFT) & 1u);
                                         k10_fence_after();
                                     }
+                                    if (slot == 0) mbar_wait(&my_tab_full[ts], tphase);
                                     const uint32_t d = tmem_base + buf * K10_ACC_COLS;
                                     const uint32_t a_hi =
                                         a_base + ((o >> (K10_OP_ASTAGE_SHIFT - 6)) & 192u) +
                                         ((o >> (K10_OP_SLICE_SHIFT - 4)) & 48u);
-                                    const uint32_t b = desc_lo + (uint32_t)(sub * 2);
-                                    k10_mma2(d, a_hi, b, desc_hi32, IDESC,
+                                    k10_mma2(d, a_hi, desc, desc_hi32, IDESC,
                                              (o & K10_OP_FIRST) ? 0u : 1u);
-                                    k10_mma2(d, a_hi, b + DESC_LO_HALF, desc_hi32, IDESC, 1u);
-                                    k10_mma2(d, a_hi + 8, b, desc_hi32, IDESC, 1u);
+                                    k10_mma2(d, a_hi, desc + DESC_LO_HALF, desc_hi32, IDESC, 1u);
+                                    k10_mma2(d, a_hi + 8, desc, desc_hi32, IDESC, 1u);
                                     if (o & K10_OP_COMMIT) k10_commit(&acc_full[2 * buf + pipe]);
+                                    desc += 2;
+                                    if (++slot == 4) {
+                                        k10_commit(&my_tab_free[ts]);
+                                        slot = 0;
+                                        desc += DESC_STAGE - 8;
+                                        if (++ts == K10_TSTAGES) {
+                                            ts = 0;
+                                            tphase ^= 1;
+                                            desc = desc_lo0;
+                                        }
+                                    }
                                 }
-                                // this pipeline's MMAs of the box (if any) release the A stage
+                                // this issuer's MMAs of the box (if any) release the A stage
                                 if (o & K10_OP_END) k10_commit(&mma_done[ast]);
                             }
-                            k10_commit(&my_tab_free[ts]);
+                            if (last_round && slot != 0) {
+                                // the last table stage of the segment is a partial one
+                                k10_commit(&my_tab_free[ts]);
+                                desc += DESC_STAGE - 2u * (uint32_t)slot;
+                                slot = 0;
+                                if (++ts == K10_TSTAGES) {
+                                    ts = 0;
+                                    tphase ^= 1;
+                                    desc = desc_lo0;
+                                }
+                            }
                         }
                         __syncwarp();
 #pragma unroll
                         for (int u = 0; u < 4; u++) asm volatile("" : "+r"(nx[u])::"memory");
-                        desc_lo += DESC_STAGE;
-                        if (++ts == K10_TSTAGES) {
-                            ts = 0;
-                            tphase ^= 1;
-                            desc_lo = desc_lo0;
-                        }
                     }
                 }
             }
@@ -683,6 +704,7 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
                                        const uint32_t* ops2, const uint32_t* ops3,
                                        const uint32_t* events0, const uint32_t* events1,
                                        const float* table0, const float* table1,
+                                       const float* table2, const float* table3,
                                        const int32_t* seg_off_host,
                                        int n_segments, int n_groups, int n_pairs, float* out,
                                        int64_t ld_out, int accumulate, void* workspace,
@@ -693,14 +715,15 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     LTB_REQUIRE(n_segments >= 1 && n_segments <= K10_MAXSEG,
                 "group_masks_walk: 1..%d segments", K10_MAXSEG);
     if (n_frames == 0) return LTB_OK;
-    LTB_REQUIRE(tile && boxes && ops0 && ops1 && ops2 && ops3 && events0 && events1 && table0 && table1 &&
+    LTB_REQUIRE(tile && boxes && ops0 && ops1 && ops2 && ops3 && events0 && events1 && table0 && table1 && table2 && table3 &&
                     seg_off_host && out,
                 "group_masks_walk: NULL pointer");
     LTB_REQUIRE(sig_size % 32 == 0 && sig_size < (1ll << 31),
                 "group_masks_walk: sig_size must be a multiple of 32");
     LTB_REQUIRE((uintptr_t)tile % 16 == 0 && ld_tile % 4 == 0 && ld_tile >= sig_size,
                 "group_masks_walk: frame rows must be 16-byte aligned");
-    LTB_REQUIRE((uintptr_t)table0 % 16 == 0 && (uintptr_t)table1 % 16 == 0,
+    LTB_REQUIRE((uintptr_t)table0 % 16 == 0 && (uintptr_t)table1 % 16 == 0 &&
+                    (uintptr_t)table2 % 16 == 0 && (uintptr_t)table3 % 16 == 0,
                 "group_masks_walk: tables must be 16 B aligned");
     LTB_REQUIRE(ld_out >= (int64_t)n_groups * n_pairs * 2, "group_masks_walk: ld_out too small");
     const size_t need = ltb200_group_masks_walk_workspace(n_frames, n_groups, n_pairs, accumulate);
@@ -718,16 +741,20 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     p.events[1] = events1;
     p.table[0] = table0;
     p.table[1] = table1;
+    p.table[2] = table2;
+    p.table[3] = table3;
     const int ns1 = n_segments + 1;
+    // seg_off_host rows: 0 visits, 1..4 words of issuer 0..3, 5..8 table stages, 9..10 events
     for (int s = 0; s <= K10_MAXSEG; s++) {
         const int t = s <= n_segments ? s : n_segments;
         p.visit_off[s] = seg_off_host[t];
-        for (int k = 0; k < 2; k++) {
-            p.op_off[k][s] = seg_off_host[(1 + k) * ns1 + t];
-            p.ev_off[k][s] = seg_off_host[(3 + k) * ns1 + t];
-            LTB_REQUIRE(p.op_off[k][s] % 4 == 0,
-                        "group_masks_walk: op offsets must be multiples of 4");
+        for (int c = 0; c < 4; c++) {
+            p.op_off[c][s] = seg_off_host[(1 + c) * ns1 + t];
+            p.tab_off[c][s] = seg_off_host[(5 + c) * ns1 + t];
+            LTB_REQUIRE(p.op_off[c][s] % 4 == 0,
+                        "group_masks_walk: word offsets must be multiples of 4");
         }
+        for (int k = 0; k < 2; k++) p.ev_off[k][s] = seg_off_host[(9 + k) * ns1 + t];
         LTB_REQUIRE(p.visit_off[s] % (2 * K10_AS) == 0,
                     "group_masks_walk: visit offsets must be multiples of %d", 2 * K10_AS);
     }

@@ -321,11 +321,14 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
                 boxes=dev_u32(w['boxes']),
                 ops=[dev_u32(w[f'ops{c}']) for c in range(4)],
                 events=[dev_u32(w['events0']), dev_u32(w['events1'])],
-                table=[torch.from_numpy(w['table0']).to(device),
-                       torch.from_numpy(w['table1']).to(device)],
+                # (an issuer without ops has an empty table: keep the pointer valid)
+                table=[torch.from_numpy(w[f'table{c}'] if len(w[f'table{c}']) else
+                                        np.zeros((1,) + w[f'table{c}'].shape[1:], np.float32)
+                                        ).to(device) for c in range(4)],
                 seg_off_host=np.ascontiguousarray(
-                    np.stack([w['visit_off'], w['op_off0'], w['op_off1'], w['ev_off0'],
-                              w['ev_off1']]), dtype=np.int32))
+                    np.stack([w['visit_off']] + [w[f'op_off{c}'] for c in range(4)] +
+                             [w[f'tab_off{c}'] for c in range(4)] +
+                             [w['ev_off0'], w['ev_off1']]), dtype=np.int32))
     if (SYM_PATH if sym is None else sym) and banded is not None and len(sig_shape) == 2:
         plan.sym = _sym_to_device(flat, sig_shape, group_size, max(1, n_bands // 2), n_cols,
                                   device)
@@ -397,8 +400,8 @@ def group_masks(tile, plan, out=None, accumulate=False, kernel='auto', chain=0):
                 tile.data_ptr(), F, K, ld_tile, w['boxes'].data_ptr(), w['ops'][0].data_ptr(),
                 w['ops'][1].data_ptr(), w['ops'][2].data_ptr(), w['ops'][3].data_ptr(),
                 w['events'][0].data_ptr(), w['events'][1].data_ptr(),
-                w['table'][0].data_ptr(), w['table'][1].data_ptr(),
-                w['seg_off_host'].ctypes.data,
+                w['table'][0].data_ptr(), w['table'][1].data_ptr(), w['table'][2].data_ptr(),
+                w['table'][3].data_ptr(), w['seg_off_host'].ctypes.data,
                 w['n_segments'], plan.n_groups, plan.n_pairs, real.data_ptr(), ld_out,
                 int(bool(accumulate)), ws.data_ptr(), ws.numel(),
                 torch.cuda.current_stream(tile.device).cuda_stream))

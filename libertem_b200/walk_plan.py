@@ -22,14 +22,13 @@ only the boxes and their A-operand stages:
 * ``boxes``   -- per visit: first pixel of the box | 4-bit mask of the slices that are used;
   every segment holds a multiple of 4 visits (padded with empty ones), so that the A stage and
   the mbarrier parity of a box are static;
-* ``ops[c]``  -- per issuer warp c = g % 4 (two per pipeline), a list aligned with the op
-  stream of its pipeline (own ops, empty words for the other issuer's); per op, in walk order: accumulator buffer, first / last op of an
+* ``ops[c]``  -- per issuer warp c = g % 4 (two per pipeline) its own list; per op, in walk order: accumulator buffer, first / last op of an
   accumulation chain (+ the static mbarrier parity), slice and A stage of the box, first / last
   op of the pipeline in its box (A-stage hand-over with the converter warps; a box without ops
   of the pipeline gets an empty marker word);
 * ``events[p]`` -- per chain: buffer, register slot, group, last-chain-of-the-group (write the
   result), mbarrier parity;
-* ``table[p]`` -- the split-TF32 weight blocks of ``ops[p]`` as the byte image of the kernel's
+* ``table[c]`` -- the split-TF32 weight blocks of ``ops[c]`` as the byte image of the kernel's
   shared-memory stages (4 ops = 32 entries per stage, rows [hi | lo], 128-byte swizzle applied
   on the host so that the kernel issues one contiguous bulk copy per stage).
 
@@ -181,12 +180,14 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
     n_seg = len(bounds) - 1
 
     boxes = []
-    ops = ([], [], [], [])         # per issuer (g % 4): aligned with its pipeline's stream
-    op_slice = ([], [])            # global slice index of every word (-1: no weights)
-    op_group = ([], [])            # group of every word (-1 marker / padding, <= -2 empty chain)
-    op_seq = ([], [])              # position of every op in the walk order (emulator only)
-    events = ([], [])
-    visit_off, op_off, ev_off = [0], ([0], [0]), ([0], [0])
+    ops = ([], [], [], [])         # per issuer (g % 4): its words
+    op_group = ([], [], [], [])    # group of every word (-1 marker / padding, <= -2 empty chain)
+    op_seq = ([], [], [], [])      # position of every op in the walk order (emulator only)
+    slot_slice = ([], [], [], [])  # per table slot of the issuer: global slice index (-1: pad)
+    slot_group = ([], [], [], [])  # per table slot: group (< 0: zero block)
+    events = ([], [])              # per pipeline (= drain group)
+    visit_off, ev_off = [0], ([0], [0])
+    op_off, tab_off = ([0], [0], [0], [0]), ([0], [0], [0], [0])
     for s in range(n_seg):
         v0, v1 = bounds[s], bounds[s + 1]
         seq = []                                   # [box index in the segment, slice, group]
@@ -285,46 +286,42 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
                     events[par][ev] |= nxt << EV_NEXT_SHIFT
                 assert chains[b][0][0] == 0 and not any(v & 1 for v in n_before)
                 assert not uses_p[b][0] & 1 and not uses_p[b][1] & 1
-        # per pipeline: the op stream (= table slot order); a box without ops of the pipeline
-        # gets a marker slot.  Per ISSUER (two per pipeline, groups g % 4 = par and par + 2):
-        # a word list aligned with the stream -- its own ops, empty words for the other
-        # issuer's -- with ITS box hand-over flags (wait for the converters before its first
-        # op of a box, release the A stage after its last one; in a box without own ops both
-        # flags sit on the first word of the box)
-        for par in range(2):
+        # per ISSUER (groups g % 4; two per pipeline): its own word list -- its ops in walk
+        # order, one marker word in a box without own ops -- with its box hand-over flags (wait
+        # for the converters before its first word of a box, release the A stage after its
+        # last one), and its own weight-table stream (the blocks of its ops, 4 per stage;
+        # markers take no table slot; a segment starts on a new stage)
+        for cls in range(4):
             by_box = {}
-            for w in words[par]:
-                by_box.setdefault(w[1], []).append(w)
+            for w in words[cls & 1]:
+                if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 - cls:
+                    by_box.setdefault(w[1], []).append(w)
             for b_i in range(len(seg_boxes)):
-                ws = by_box.get(b_i)
-                if not ws:
-                    ws = [[OP_NOMMA, b_i, 0, -1, -1]]
+                ws = by_box.get(b_i) or [[OP_NOMMA, b_i, 0, -1, -1]]
                 stage_bits = (((b_i % A_STAGES) << OP_ASTAGE_SHIFT) |
                               (((b_i // A_STAGES) & 1) << OP_APARITY_SHIFT))
-                for k in range(2):
-                    cls = par + 2 * k
-                    own = [n for n, w in enumerate(ws)
-                           if w[3] >= 0 and (w[3] & 3) == cls or w[3] == -2 - cls]
-                    first, last = (own[0], own[-1]) if own else (0, 0)
-                    for n, w in enumerate(ws):
-                        word = (w[0] if n in own else OP_NOMMA) | stage_bits
-                        if n == first:
-                            word |= OP_NEW_BOX
-                        if n == last:
-                            word |= OP_END_BOX
-                        ops[cls].append(word)
-                for w in ws:
-                    op_seq[par].append(w[4])
-                    op_group[par].append(w[3])
-                    op_slice[par].append(
-                        (seg_boxes[b_i] & ~31) // SL + w[2] if w[3] != -1 else -1)
-            while len(op_group[par]) % STAGE_OPS:
-                for k in range(2):
-                    ops[par + 2 * k].append(OP_NOP)
-                op_group[par].append(-1)
-                op_slice[par].append(-1)
-                op_seq[par].append(-1)
-            op_off[par].append(len(op_group[par]))
+                for n, w in enumerate(ws):
+                    word = w[0] | stage_bits
+                    if n == 0:
+                        word |= OP_NEW_BOX
+                    if n == len(ws) - 1:
+                        word |= OP_END_BOX
+                    ops[cls].append(word)
+                    op_seq[cls].append(w[4])
+                    op_group[cls].append(w[3])
+                    if w[3] != -1:
+                        slot_slice[cls].append((seg_boxes[b_i] & ~31) // SL + w[2])
+                        slot_group[cls].append(w[3])
+            while len(ops[cls]) % STAGE_OPS:           # whole rounds of 4 words
+                ops[cls].append(OP_NOP)
+                op_seq[cls].append(-1)
+                op_group[cls].append(-1)
+            while len(slot_slice[cls]) % STAGE_OPS:    # the last table stage of the segment
+                slot_slice[cls].append(-1)
+                slot_group[cls].append(-1)
+            op_off[cls].append(len(ops[cls]))
+            tab_off[cls].append(len(slot_slice[cls]) // STAGE_OPS)
+        for par in range(2):
             ev_off[par].append(len(events[par]))
         boxes.extend(seg_boxes)
         visit_off.append(len(boxes))
@@ -333,21 +330,23 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
         n_groups=n_groups, group_size=group_size, sig_size=K, n_segments=n_seg, chain=chain,
         boxes=np.array(boxes, dtype=np.uint32),
         visit_off=np.array(visit_off, dtype=np.int32),
-        n_real_ops=sum(int((np.array(op_group[p]) >= 0).sum()) for p in range(2)),
-        n_entries=sum(len(op_group[p]) for p in range(2)) * SL,
+        n_real_ops=sum(int((np.array(slot_group[c]) >= 0).sum()) for c in range(4)),
+        n_entries=sum(len(slot_slice[c]) for c in range(4)) * SL,
     )
     for p in range(2):
-        sl_p = np.array(op_slice[p], dtype=np.int64)
-        gr_p = np.array(op_group[p], dtype=np.int64)
-        for k in range(2):
-            plan[f'ops{p + 2 * k}'] = np.array(ops[p + 2 * k], dtype=np.uint32)
         plan[f'events{p}'] = np.array(events[p], dtype=np.uint32)
-        plan[f'op_off{p}'] = np.array(op_off[p], dtype=np.int32)
         plan[f'ev_off{p}'] = np.array(ev_off[p], dtype=np.int32)
-        plan[f'op_slice{p}'] = sl_p
-        plan[f'op_group{p}'] = gr_p
-        plan[f'op_seq{p}'] = np.array(op_seq[p], dtype=np.int64)
-        plan[f'table{p}'] = _table_image(flat, group_size, sl_p, gr_p)
+    for c in range(4):
+        sl_c = np.array(slot_slice[c], dtype=np.int64)
+        gr_c = np.array(slot_group[c], dtype=np.int64)
+        plan[f'ops{c}'] = np.array(ops[c], dtype=np.uint32)
+        plan[f'op_off{c}'] = np.array(op_off[c], dtype=np.int32)
+        plan[f'tab_off{c}'] = np.array(tab_off[c], dtype=np.int32)
+        plan[f'op_group{c}'] = np.array(op_group[c], dtype=np.int64)
+        plan[f'op_seq{c}'] = np.array(op_seq[c], dtype=np.int64)
+        plan[f'slot_slice{c}'] = sl_c
+        plan[f'slot_group{c}'] = gr_c
+        plan[f'table{c}'] = _table_image(flat, group_size, sl_c, gr_c)
     return plan
 
 
@@ -389,43 +388,9 @@ def unswizzle_table(table):
     return t[:, np.arange(STAGE_ROWS)[:, None], chunk].reshape(n_stages, STAGE_ROWS, STAGE_OPS, SL)
 
 
-def _merge_issuers(plan, p):
-    """the op stream of pipeline p from its two issuer lists (checks their box flags)"""
-    a, b = plan[f'ops{p}'].astype(np.int64), plan[f'ops{p + 2}'].astype(np.int64)
-    assert len(a) == len(b) == len(plan[f'op_group{p}'])
-    own_a, own_b = (a & OP_NOMMA) == 0, (b & OP_NOMMA) == 0
-    assert not np.any(own_a & own_b)
-    g = plan[f'op_group{p}']
-    assert np.all((g[own_a][g[own_a] >= 0] & 3) == p) and np.all(g[own_a][g[own_a] < 0] == -2 - p)
-    assert np.all((g[own_b][g[own_b] >= 0] & 3) == p + 2) and \
-        np.all(g[own_b][g[own_b] < 0] == -4 - p)
-    stage_mask = (3 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
-    real = (a != OP_NOP) | (b != OP_NOP)
-    assert np.all((a & stage_mask)[real] == (b & stage_mask)[real])
-    merged = np.where(own_b, b, a) & ~(OP_NEW_BOX | OP_END_BOX)
-    # per issuer: exactly one NEW and one END per box, NEW not after its first own op, END not
-    # before its last one; the stream's box boundaries = where the A stage / parity bits change
-    key = (a & stage_mask)
-    box_id = np.concatenate([[0], np.cumsum(key[1:] != key[:-1])])
-    box_id[~real] = -1
-    for lst, own in ((a, own_a), (b, own_b)):
-        for bid in np.unique(box_id[box_id >= 0]):
-            idx = np.nonzero(box_id == bid)[0]
-            new = idx[(lst[idx] & OP_NEW_BOX) != 0]
-            end = idx[(lst[idx] & OP_END_BOX) != 0]
-            assert len(new) == 1 and len(end) == 1 and new[0] <= end[0]
-            mine = idx[own[idx]]
-            if len(mine):
-                assert new[0] <= mine[0] and end[0] >= mine[-1]
-    first = np.concatenate([[True], box_id[1:] != box_id[:-1]]) & real
-    last = np.concatenate([box_id[1:] != box_id[:-1], [True]]) & real
-    merged = merged | np.where(first, OP_NEW_BOX, 0) | np.where(last, OP_END_BOX, 0)
-    return merged
-
-
 def emulate(plan, tile):
     """numpy model of what the kernel does with the lists (float64 arithmetic; checks the
-    invariants the kernel relies on).  The two pipelines are replayed in the walk order of the
+    invariants the kernel relies on).  The four issuers are replayed in the walk order of the
     plan (any interleaving that respects the mbarrier waits gives the same result).
     tile: (F, K) -> (F, n_groups * group_size) complex128"""
     F = tile.shape[0]
@@ -433,10 +398,9 @@ def emulate(plan, tile):
     out = np.zeros((F, G, 2 * gs), dtype=np.float64)
     written = np.zeros(G, dtype=np.int64)
     w = []
-    for p in range(2):
-        t = unswizzle_table(plan[f'table{p}']).astype(np.float64)
+    for c in range(4):
+        t = unswizzle_table(plan[f'table{c}']).astype(np.float64)
         w.append(t[:, :HR] + t[:, HR:])                              # (stages, HR, 4, 8)
-    streams = [_merge_issuers(plan, p) for p in range(2)]
     stage_mask = (3 << OP_ASTAGE_SHIFT) | (1 << OP_APARITY_SHIFT)
     for s in range(plan['n_segments']):
         v0, v1 = plan['visit_off'][s], plan['visit_off'][s + 1]
@@ -452,15 +416,16 @@ def emulate(plan, tile):
                for p in range(2)]
         open_groups = {}
         order = []
-        for p in range(2):
-            o0, o1 = plan[f'op_off{p}'][s], plan[f'op_off{p}'][s + 1]
+        for c in range(4):
+            o0, o1 = plan[f'op_off{c}'][s], plan[f'op_off{c}'][s + 1]
             assert o0 % STAGE_OPS == 0 and o1 % STAGE_OPS == 0
             b_i, in_box = -1, False
+            slot = plan[f'tab_off{c}'][s] * STAGE_OPS      # table slot of the next op
             for i in range(o0, o1):
-                word = int(streams[p][i])
-                if (word & ~stage_mask) == OP_NOP and plan[f'op_group{p}'][i] == -1 \
-                        and not in_box and not word & (OP_NEW_BOX | OP_END_BOX):
-                    continue                           # padding of the last table stage
+                word = int(plan[f'ops{c}'][i])
+                if word == OP_NOP:
+                    assert not in_box and plan[f'op_group{c}'][i] == -1
+                    continue                           # padding of the last round
                 if word & OP_NEW_BOX:
                     assert not in_box
                     b_i += 1
@@ -469,37 +434,42 @@ def emulate(plan, tile):
                 assert ((word >> OP_ASTAGE_SHIFT) & 3) == b_i % A_STAGES
                 assert ((word >> OP_APARITY_SHIFT) & 1) == ((b_i // A_STAGES) & 1)
                 if not word & OP_NOMMA:
-                    order.append((int(plan[f'op_seq{p}'][i]), p, i, b_i))
+                    order.append((int(plan[f'op_seq{c}'][i]), c, i, b_i, slot))
+                    slot += 1
+                else:
+                    assert (word & ~stage_mask) == OP_NOMMA | OP_NEW_BOX | OP_END_BOX
                 if word & OP_END_BOX:
                     in_box = False
-            assert b_i == v1 - v0 - 1 and not in_box
+            assert b_i == v1 - v0 - 1 and not in_box       # every issuer sees every box
+            assert -(-slot // STAGE_OPS) == plan[f'tab_off{c}'][s + 1]
         order.sort()
-        last_seq = [-1, -1]
-        for seq_no, p, i, b_i in order:
-            assert seq_no > last_seq[p]                # a pipeline keeps the walk order
-            last_seq[p] = seq_no
-            word = int(streams[p][i])
+        last_seq = [-1] * 4
+        for seq_no, c, i, b_i, slot in order:
+            assert seq_no > last_seq[c]                # an issuer keeps the walk order
+            last_seq[c] = seq_no
+            p = c & 1
+            word = int(plan[f'ops{c}'][i])
             box_word = int(plan['boxes'][v0 + b_i])
             px0, mask = box_word & ~31, box_word & 15
-            g = int(plan[f'op_group{p}'][i])
-            cls = (g & 3) if g >= 0 else -2 - g        # issuer
-            assert (cls & 1) == p
+            g = int(plan[f'op_group{c}'][i])
+            assert ((g & 3) if g >= 0 else -2 - g) == c
             j = (word >> OP_SLICE_SHIFT) & 3
             assert mask >> j & 1                       # the converters fill only masked slices
-            assert px0 + j * SL == plan[f'op_slice{p}'][i] * SL
+            assert plan[f'slot_slice{c}'][slot] * SL == px0 + j * SL
+            assert plan[f'slot_group{c}'][slot] == g
             b = word & 7
             assert b < NBUF
             x = tile[:, px0 + j * SL:px0 + (j + 1) * SL].astype(np.float64)
-            prod = x @ w[p][i // STAGE_OPS, :, i % STAGE_OPS].T                    # (F, HR)
+            prod = x @ w[c][slot // STAGE_OPS, :, slot % STAGE_OPS].T              # (F, HR)
             if g <= -2:                                # empty chain
                 assert word & OP_FIRST and word & OP_COMMIT and not busy[b]
                 assert not np.any(prod)
             if word & OP_FIRST:
                 assert not busy[b] and g not in open_groups
                 assert ((word >> OP_PARITY_SHIFT) & 1) == \
-                    (uses_c[b][cls] & 1) ^ (1 if cls == 0 else 0)
-                assert next_user[b] == cls             # the last drain was addressed to it
-                uses_c[b][cls] += 1
+                    (uses_c[b][c] & 1) ^ (1 if c == 0 else 0)
+                assert next_user[b] == c               # the last drain was addressed to it
+                uses_c[b][c] += 1
                 busy[b] = True
                 open_groups[g] = b
                 bufs[b] = prod
@@ -520,16 +490,16 @@ def emulate(plan, tile):
                     assert not ev & EV_LAST
                 else:
                     assert (ev >> 8) == g
-                    slot = 1 if ev & EV_SLOT else 0
-                    assert slot == ((g >> 1) & 1)
-                    assert slot_owner[p][slot] in (None, g)
-                    slot_owner[p][slot] = g
-                    acc[p, slot] += bufs[b]
+                    slot_r = 1 if ev & EV_SLOT else 0
+                    assert slot_r == ((g >> 1) & 1)
+                    assert slot_owner[p][slot_r] in (None, g)
+                    slot_owner[p][slot_r] = g
+                    acc[p, slot_r] += bufs[b]
                     if ev & EV_LAST:
-                        out[:, g] += acc[p, slot][:, :2 * gs]
+                        out[:, g] += acc[p, slot_r][:, :2 * gs]
                         written[g] += 1
-                        acc[p, slot] = 0
-                        slot_owner[p][slot] = None
+                        acc[p, slot_r] = 0
+                        slot_owner[p][slot_r] = None
         assert not any(busy) and not evs[0] and not evs[1] and not open_groups
         assert slot_owner == [[None, None], [None, None]]
         assert not any(v & 1 for u in uses_p for v in u) and not any(v & 1 for u in uses_c for v in u)

@@ -48,14 +48,13 @@ def test_walk_plan_radial(S, n_bins, max_order, kw):
     assert plan is not None
     # what the C ABI documents (include/ltb200.h, ltb200_group_masks_walk)
     assert np.all(np.diff(plan['visit_off']) % wp.BOX_PAD == 0)
-    for p in range(2):
-        assert np.all(plan[f'op_off{p}'] % wp.STAGE_OPS == 0)
-        assert len(plan[f'ops{p}']) == len(plan[f'ops{p + 2}']) == plan[f'op_off{p}'][-1]
-        assert plan[f'table{p}'].shape == (plan[f'op_off{p}'][-1] // wp.STAGE_OPS,
-                                           wp.STAGE_ROWS, 32)
-        assert plan[f'table{p}'].dtype == np.float32
+    for c in range(4):
+        assert np.all(plan[f'op_off{c}'] % wp.STAGE_OPS == 0)
+        assert len(plan[f'ops{c}']) == plan[f'op_off{c}'][-1]
+        assert plan[f'table{c}'].shape == (plan[f'tab_off{c}'][-1], wp.STAGE_ROWS, 32)
+        assert plan[f'table{c}'].dtype == np.float32
         # the table holds only TF32 numbers (low 13 bits zero)
-        assert not np.any(plan[f'table{p}'].view(np.uint32) & np.uint32(0x1FFF))
+        assert not np.any(plan[f'table{c}'].view(np.uint32) & np.uint32(0x1FFF))
     assert np.all((plan['boxes'] & ~np.uint32(31)) < flat.shape[1])
     check(plan, flat)
 
