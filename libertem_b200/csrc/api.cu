@@ -59,6 +59,14 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, s
 int encode_tmap_2d_sw(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0,
                       uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
                       CUtensorMapSwizzle swizzle) {
+    return encode_tmap_2d_sw_promo(out, base, dt, dim0, dim1, stride1_bytes, box0, box1, swizzle,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+int encode_tmap_2d_sw_promo(CUtensorMap* out, const void* base, CUtensorMapDataType dt,
+                            uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
+                            uint32_t box1, CUtensorMapSwizzle swizzle,
+                            CUtensorMapL2promotion promotion) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -70,7 +78,7 @@ int encode_tmap_2d_sw(CUtensorMap* out, const void* base, CUtensorMapDataType dt
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, "
                   "box %u x %u)",

@@ -125,6 +125,12 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, s
 int encode_tmap_2d_sw(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0,
                       uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
                       CUtensorMapSwizzle swizzle);
+// same with the L2 promotion granularity (the default above is 256 B: right for streams that
+// walk a row, wasteful for boxes of 128-byte rows visited in another order)
+int encode_tmap_2d_sw_promo(CUtensorMap* out, const void* base, CUtensorMapDataType dt,
+                            uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
+                            uint32_t box1, CUtensorMapSwizzle swizzle,
+                            CUtensorMapL2promotion promotion);
 
 // ---- K6 (tcgen05 dense masked reduction, k6_tensor.cu) used by the K1 dispatcher -----------
 bool k6_shape_ok(const void* tile, int64_t n_frames, int64_t sig_size, int64_t ld_tile);

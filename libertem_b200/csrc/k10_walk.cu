@@ -84,6 +84,7 @@ struct K10Params {
     int* counter;
     int atomic_out;                // several segments: red.add into a zeroed / staged result
     int fgroup;                    // frame blocks per scheduling group
+    int tab_policy;                // L2 policy of the table stream: 0 evict_last, 1 normal, 2 evict_first
 };
 
 struct K10QItem {
@@ -516,7 +517,11 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             // ===== weight-table producer: one ring of K10_TSTAGES stages per issuer, served by
             // one lane that polls whichever ring has a free stage =====
             if (lane == 0) {
-                const uint64_t pol_keep = l2_policy_evict_last();
+                uint64_t pol_keep = l2_policy_evict_last();
+                if (p.tab_policy == 1)
+                    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+                else if (p.tab_policy == 2)
+                    pol_keep = l2_policy_evict_first();
                 int ts[4] = {0, 0, 0, 0};
                 uint32_t tphase[4] = {0, 0, 0, 0};
                 for (uint32_t qn = 0;; qn++) {
@@ -774,11 +779,21 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     p.fgroup = grid;
     if (const char* e = getenv("LTB200_K10_FGROUP"))
         if (atoi(e) > 0) p.fgroup = atoi(e);
+    p.tab_policy = 0;
+    if (const char* e = getenv("LTB200_K10_TABPOL")) p.tab_policy = atoi(e);
     if (p.n_items < grid) grid = (int)p.n_items;
     CUtensorMap tm;
-    int rc = encode_tmap_2d_sw(&tm, tile, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)sig_size,
-                               (uint64_t)n_frames, (uint64_t)ld_tile * 4, 32, K10_FB,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
+    // 128-byte L2 promotion: the boxes are 128-byte row pieces visited in ring order; with the
+    // 256-byte default every box pulled its row neighbour out of DRAM too (1.44x the frame
+    // bytes in ncu), which is gone from L2 (evict_first) before the walk gets there
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* e = getenv("LTB200_K10_PROMO"))
+        promo = atoi(e) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                               : atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : promo;
+    int rc = encode_tmap_2d_sw_promo(&tm, tile, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                     (uint64_t)sig_size, (uint64_t)n_frames,
+                                     (uint64_t)ld_tile * 4, 32, K10_FB,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, promo);
     if (rc != LTB_OK) return rc;
     LTB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 4, st));
     // the segments add their partial sums into a zeroed result (<= 2 addends per element: the

@@ -139,7 +139,7 @@ def _segment_bounds(key, n_ops_visit, n_segments):
     return bounds
 
 
-def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_per_slice=2):
+def build_walk(flat, group_size, n_segments=None, chain=None, max_dup=1.0, max_per_slice=2):
     """flat: (M, K) complex stack, M = n_groups * group_size.  Returns the plan as a dict of
     numpy arrays or None when the stack does not fit this form: K % 32, group_size > HR / 2,
     boxes that would have to be visited more than ``max_dup`` times on average (groups narrower
@@ -149,6 +149,9 @@ def build_walk(flat, group_size, n_segments=None, chain=CHAIN, max_dup=1.0, max_
     (``max_dup=inf, max_per_slice=inf``) are handled by the same lists and pass the numerical
     tests, but one narrow-ring geometry showed a rare data race under stress (NEXT.md), so
     such stacks stay on K7."""
+    if chain is None:
+        import os
+        chain = int(os.environ.get('LTB200_K10_CHAIN', 0)) or CHAIN
     M, K = flat.shape
     if group_size < 1 or M % group_size or K % BOX or 2 * group_size > HR or K >= (1 << 31):
         return None
