@@ -315,6 +315,8 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
                                  max_per_slice=2 if walk_max_dup <= 1.0 else 1 << 30)
         if w is not None:
             def dev_u32(a):
+                if len(a) == 0:                     # keep the pointer valid
+                    a = np.zeros(1, dtype=np.uint32)
                 return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(device)
             plan.walk = dict(
                 n_segments=w['n_segments'], n_entries=w['n_entries'],
