@@ -85,6 +85,7 @@ struct K10Params {
     int atomic_out;                // several segments: red.add into a zeroed / staged result
     int fgroup;                    // frame blocks per scheduling group
     int tab_policy;                // L2 policy of the table stream: 0 evict_last, 1 normal, 2 evict_first
+    uint32_t zero;                 // 0, unknown to the compiler (see the converters)
 };
 
 struct K10QItem {
@@ -301,7 +302,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             if (m < 0) break;
             const uint8_t* dbase = smem + (size_t)stage * K10_BOX_BYTES + row_off;
             // the used slices of a box alternate between the two sets (at most 2 of the 4 each):
-            // load, release the stage, then convert
+            // load, release the stage (once the loads have returned), then convert
             float4 x[2][2];
             int jj[2];
             int n_mine = 0, c = 0;
@@ -327,15 +328,20 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     c++;
                 }
             }
-#pragma unroll
-            for (int s = 0; s < 2; s++)
-#pragma unroll
-                for (int h = 0; h < 2; h++)
-                    if (s < n_mine)
-                        asm volatile("" : "+f"(x[s][h].x), "+f"(x[s][h].y), "+f"(x[s][h].z),
-                                          "+f"(x[s][h].w)::"memory");
+            // The stage may be handed back as soon as the loads have RETURNED.  An empty asm
+            // that only names the registers does not make the hardware wait for them: the arrive
+            // then overtakes the LDS and the TMA refill of the stage (fast when the next box is
+            // L2-resident and boxes carry a single op) lands before the load has read it --
+            // wrong rows in 5-50 % of launches on narrow-ring stacks.  The barrier ADDRESS of the
+            // arrive is therefore made to depend on one word of every LDS.128 (`p.zero` is 0,
+            // but only at run time; a value that is merely computed and not used is dropped by
+            // ptxas): the scoreboard wait of the loads sits in front of the arrive.
+            uint32_t dep = 0;
+            if (n_mine > 0) dep = __float_as_uint(x[0][0].x) ^ __float_as_uint(x[0][1].x);
+            if (n_mine > 1) dep ^= __float_as_uint(x[1][0].x) ^ __float_as_uint(x[1][1].x);
+            dep &= p.zero;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&data_free[stage]);
+            if (lane == 0) mbar_arrive(&data_free[stage] + dep);
             if (++stage == K10_DSTAGES) {
                 stage = 0;
                 dphase ^= 1;
@@ -780,6 +786,7 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     if (const char* e = getenv("LTB200_K10_FGROUP"))
         if (atoi(e) > 0) p.fgroup = atoi(e);
     p.tab_policy = 0;
+    p.zero = 0u;
     if (const char* e = getenv("LTB200_K10_TABPOL")) p.tab_policy = atoi(e);
     if (p.n_items < grid) grid = (int)p.n_items;
     CUtensorMap tm;

@@ -80,6 +80,7 @@ struct K7Params {
     int band_major;                // banded plan: item order [band][frame-block group][ring][fb]
     int quad;                      // entry_px lists QUADS (4 consecutive, 16-byte aligned pixels)
     int64_t sig_size;
+    uint32_t zero;                 // 0, unknown to the compiler (stage release in the converters)
 };
 
 constexpr int K7_PF_PX = 256;         // pixels per L2-prefetch box (x 128 frames = 128 KiB)
@@ -749,16 +750,19 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 for (int j = 0; j < 4; j++)
                     x[s][j] = *reinterpret_cast<const float4*>(
                         dbase + s * K7_SUB_BYTES + (((uint32_t)(hh * 4 + j) ^ swz) << 4));
-            // the stage is in registers (the empty asm pins the loaded values in front of the
-            // arrive): hand it back to the gather producers right away
+            // the stage is handed back to the gather producers as soon as the loads have
+            // RETURNED: the barrier address of the arrive depends on one word of every LDS.128
+            // (`p.zero` is 0, but only at run time), which puts the scoreboard wait of the loads
+            // in front of the arrive.  An empty asm that only names the registers does not --
+            // the arrive could overtake the loads (found with K10, csrc/k10_walk.cu).
+            uint32_t dep = 0;
 #pragma unroll
             for (int s = 0; s < 2; s++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    asm volatile("" : "+f"(x[s][j].x), "+f"(x[s][j].y), "+f"(x[s][j].z),
-                                      "+f"(x[s][j].w)::"memory");
+                for (int j = 0; j < 4; j++) dep ^= __float_as_uint(x[s][j].x);
+            dep &= p.zero;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&data_free[stage]);
+            if (lane == 0) mbar_arrive(&data_free[stage] + dep);
             if (++stage == K7_DSTAGES) {
                 stage = 0;
                 dphase ^= 1;
@@ -957,6 +961,7 @@ static int k7_run(const float* tile, int64_t n_frames, int64_t sig_size, int64_t
     p.prefetch = 0;
     p.band_major = 0;
     p.sig_size = sig_size;
+    p.zero = 0u;
     CUtensorMap tmt = tm;
     if (quad) {
         p.fbgroup = 8;

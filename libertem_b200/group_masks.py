@@ -259,7 +259,7 @@ def build_sym(stack3, group_size, n_bands):
 
 
 def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None,
-               walk_max_dup=1.0):
+               walk_max_dup=1.5):
     """stack: complex (M, *sig) dense array with M = n_groups * group_size (``sig_shape`` gives
     the 2D signal shape when the stack comes flattened)"""
     M = stack.shape[0]
@@ -311,8 +311,7 @@ def build_plan(stack, group_size, device, n_bands=None, sig_shape=None, sym=None
     plan = GroupPlan(entry_px, pack_rows(table), np.array(offs, dtype=np.int32), n_groups,
                      group_size, M, device, table_split=split, n_cols=n_cols, banded=banded)
     if WALK_PATH and n_cols and n_groups > 0:
-        w = walk_plan.build_walk(flat, group_size, max_dup=walk_max_dup,
-                                 max_per_slice=2 if walk_max_dup <= 1.0 else 1 << 30)
+        w = walk_plan.build_walk(flat, group_size, max_dup=walk_max_dup)
         if w is not None:
             def dev_u32(a):
                 if len(a) == 0:                     # keep the pointer valid

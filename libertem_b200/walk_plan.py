@@ -139,16 +139,13 @@ def _segment_bounds(key, n_ops_visit, n_segments):
     return bounds
 
 
-def build_walk(flat, group_size, n_segments=None, chain=None, max_dup=1.0, max_per_slice=2):
+def build_walk(flat, group_size, n_segments=None, chain=None, max_dup=1.5, max_per_slice=None):
     """flat: (M, K) complex stack, M = n_groups * group_size.  Returns the plan as a dict of
-    numpy arrays or None when the stack does not fit this form: K % 32, group_size > HR / 2,
-    boxes that would have to be visited more than ``max_dup`` times on average (groups narrower
-    than a quarter of a box), or more than ``max_per_slice`` groups on one 8-pixel slice.  The
-    defaults admit what the kernel is validated for on hardware -- every box visited once, at
-    most two (adjacent) groups per slice, i.e. rings at least ~11 pixels wide; generic stacks
-    (``max_dup=inf, max_per_slice=inf``) are handled by the same lists and pass the numerical
-    tests, but one narrow-ring geometry showed a rare data race under stress (NEXT.md), so
-    such stacks stay on K7."""
+    numpy arrays or None when the stack does not fit this form: K % 32, group_size > HR / 2, or
+    boxes that would have to be visited more than ``max_dup`` times on average (a box whose
+    groups span more than W_LIVE is visited once per window: groups much narrower than a quarter
+    of a box are better served by the gathered plan of K7).  ``max_per_slice`` optionally bounds
+    the groups on one 8-pixel slice."""
     if chain is None:
         import os
         chain = int(os.environ.get('LTB200_K10_CHAIN', 0)) or CHAIN
@@ -169,7 +166,7 @@ def build_walk(flat, group_size, n_segments=None, chain=None, max_dup=1.0, max_p
         return None
     if n_visits > max_dup * max(1, int(bx.any(axis=0).sum())):
         return None
-    if int(sl.sum(axis=0).max()) > max_per_slice:
+    if max_per_slice is not None and int(sl.sum(axis=0).max()) > max_per_slice:
         return None
     sl4 = sl.reshape(n_groups, K // BOX, BOX // SL)
     n_ops_visit = np.zeros(n_visits, dtype=np.int64)

@@ -16,7 +16,8 @@ dev = torch.device('cuda')
 bad_total = 0
 CASES = [(128, 8, 24, 300), (256, 16, 24, 257), (128, 8, 24, 1000), (128, 16, 6, 2000),
          (128, 11, 24, 1000), (128, 8, 6, 2000), (128, 16, 24, 1000), (256, 16, 6, 2000),
-         (128, 16, 6, 1000), (128, 16, 24, 2000), (128, 16, 5, 2000), (128, 16, 7, 2000)]
+         (128, 16, 6, 1000), (128, 16, 24, 2000), (128, 16, 5, 2000), (128, 16, 7, 2000),
+         (512, 32, 24, 1024), (256, 16, 7, 3000), (128, 8, 7, 4000), (128, 8, 11, 2000)]
 if len(sys.argv) > 2:
     CASES = [CASES[int(a)] for a in sys.argv[2:]]
 for S, nb, mo, F in CASES:

@@ -306,6 +306,30 @@ def test_group_masks_walk_bands(n_groups, size, K, F):
     assert np.abs(out - ref).max() / scale <= 2e-6
 
 
+@pytest.mark.parametrize('max_order', [6, 7])
+def test_group_masks_walk_narrow_rings_repeated(max_order):
+    """regression: boxes with a single op hand their shared-memory stage back almost at once;
+    the converters used to release it before their loads had returned (an empty asm is no
+    scoreboard wait) and the TMA refill corrupted rows of the outermost rings in 5-50 % of the
+    launches of exactly this geometry (scripts/k10_stress.py)"""
+    from libertem_b200 import engine, group_masks as gm
+    S, F = 128, 2000
+    flat = _radial_flat(S, 16, max_order)
+    plan = gm.build_plan(flat, max_order + 1, torch.device('cuda'), walk_max_dup=1e9)
+    assert plan.walk is not None
+    data = synth.uniform_f32(0, F * S * S, 23).reshape(F, S * S)
+    t = torch.from_numpy(data).cuda()
+    ref = data.astype(np.float64) @ flat.astype(np.complex128).T
+    scale = (np.abs(data).astype(np.float64) @ np.abs(flat).astype(np.float64).T).max() + 1e-30
+    first = None
+    for _ in range(25):
+        out = gm.group_masks(t, plan, kernel='walk').cpu().numpy()
+        assert engine.last_kernel() == 10
+        assert np.abs(out - ref).max() / scale <= 2e-6
+        first = out if first is None else first
+        assert np.array_equal(out, first)
+
+
 def test_group_masks_walk_rejects():
     from libertem_b200 import _lib, group_masks as gm
     flat = _radial_flat(128, 16, 6)              # narrow rings: no walk plan by default

@@ -70,8 +70,7 @@ def test_walk_plan_bands(n_groups, size, K, seed):
 
 @pytest.mark.parametrize('seed', range(4))
 def test_walk_plan_generic_stacks(seed):
-    """random supports (boxes visited once per window of 4 groups, many groups per slice): the
-    lists are still exact -- only the kernel's default routing excludes such stacks"""
+    """random supports (boxes visited once per window of 4 groups, many groups per slice)"""
     rng = np.random.default_rng(seed)
     n_groups, size, K = int(rng.integers(2, 10)), int(rng.integers(1, 9)), 32 * int(rng.integers(4, 24))
     stack = np.zeros((n_groups * size, K), dtype=np.complex64)
@@ -79,16 +78,19 @@ def test_walk_plan_generic_stacks(seed):
         px = np.sort(rng.choice(K, size=int(rng.integers(1, K // 2)), replace=False))
         stack[g * size:(g + 1) * size, px] = (rng.random((size, len(px))) - 0.5 +
                                               1j * (rng.random((size, len(px))) - 0.5))
-    plan = wp.build_walk(stack, size, max_dup=np.inf, max_per_slice=1 << 30)
+    plan = wp.build_walk(stack, size, max_dup=np.inf)
     assert plan is not None
     check(plan, stack, seed=seed)
 
 
 def test_walk_plan_gate():
-    """narrow rings (boxes that span more than 4 groups, or 3 groups on a slice) are not
-    admitted by default: those stacks stay on K7"""
+    """narrow rings (boxes that span more than 4 groups would be visited > 1.5 times on average)
+    are not admitted by default: those stacks stay on K7"""
     flat = radial_stack(128, 16, 6)
     assert wp.build_walk(flat, 7) is None
-    assert wp.build_walk(flat, 7, max_dup=np.inf, max_per_slice=1 << 30) is not None
+    assert wp.build_walk(flat, 7, max_per_slice=2, max_dup=np.inf) is None
+    plan = wp.build_walk(flat, 7, max_dup=np.inf)
+    assert plan is not None
+    check(plan, flat)
     assert wp.build_walk(radial_stack(64, 4, 6)[:, :4010], 7) is None      # K % 32
     assert wp.build_walk(np.zeros((58, 64), np.complex64), 29) is None     # > 28 columns
