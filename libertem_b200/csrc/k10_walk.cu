@@ -396,7 +396,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
             mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
             const K10QItem qi = queue[q];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&q_free[q]);
+            if (lane == 0) mbar_arrive(&q_free[q] + ((uint32_t)qi.item & p.zero));
             if (qi.item < 0) break;
             const int e0 = p.ev_off[grp][qi.seg], e1 = p.ev_off[grp][qi.seg + 1];
             const uint32_t* __restrict__ events = p.events[grp];
@@ -534,7 +534,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                     const int q = qn % K10_QLEN;
                     mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
                     const K10QItem qi = queue[q];
-                    mbar_arrive(&q_free[q]);
+                    mbar_arrive(&q_free[q] + ((uint32_t)qi.item & p.zero));
                     if (qi.item < 0) break;
                     int t[4], t1[4];
 #pragma unroll
@@ -592,7 +592,7 @@ k10_walk_kernel(const __grid_constant__ CUtensorMap tm_tile, const K10Params p) 
                 mbar_wait(&q_full[q], (qn / K10_QLEN) & 1);
                 const K10QItem qi = queue[q];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&q_free[q]);
+                if (lane == 0) mbar_arrive(&q_free[q] + ((uint32_t)qi.item & p.zero));
                 if (qi.item < 0) break;
                 const int o0 = p.op_off[me][qi.seg], o1 = p.op_off[me][qi.seg + 1];
                 uint32_t w_next = o0 + lane < o1 ? ops[o0 + lane] : K10_OP_NOMMA;

@@ -52,6 +52,7 @@ struct K1Params {
     int accumulate;
     int n_stages;
     float* sig_part;       // pair kernel only: (gridDim.x, sig_size) per-CTA frame sums or NULL
+    uint32_t zero;         // 0, unknown to the compiler (orders the stage release after the loads)
 };
 
 __host__ __device__ constexpr size_t k1_stage_bytes(int nrows) {
@@ -213,8 +214,13 @@ k1_dense_tma_kernel(const __grid_constant__ CUtensorMap tm_data,
                     }
                 }
             }
+            // the stage goes back to the producer only when its loads have RETURNED: the barrier
+            // address depends on the accumulator fed by the last data and mask loads (p.zero is
+            // 0 at run time only) -- mbarrier.arrive does not wait for LDS in flight by itself
+            // (found with K10, csrc/k10_walk.cu)
+            const uint32_t dep = __float_as_uint(acc[FR - 1][NM - 1].y) & p.zero;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0) mbar_arrive(&empty_bar[stage] + dep);
             if (++since_flush == FLUSH_EVERY) {
                 flush();
                 since_flush = 0;
@@ -658,6 +664,7 @@ static int run_tma_group(const void* tile, int64_t n_frames, int64_t sig_size, i
     const int sms = sm_count();
     const int64_t n_fb = (n_frames + K1_FB - 1) / K1_FB;
     K1Params p;
+    p.zero = 0u;
     p.n_frames = n_frames;
     p.sig_size = sig_size;
     p.n_masks = nm;

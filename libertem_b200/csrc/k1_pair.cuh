@@ -307,8 +307,10 @@ k1_pair_kernel(const __grid_constant__ CUtensorMap tm_data,
                         }
                     }
                 }
+                // release after the loads have returned (see k1_dense_tma_kernel)
+                const uint32_t dep = __float_as_uint(acc[FR - 1][NP - 1].y) & p.zero;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (lane == 0) mbar_arrive(&empty_bar[stage] + dep);
                 if (++since_flush == FLUSH_EVERY) {
                     flush();
                     since_flush = 0;

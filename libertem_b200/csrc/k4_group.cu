@@ -45,6 +45,7 @@ struct K4Params {
     int accumulate;
     int64_t n_items;
     int* counter;
+    uint32_t zero;                 // 0, unknown to the compiler (stage release after the loads)
 };
 
 struct K4Meta {
@@ -226,8 +227,10 @@ k4_group_kernel(const __grid_constant__ CUtensorMap tm_table, const K4Params p) 
                     }
                 }
             }
+            // release after the loads have returned (see k1_dense_tma_kernel)
+            const uint32_t dep = __float_as_uint(acc[FR - 1][NP - 1].y) & p.zero;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0) mbar_arrive(&empty_bar[stage] + dep);
             since_flush++;
             if (since_flush == 16 || m.last) {      // chains of <= 256 terms
                 flush();
@@ -283,6 +286,7 @@ extern "C" int ltb200_group_masks(const void* tile, int tile_dtype, int64_t n_fr
                             256, K4_NPR);
     if (rc != LTB_OK) return rc;
     K4Params p;
+    p.zero = 0u;
     p.tile = (const float*)tile;
     p.n_frames = n_frames;
     p.ld_tile = ld_tile;

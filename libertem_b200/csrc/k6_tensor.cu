@@ -80,6 +80,7 @@ struct K6Params {
     int chain;             // sub-stages per TMEM accumulation chain
     int debug;             // bring-up switches (LTB200_K6_DEBUG): 1 no convert, 2 no MMA, 4 no drain
     unsigned long long* sig_acc;   // uint16 tiles: (sig_size) exact integer frame sums, or NULL
+    uint32_t zero;                 // 0, unknown to the compiler (stage release of the sum warps)
 };
 
 // per input type: a data stage is one 128-byte row per frame = 32 float32 or 64 uint16 pixels,
@@ -624,7 +625,9 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                         s1 += v >> 16;
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&data_free[ds]);
+                    // the release must not overtake the loads of this stage: its address depends
+                    // on the sums (p.zero is 0 at run time only), see k7_group_tensor.cu
+                    if (lane == 0) mbar_arrive(&data_free[ds] + ((s0 ^ s1) & p.zero));
                     s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
                     s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
                     s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
@@ -781,6 +784,7 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
     p.chain = chain > 0 ? chain : k6_default_chain();
     p.debug = 0;
     p.sig_acc = nullptr;
+    p.zero = 0u;
     if (const char* e = getenv("LTB200_K6_DEBUG")) p.debug = atoi(e);
     const int grid = (int)(p.n_items < sms ? p.n_items : sms);
     if (sig_sum != nullptr) {

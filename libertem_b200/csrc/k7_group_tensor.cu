@@ -558,7 +558,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
                 const int q = qn % K7_QLEN;
                 mbar_wait(&q_full[q], (qn / K7_QLEN) & 1);
                 const K7QItem qi = queue[q];
-                mbar_arrive(&q_free[q]);
+                mbar_arrive(&q_free[q] + ((uint32_t)qi.item & p.zero));
                 const int nch = qi.item < 0 ? 1 : qi.nchunks;
                 for (int c = 0; c < nch; c++) {
                     mbar_wait(&tab_free[ts], tphase ^ 1);
@@ -657,7 +657,7 @@ k7_group_tensor_kernel(const __grid_constant__ CUtensorMap tm_table,
             mbar_wait(&q_full[q], (qn / K7_QLEN) & 1);
             const K7QItem qi = queue[q];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&q_free[q]);
+            if (lane == 0) mbar_arrive(&q_free[q] + ((uint32_t)qi.item & p.zero));
             if (qi.item < 0) break;
             float acc[2][NQ];
 #pragma unroll
