@@ -81,6 +81,8 @@ struct K6Params {
     int debug;             // bring-up switches (LTB200_K6_DEBUG): 1 no convert, 2 no MMA, 4 no drain
     unsigned long long* sig_acc;   // uint16 tiles: (sig_size) exact integer frame sums, or NULL
     uint32_t zero;                 // 0, unknown to the compiler (stage release of the sum warps)
+    int issuers;                   // 1: warp 2 issues every MMA; 2: warp 3 takes frame group 1
+    int three;                     // 1: lo(x) meets hi(mask) only (N / 2 columns): "3xTF32"
 };
 
 // per input type: a data stage is one 128-byte row per frame = 32 float32 or 64 uint16 pixels,
@@ -163,6 +165,23 @@ __device__ __forceinline__ void tc_ld_fence16(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tc_ldn(uint32_t taddr, uint32_t (&r)[16]) { tc_ld16(taddr, r); }
+__device__ __forceinline__ void tc_ld_fencen(uint32_t (&r)[16]) { tc_ld_fence16(r); }
+__device__ __forceinline__ void tc_ldn(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_fencen(uint32_t (&r)[8]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+                   "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -241,8 +260,24 @@ struct K6Smem {
     static constexpr uint32_t total(int n) { return bar_off(n) + 256 + 1024; }   // + align slack
 };
 
-template <int N, typename TIN>
-__global__ void __launch_bounds__(K6In<TIN>::THREADS, 1)
+// DW ("drain warps", float32 tiles with N = 64 only): the accumulators are drained by eight
+// extra warps (12..19) instead of the converters.  At 25-32 columns the converters' instruction
+// stream per sub-stage (conversion + 64-column drain, ~330 instructions at ~5 cycles each in a
+// warp that owns its frame rows alone) was longer than the HBM time of the sub-stage; the drain
+// is a third of it and runs concurrently here.  Handshake: the MMA warp commits `acc_full[b]` at
+// the end of a chain and waits for `acc_free[b]` (8 drain warps) before it restarts buffer b;
+// chains are numbered over the lifetime of the CTA, so every parity is (chain / 2) & 1.
+// DWM = 2 additionally doubles the converter warps (4..19, drain warps 20..27): the two warps
+// of a frame-row quarter split the 32 pixels of the sub-stage, which halves the instruction
+// stream in front of every A-operand hand-over (the bound at 25-32 columns once the drain is
+// gone: ncu warp-state samples sit on the conversion ALU code, not on the mbarrier waits).
+constexpr int K6_DRAIN_WARPS = 8;
+__host__ __device__ constexpr int k6_threads(int base, int dwm) {
+    return base + (dwm > 0 ? K6_DRAIN_WARPS * 32 : 0) + (dwm == 2 ? K6_CONV_WARPS * 32 : 0);
+}
+
+template <int N, typename TIN, int DWM = 0>
+__global__ void __launch_bounds__(k6_threads(K6In<TIN>::THREADS, DWM), 1)
 k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                  const __grid_constant__ CUtensorMap tm_mask, const K6Params p) {
     constexpr int NH = N / 2;
@@ -251,6 +286,11 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
     constexpr uint32_t MASK_BYTES = (uint32_t)N * 128u;
     constexpr uint32_t IDESC = umma_idesc_tf32(N);
     static_assert(N % 16 == 0 && N >= 16 && N <= 64, "K6: N in {16, 32, 48, 64}");
+    constexpr bool DW = DWM > 0;
+    constexpr int CONVW = DWM == 2 ? 2 * K6_CONV_WARPS : K6_CONV_WARPS;
+    // registers per role after setmaxnreg: 640 x 96 -> 40 / 88 / 128; 896 x 72 -> 40 / 64 / 104
+    constexpr int DRAIN_COLS = DWM == 2 ? 8 : 16;     // columns per tcgen05.ld round of the drain
+    static_assert(!DW || (N == 64 && K6In<TIN>::HALVES == 1), "K6 drain warps: float32, N = 64");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -263,7 +303,9 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
     uint64_t* mask_empty = mask_full + K6_MS;         // [MS]
     uint64_t* a_full = mask_empty + K6_MS;            // [AS]  lo parts written to TMEM
     uint64_t* mma_done = a_full + K6_AS;              // [AS]  MMAs of the sub-stage completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + K6_AS);
+    uint64_t* acc_full = mma_done + K6_AS;            // [2]   DW: chain in buffer b completed
+    uint64_t* acc_free = acc_full + 2;                // [2]   DW: buffer b drained (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
     // warp index made warp-uniform for the compiler: the MMA issue loop must be uniform control
     // flow, otherwise every UTCHMMA is wrapped in an election loop (~90 cycles per issue)
@@ -274,15 +316,19 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
         for (int s = 0; s < K6_DS; s++) {
             mbar_init(&data_full[s], 1);
             mbar_init(&data_free[s],
-                      K6_CONV_WARPS + (p.sig_acc != nullptr ? K6In<TIN>::SUM_WARPS : 0));
+                      CONVW + (p.sig_acc != nullptr ? K6In<TIN>::SUM_WARPS : 0));
         }
         for (int s = 0; s < K6_MS; s++) {
             mbar_init(&mask_full[s], 1);
-            mbar_init(&mask_empty[s], 1);
+            mbar_init(&mask_empty[s], p.issuers);
         }
         for (int s = 0; s < K6_AS; s++) {
-            mbar_init(&a_full[s], K6_CONV_WARPS);
-            mbar_init(&mma_done[s], 1);
+            mbar_init(&a_full[s], CONVW);
+            mbar_init(&mma_done[s], p.issuers);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&acc_full[s], p.issuers);
+            mbar_init(&acc_free[s], K6_DRAIN_WARPS);
         }
         fence_mbar_init();
     }
@@ -300,8 +346,11 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 
     const int chain = p.chain;
 
+    // DW: 640 threads x 96 registers are re-dealt per role (setmaxnreg, whole warpgroups):
+    // producers / issuer 40, converters 88, drain warps 128
     if (warp == 0) {
         // ===== frame stream producer =====
+        if constexpr (DW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (lane == 0) {
             prefetch_tmap(&tm_data);
             const uint64_t pol = l2_policy_evict_first();
@@ -324,6 +373,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
         }
     } else if (warp == 1) {
         // ===== mask tile producer =====
+        if constexpr (DW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (lane == 0) {
             prefetch_tmap(&tm_mask);
             const uint64_t pol = l2_policy_evict_last();
@@ -342,9 +392,20 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == 2 || (warp == 3 && p.issuers == 2)) {
         // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+        // One thread issues a tcgen05.mma at most every ~45 cycles (scripts/ubench/
+        // mma_rate_probe.cu), i.e. 16 MMAs = 710 cycles of the ~1400 a sub-stage has at the HBM
+        // rate; with `issuers == 2` warp 3 issues the MMAs of frame group 1 and commits onto the
+        // same mbarriers (count 2), which halves the issue phase of the hand-over loop.
+        if constexpr (DW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        // `three`: the lo(x) MMAs read only the hi(mask) rows [0, NH) of the tile (N = NH)
+        const uint32_t idesc_lo =
+            (NH % 16 == 0 && p.three) ? umma_idesc_tf32(NH % 16 == 0 ? NH : N) : IDESC;
+        const int g_lo = (p.issuers == 2 && warp == 3) ? 1 : 0;
+        const int g_hi = (p.issuers == 2 && warp == 2) ? 1 : 2;
         uint32_t it = 0;
+        uint32_t gc = 0;                             // DW: chains started by this CTA
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int64_t k0 = (item % p.ksplit) * p.k_per_split;
             int64_t k1 = k0 + p.k_per_split;
@@ -356,6 +417,15 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 const int as = it % K6_AS;
                 mbar_wait(&mask_full[ms], (it / K6_MS) & 1);
                 mbar_wait(&a_full[as], (it / K6_AS) & 1);
+                bool chain_last = false;
+                if constexpr (DW) {
+                    if (in_chain == 0) {
+                        // buffer gc & 1 restarts: its previous chain (gc - 2) must be drained
+                        cbuf = (int)(gc & 1u);
+                        mbar_wait(&acc_free[cbuf], ((gc >> 1) & 1u) ^ 1u);
+                    }
+                    chain_last = in_chain + 1 == chain || i == n_sub - 1;
+                }
                 tc_fence_after();
                 const uint64_t bdesc0 =
                     umma_desc_k_sw128(smem_u32(smem + K6Smem::mask_off(ms, N)));
@@ -365,30 +435,44 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     if (!(p.debug & 2)) {
 #pragma unroll
                         for (int g = 0; g < 2; g++) {
+                            if (g < g_lo || g >= g_hi) continue;
 #pragma unroll
                             for (int kk = 0; kk < 4; kk++) {
                                 const uint64_t bdesc = bdesc0 + (uint64_t)(kk * 2);   // +32 bytes
                                 tc_mma_tf32_ts(d0 + g * 2 * N, a0 + g * 64 + kk * 8, bdesc, IDESC,
                                                (in_chain | kk) != 0 ? 1u : 0u);
                                 tc_mma_tf32_ts(d0 + g * 2 * N, a0 + g * 64 + 32 + kk * 8, bdesc,
-                                               IDESC, 1u);
+                                               idesc_lo, 1u);
                             }
                         }
                     }
                     tc_commit(&mma_done[as]);
                     tc_commit(&mask_empty[ms]);
+                    if (DW && chain_last) tc_commit(&acc_full[cbuf]);
                 }
                 __syncwarp();
-                if (++in_chain == chain) {
+                if constexpr (DW) {
+                    in_chain++;
+                    if (chain_last) {
+                        in_chain = 0;
+                        gc++;
+                    }
+                } else if (++in_chain == chain) {
                     in_chain = 0;
                     cbuf ^= 1;
                 }
             }
         }
-    } else if (warp >= 4 && warp < 4 + K6_CONV_WARPS) {
+    } else if (DW && warp == 3) {
+        // (setmaxnreg is warpgroup-wide: the TMEM-allocating warp of warpgroup 0 joins in)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    } else if (warp >= 4 && warp < 4 + CONVW) {
         // ===== converters / accumulator drain =====
+        if constexpr (DWM == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        if constexpr (DWM == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         const int cw = warp - 4;
-        const int g = cw >> 2;
+        const int px_half = cw >> 3;                // DWM == 2: which 16 pixels of the sub-stage
+        const int g = (cw >> 2) & 1;
         const int w = cw & 3;                       // == warp % 4: the TMEM lane quarter
         const int row = g * 128 + w * 32 + lane;    // frame row inside the item
         const uint32_t lane_sel = (uint32_t)(w * 32) << 16;
@@ -462,8 +546,10 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 const uint8_t* rp = smem + K6Smem::data_off(ds) + row_off;
                 uint4 x[8];                           // this frame's 128-byte row of the stage
 #pragma unroll
-                for (int j = 0; j < 8; j++)
+                for (int j = 0; j < 8; j++) {
+                    if (DWM == 2 && (j >> 2) != px_half) continue;     // (its 64-byte half)
                     x[j] = *reinterpret_cast<const uint4*>(rp + (((uint32_t)j ^ swz) << 4));
+                }
 #pragma unroll
                 for (int h2 = 0; h2 < HALVES; h2++, it++) {
                     const int i = di * HALVES + h2;
@@ -473,7 +559,8 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     int known = i - K6_AS;
                     // chain i/chain - 2 shares its accumulator with the chain that starts at
                     // sub-stage i: it must be drained before this sub-stage is handed to the MMAs
-                    if (i % chain == 0 && i >= 2 * chain) {
+                    // (DW: the MMA warp waits for the drain warps instead)
+                    if (!DW && i % chain == 0 && i >= 2 * chain) {
                         const int must = i - chain - 1;
                         if (must > known) {
                             const uint32_t itm = it - (uint32_t)(i - must);
@@ -486,7 +573,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     // them after the conversion below (the load latency hides behind the ALU work)
                     uint32_t v[N / 16][16];
                     bool pend = false;
-                    if (known >= 0 && !(p.debug & 4) && next_chain * chain < n_sub &&
+                    if (!DW && known >= 0 && !(p.debug & 4) && next_chain * chain < n_sub &&
                         chain_end(next_chain) <= known) {
                         const uint32_t d =
                             tmem_base + lane_sel + (uint32_t)((g * 2 + (next_chain & 1)) * N);
@@ -500,6 +587,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         if (p.debug & 1) break;
+                        if (DWM == 2 && h != px_half) continue;
                         uint32_t hi[16], lo[16];
                         if constexpr (HALVES == 1) {
 #pragma unroll
@@ -564,6 +652,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     }
                 }
             }
+            if constexpr (DW) continue;               // drained and stored by warps 12..19
             // item tail: the last commit covers every earlier MMA of the item
             {
                 const uint32_t itl = it - 1;
@@ -589,6 +678,80 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
                     for (int c = 0; c < NH; c++)
                         if (c < p.n_masks) o[c] = acc[c];
+                }
+            }
+        }
+    } else if (DW && warp >= 4 + CONVW) {
+        // ===== DW: accumulator drain (thread <-> frame row = TMEM lane, like the converters) =====
+        if constexpr (DW) {
+            if constexpr (DWM == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+            if constexpr (DWM == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+            const int cw = warp - (4 + CONVW);
+            const int g = cw >> 2;
+            const int w = cw & 3;                   // == warp % 4: the TMEM lane quarter
+            const int row = g * 128 + w * 32 + lane;
+            const uint32_t lane_sel = (uint32_t)(w * 32) << 16;
+            uint32_t gc = 0;
+            for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int64_t fb = item / p.ksplit;
+                const int ksi = (int)(item % p.ksplit);
+                const int64_t k0 = (int64_t)ksi * p.k_per_split;
+                int64_t k1 = k0 + p.k_per_split;
+                if (k1 > p.sig_size) k1 = p.sig_size;
+                const int n_sub = (int)((k1 - k0 + PX - 1) / PX);
+                const int n_chains = (n_sub + chain - 1) / chain;
+                // two-level sum of the chain totals (see the converters): 32 chains, then up
+                float acc[NH], acc_hi[NH];
+#pragma unroll
+                for (int c = 0; c < NH; c++) acc[c] = acc_hi[c] = 0.f;
+                int in_block = 0;
+                for (int c = 0; c < n_chains; c++, gc++) {
+                    const uint32_t b = gc & 1u;
+                    mbar_wait(&acc_full[b], (gc >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + lane_sel + (uint32_t)((g * 2 + (int)b) * N);
+                    // columns [0, 32): x * hi(mask), [32, 64): x * lo(mask); 16 columns of each
+                    // per round keep the live registers at acc + acc_hi + 32
+#pragma unroll
+                    for (int h = 0; h < NH / DRAIN_COLS; h++) {
+                        uint32_t vh[DRAIN_COLS], vl[DRAIN_COLS];
+                        tc_ldn(d + h * DRAIN_COLS, vh);
+                        tc_ldn(d + NH + h * DRAIN_COLS, vl);
+                        tc_wait_ld();
+                        tc_ld_fencen(vh);
+                        tc_ld_fencen(vl);
+#pragma unroll
+                        for (int j = 0; j < DRAIN_COLS; j++)
+                            acc[h * DRAIN_COLS + j] +=
+                                __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_free[b]);
+                    if (++in_block == 32) {
+                        in_block = 0;
+#pragma unroll
+                        for (int cc = 0; cc < NH; cc++) {
+                            acc_hi[cc] += acc[cc];
+                            acc[cc] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NH; c++) acc[c] += acc_hi[c];
+                const int64_t f = fb * K6_FB + row;
+                if (f < p.n_frames) {
+                    if (p.ksplit == 1) {
+                        float* o = p.out + f * p.ld_out;
+#pragma unroll
+                        for (int c = 0; c < NH; c++)
+                            if (c < p.n_masks) o[c] = p.accumulate ? (o[c] + acc[c]) : acc[c];
+                    } else {
+                        float* o = p.part + ((int64_t)ksi * p.n_frames + f) * p.n_masks;
+#pragma unroll
+                        for (int c = 0; c < NH; c++)
+                            if (c < p.n_masks) o[c] = acc[c];
+                    }
                 }
             }
         }
@@ -696,10 +859,10 @@ static K6Ws k6_ws(int64_t n_frames, int64_t sig_size, int n_masks, int px, bool 
     return w;
 }
 
-template <int N, typename TIN>
+template <int N, typename TIN, int DWM = 0>
 static int k6_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K6Params& p, int grid,
                      cudaStream_t st) {
-    auto kern = k6_tensor_kernel<N, TIN>;
+    auto kern = k6_tensor_kernel<N, TIN, DWM>;
     const size_t smem = K6Smem::total(N);
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -709,7 +872,7 @@ static int k6_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K6Par
                                             (int)smem));
         configured_dev = dev;
     }
-    kern<<<grid, K6In<TIN>::THREADS, smem, st>>>(tmd, tmm, p);
+    kern<<<grid, k6_threads(K6In<TIN>::THREADS, DWM), smem, st>>>(tmd, tmm, p);
     count_launch();
     LTB_CUDA_CHECK(cudaGetLastError());
     return LTB_OK;
@@ -749,6 +912,33 @@ int k6_default_chain() {
     return chain;
 }
 
+// 25-32 columns: drain warps on (LTB200_K6_DW=0 selects the 12-warp form, kept for comparison)
+// 25-32 columns.  0: 12 warps, 1 (default): + 8 drain warps, 2: + 8 drain warps and 16
+// converter warps (measured slower than 1: the kernel runs at the board's power limit there and
+// the extra warps cost clock).  Read per call: the tests compare the forms in one process.
+static int k6_drain_warps() {
+    const char* e = getenv("LTB200_K6_DW");
+    const int v = e == nullptr ? 1 : atoi(e);
+    return v < 0 ? 0 : v > 2 ? 2 : v;
+}
+
+// MMA-issuing warps: two with the drain-warp forms (+6 % at 25-32 columns at steady state), one
+// otherwise (no gain up to 24 columns, -1.6 % at 19); LTB200_K6_ISSUERS=1|2 overrides
+static int k6_issuers(bool drain_warps) {
+    if (const char* e = getenv("LTB200_K6_ISSUERS")) return atoi(e) == 2 ? 2 : 1;
+    return drain_warps ? 2 : 1;
+}
+
+// float32 tiles, N = 32 or 64: the lo(x) x lo(mask) products are dropped (LTB200_K6_THREE=0
+// keeps all four); a quarter of the tensor work for a term below 2^-21 |x||m| with lo(mask)
+// rounded to nearest, i.e. of either sign -- the measured error against float64 is unchanged to
+// three digits, and at the power limit the kernel runs 3-4 % faster
+static int k6_three(int n, bool is_float) {
+    if (!is_float || (n != 32 && n != 64)) return 0;
+    if (const char* e = getenv("LTB200_K6_THREE")) return atoi(e) != 0;
+    return 1;
+}
+
 // sig_sum[k] += exact integer frame sum (rounded once to float32)
 __global__ void k6_sig_finalize_kernel(const unsigned long long* __restrict__ acc,
                                        int64_t sig_size, float* __restrict__ sig_sum) {
@@ -785,6 +975,8 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
     p.debug = 0;
     p.sig_acc = nullptr;
     p.zero = 0u;
+    p.issuers = k6_issuers(sizeof(TIN) == 4 && n == 64 && k6_drain_warps() > 0);
+    p.three = k6_three(n, sizeof(TIN) == 4);
     if (const char* e = getenv("LTB200_K6_DEBUG")) p.debug = atoi(e);
     const int grid = (int)(p.n_items < sms ? p.n_items : sms);
     if (sig_sum != nullptr) {
@@ -823,7 +1015,13 @@ static int k6_run_group(const void* tile, int64_t n_frames, int64_t sig_size, in
             case 16: rc = k6_launch<16, TIN>(tmd, tmm, p, grid, st); break;
             case 32: rc = k6_launch<32, TIN>(tmd, tmm, p, grid, st); break;
             case 48: rc = k6_launch<48, TIN>(tmd, tmm, p, grid, st); break;
-            default: rc = k6_launch<64, TIN>(tmd, tmm, p, grid, st); break;
+            default:
+                switch (k6_drain_warps()) {
+                    case 0: rc = k6_launch<64, TIN, 0>(tmd, tmm, p, grid, st); break;
+                    case 1: rc = k6_launch<64, TIN, 1>(tmd, tmm, p, grid, st); break;
+                    default: rc = k6_launch<64, TIN, 2>(tmd, tmm, p, grid, st); break;
+                }
+                break;
         }
     }
     if (rc != LTB_OK) return rc;

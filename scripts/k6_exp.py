@@ -31,7 +31,7 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None
     data = engine.synth_fill((F, K), np.float32, 1, 'cuda')
     gb = F * K * 4 / 1e9
-    for M in (11, 19, 32):
+    for M in [int(a) for a in os.environ.get('K6_EXP_M', '11,19,32').split(',')]:
         masks = engine.synth_fill((M, K), np.float32, 2, 'cuda')
         if only == 'ncu':
             os.environ['LTB200_K6_DEBUG'] = '0'

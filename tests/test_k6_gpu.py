@@ -76,6 +76,73 @@ def test_tc_chain_lengths(eng, chain):
     assert_close_rel(out, f64_truth(data, masks), 5e-6)
 
 
+@pytest.mark.parametrize('n_masks', [25, 28, 32])
+@pytest.mark.parametrize('chain', [0, 2, 5])
+def test_tc_drain_warps(eng, n_masks, chain, monkeypatch):
+    # 25-32 columns: the accumulators are drained by eight extra warps (two-level sums of the
+    # chain totals); LTB200_K6_DW=0 is the 12-warp form with the converters draining.  Ragged
+    # frame count, a K split and a signal size that is not a multiple of the chain length.
+    F, K = 1100, 8192 + 96
+    data = synth.uniform_f32(0, F * K, 21).reshape(F, K)
+    masks = synth.uniform_f32(0, n_masks * K, 22).reshape(n_masks, K) - 0.25
+    truth, scale = f64_truth(data, masks), abs_scale(data, masks)
+    monkeypatch.setenv('LTB200_K6_DW', '0')
+    out_cv = eng.masks_dense_tc(dev(data), dev(masks), chain=chain).cpu().numpy()
+    tol = TIGHT if chain in (0, 1) else 5e-6
+    assert_close_rel(out_cv, truth, tol, scale)
+    outs = []
+    for mode in ('1', '2'):                  # 8 / 16 converter warps in front of the drain warps
+        monkeypatch.setenv('LTB200_K6_DW', mode)
+        out_dw = eng.masks_dense_tc(dev(data), dev(masks), chain=chain).cpu().numpy()
+        assert eng.last_kernel() == 6
+        assert_close_rel(out_dw, truth, tol, scale)
+        assert_close_rel(out_dw, out_cv, 2e-6, scale)
+        outs.append(out_dw)
+    assert np.array_equal(outs[0], outs[1])  # same arithmetic, different warp layout
+
+
+@pytest.mark.parametrize('n_masks', [11, 32])
+def test_tc_three_products(eng, n_masks, monkeypatch):
+    # 9-16 and 25-32 columns drop the lo(x) * lo(mask) products (LTB200_K6_THREE=0 keeps them):
+    # below 2^-21 |x||m| per term; constant masks are the worst case (lo(mask) of one sign)
+    F, K = 700, 16384
+    data = synth.uniform_f32(0, F * K, 31).reshape(F, K)
+    masks = synth.uniform_f32(0, n_masks * K, 32).reshape(n_masks, K) - 0.25
+    masks[0] = 0.3
+    masks[1] = -1.0 / 3.0
+    masks[2] = 1.0 + 2.0 ** -12 - 2.0 ** -23       # largest lo(mask) relative to the value
+    truth, scale = f64_truth(data, masks), abs_scale(data, masks)
+    outs = {}
+    for three in ('0', '1'):
+        monkeypatch.setenv('LTB200_K6_THREE', three)
+        outs[three] = eng.masks_dense_tc(dev(data), dev(masks)).cpu().numpy()
+        assert_close_rel(outs[three], truth, TIGHT, scale)
+    assert not np.array_equal(outs['0'], outs['1'])
+    # element-wise the two differ by their (independent) accumulation rounding; the dropped term
+    # itself shows as a shift of the column mean
+    assert_close_rel(outs['1'], outs['0'], 8e-7, scale)
+    shift = np.abs((outs['1'].astype(np.float64) - outs['0']).mean(axis=0)) / scale[0]
+    assert shift.max() <= 1.5e-7, f'mean shift {shift.max():.3e}'
+
+
+def test_tc_drain_warps_many_items(eng, monkeypatch):
+    # many items per CTA (the chain counter and its mbarrier parities run across items), then a
+    # long signal with few frames; accumulate into a strided view
+    monkeypatch.delenv('LTB200_K6_DW', raising=False)       # the default form
+    for F, K, M in ((148 * 256 * 3 + 77, 256, 32), (300, 65536, 29)):
+        data = synth.uniform_f32(0, F * K, 23).reshape(F, K)
+        masks = synth.uniform_f32(0, M * K, 24).reshape(M, K) - 0.5
+        out = torch.full((F, M + 3), 2.0, dtype=torch.float32, device='cuda')
+        view = out[:, 2:2 + M]
+        eng.masks_dense_tc(dev(data), dev(masks), out=view, accumulate=True)
+        res = out.cpu().numpy()
+        assert np.all(res[:, :2] == 2.0) and np.all(res[:, -1] == 2.0)
+        assert_close_rel(res[:, 2:2 + M] - 2.0, f64_truth(data, masks), TIGHT,
+                         abs_scale(data, masks))
+        again = eng.masks_dense_tc(dev(data), dev(masks)).cpu().numpy()
+        assert np.array_equal(again, eng.masks_dense_tc(dev(data), dev(masks)).cpu().numpy())
+
+
 def test_tc_strided_accumulate(eng):
     F, K, M = 530, 1024, 6
     big = synth.uniform_f32(0, F * (K + 64), 5).reshape(F, K + 64)
