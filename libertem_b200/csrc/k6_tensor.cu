@@ -44,10 +44,16 @@
 //   * the converters also drain the accumulators: tcgen05.ld of a finished chain is issued
 //     before the conversion of the next sub-stage and consumed after it; at the end of an item
 //     they store the (frames x columns) block.
+//   * N = 64 (25-32 columns): eight more warps drain the accumulators and warp 3 issues the
+//     MMAs of frame group 1 (template parameter DWM below); N = 32 / 64: the lo(x) MMAs read
+//     only the hi(mask) rows (three products, K6Params::three).
 // The frames never pass through the FP32 FMA pipe and the shared-memory operand traffic of the
 // tensor core is only the (small) mask tile, so the kernel stays HBM-bound up to 24 columns
-// (0.95-0.99 of the measured copy bandwidth) and reaches 0.85 at 32 columns, where the FFMA2
-// kernel is at 0.72 / 0.37.
+// (0.95-0.99 of the measured copy bandwidth in bursts) and reaches 0.90 at 32 columns, where the
+// FFMA2 kernel is at 0.72 / 0.37.  Sustained (seconds of back-to-back launches) the board sits
+// at its power limit and every form loses ~10 % to the SM clock.
+// Switches (read per call): LTB200_K6_CHAIN, LTB200_K6_DW (0/1/2), LTB200_K6_ISSUERS (1/2),
+// LTB200_K6_THREE (0/1), LTB200_K6_DEBUG (bring-up).
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
