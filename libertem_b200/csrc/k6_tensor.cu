@@ -522,13 +522,15 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                 }
             };
             int next_chain = 0;                      // first chain not yet drained
-            auto chain_end = [&](int c) {
-                const int e = (c + 1) * chain;
+            int chain_pos = 0;                       // i % chain, kept as a counter (no division)
+            int nc_start = 0;                        // next_chain * chain, likewise
+            auto next_end = [&]() {                  // last sub-stage of chain `next_chain`
+                const int e = nc_start + chain;
                 return (e < n_sub ? e : n_sub) - 1;
             };
             // drain every chain whose last sub-stage is <= done (their MMAs have completed)
             auto drain_upto = [&](int done) {
-                while (next_chain * chain < n_sub && chain_end(next_chain) <= done) {
+                while (nc_start < n_sub && next_end() <= done) {
                     const uint32_t d =
                         tmem_base + lane_sel + (uint32_t)((g * 2 + (next_chain & 1)) * N);
                     uint32_t v[N / 16][16];
@@ -543,6 +545,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                                   __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
                     level_up();
                     next_chain++;
+                    nc_start += chain;
                 }
             };
 
@@ -566,7 +569,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     // chain i/chain - 2 shares its accumulator with the chain that starts at
                     // sub-stage i: it must be drained before this sub-stage is handed to the MMAs
                     // (DW: the MMA warp waits for the drain warps instead)
-                    if (!DW && i % chain == 0 && i >= 2 * chain) {
+                    if (!DW && chain_pos == 0 && i >= 2 * chain) {
                         const int must = i - chain - 1;
                         if (must > known) {
                             const uint32_t itm = it - (uint32_t)(i - must);
@@ -579,14 +582,15 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                     // them after the conversion below (the load latency hides behind the ALU work)
                     uint32_t v[N / 16][16];
                     bool pend = false;
-                    if (!DW && known >= 0 && !(p.debug & 4) && next_chain * chain < n_sub &&
-                        chain_end(next_chain) <= known) {
+                    if (!DW && known >= 0 && !(p.debug & 4) && nc_start < n_sub &&
+                        next_end() <= known) {
                         const uint32_t d =
                             tmem_base + lane_sel + (uint32_t)((g * 2 + (next_chain & 1)) * N);
 #pragma unroll
                         for (int q = 0; q < N / 16; q++) tc_ld16(d + q * 16, v[q]);
                         pend = true;
                         next_chain++;
+                        nc_start += chain;
                     }
                     const uint32_t a =
                         tmem_base + lane_sel + (uint32_t)(K6_A_BASE + as * 128 + g * 64);
@@ -656,6 +660,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                         mbar_arrive(&a_full[as]);
                         if (h2 == HALVES - 1) mbar_arrive(&data_free[ds]);
                     }
+                    if (++chain_pos == chain) chain_pos = 0;
                 }
             }
             if constexpr (DW) continue;               // drained and stored by warps 12..19
