@@ -188,6 +188,19 @@ __device__ __forceinline__ void tc_ld_fencen(uint32_t (&r)[8]) {
                  :
                  : "memory");
 }
+// acc (two columns) += x * hi(mask) + x * lo(mask) of a drained chain: columns c, c + 1 and
+// nh + c, nh + c + 1 of the accumulator row, two packed adds (same rounding as the scalar form)
+template <int Q>
+__device__ __forceinline__ void k6_add_pair(float& a0, float& a1, const uint32_t (&v)[Q][16],
+                                            int c, int nh) {
+    const float2 t2 = __fadd2_rn(
+        make_float2(__uint_as_float(v[c / 16][c % 16]), __uint_as_float(v[c / 16][c % 16 + 1])),
+        make_float2(__uint_as_float(v[(nh + c) / 16][(nh + c) % 16]),
+                    __uint_as_float(v[(nh + c) / 16][(nh + c) % 16 + 1])));
+    const float2 a2 = __fadd2_rn(make_float2(a0, a1), t2);
+    a0 = a2.x;
+    a1 = a2.y;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -540,9 +553,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
                     for (int q = 0; q < N / 16; q++) tc_ld_fence16(v[q]);
 #pragma unroll
-                    for (int c = 0; c < NH; c++)
-                        acc[c] += __uint_as_float(v[c / 16][c % 16]) +
-                                  __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
+                    for (int c = 0; c < NH; c += 2) k6_add_pair(acc[c], acc[c + 1], v, c, NH);
                     level_up();
                     next_chain++;
                     nc_start += chain;
@@ -605,15 +616,19 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                                 const uint4 xv = x[h * 4 + j];
                                 const uint32_t e[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                                for (int t = 0; t < 4; t++) {
-                                    // hi = top 19 bits (a TF32 number); lo = x - hi exactly,
-                                    // rounded to nearest at TF32 precision by adding half a TF32
-                                    // ulp (kind::tf32 ignores the low 13 bits of its operands)
-                                    const uint32_t hb = e[t] & 0xFFFFE000u;
-                                    hi[j * 4 + t] = hb;
-                                    lo[j * 4 + t] = __float_as_uint(__uint_as_float(e[t]) -
-                                                                    __uint_as_float(hb)) +
-                                                    0x1000u;
+                                for (int t = 0; t < 4; t += 2) {
+                                    // hi = top 19 bits (a TF32 number); lo = x - hi exactly (two
+                                    // pixels per FADD2), rounded to nearest at TF32 precision by
+                                    // adding half a TF32 ulp (kind::tf32 ignores the low 13 bits)
+                                    const uint32_t h0 = e[t] & 0xFFFFE000u;
+                                    const uint32_t h1 = e[t + 1] & 0xFFFFE000u;
+                                    const float2 d = __fadd2_rn(
+                                        make_float2(__uint_as_float(e[t]), __uint_as_float(e[t + 1])),
+                                        make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
+                                    hi[j * 4 + t] = h0;
+                                    hi[j * 4 + t + 1] = h1;
+                                    lo[j * 4 + t] = __float_as_uint(d.x) + 0x1000u;
+                                    lo[j * 4 + t + 1] = __float_as_uint(d.y) + 0x1000u;
                                 }
                             }
                         } else {
@@ -648,9 +663,7 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
 #pragma unroll
                         for (int q = 0; q < N / 16; q++) tc_ld_fence16(v[q]);
 #pragma unroll
-                        for (int c = 0; c < NH; c++)
-                            acc[c] += __uint_as_float(v[c / 16][c % 16]) +
-                                      __uint_as_float(v[(NH + c) / 16][(NH + c) % 16]);
+                        for (int c = 0; c < NH; c += 2) k6_add_pair(acc[c], acc[c + 1], v, c, NH);
                         level_up();
                     }
                     tc_wait_st();
@@ -732,9 +745,15 @@ k6_tensor_kernel(const __grid_constant__ CUtensorMap tm_data,
                         tc_ld_fencen(vh);
                         tc_ld_fencen(vl);
 #pragma unroll
-                        for (int j = 0; j < DRAIN_COLS; j++)
-                            acc[h * DRAIN_COLS + j] +=
-                                __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+                        for (int j = 0; j < DRAIN_COLS; j += 2) {
+                            const float2 t2 = __fadd2_rn(
+                                make_float2(__uint_as_float(vh[j]), __uint_as_float(vh[j + 1])),
+                                make_float2(__uint_as_float(vl[j]), __uint_as_float(vl[j + 1])));
+                            const float2 a2 = __fadd2_rn(
+                                make_float2(acc[h * DRAIN_COLS + j], acc[h * DRAIN_COLS + j + 1]), t2);
+                            acc[h * DRAIN_COLS + j] = a2.x;
+                            acc[h * DRAIN_COLS + j + 1] = a2.y;
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
