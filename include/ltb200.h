@@ -107,6 +107,10 @@ LTB_API int ltb200_masks_dense_f64(const void* tile, int tile_dtype, int64_t n_f
  * The same dense contraction on the tensor cores (K6): tcgen05.mma kind::tf32 with the
  * split-TF32 scheme (hi/lo parts of tile and masks, float32 accumulation in TMEM cut into
  * chains of `chain` x 32 pixels that are summed in float32 registers; chain <= 0 -> default).
+ * 9-16 and 25-32 columns per pass use three of the four hi/lo products (lo(tile) x lo(mask),
+ * below 2^-21 |x||m| per term, is dropped); 25-32 columns run the 20-warp form with separate
+ * accumulator-drain warps.  Environment switches for A/B runs, read per call: LTB200_K6_CHAIN,
+ * LTB200_K6_THREE=0, LTB200_K6_DW=0|1|2, LTB200_K6_ISSUERS=1|2 (csrc/k6_tensor.cu).
  * float32 tiles, sig_size % 4 == 0, 16-byte aligned rows.  ltb200_masks_dense routes wide
  * float32 stacks here by itself (see ltb200_set_k1_variant); this entry point is the
  * explicit form used by the parity tests.  Returns LTB_ERR_UNSUPPORTED for shapes the TMA /
