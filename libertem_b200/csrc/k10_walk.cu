@@ -811,6 +811,16 @@ extern "C" int ltb200_group_masks_walk(const float* tile, int64_t n_frames, int6
     int dev = 0;
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
+        // setmaxnreg re-deals the CTA's registers (768 threads x the compiled count) as 56 / 144 /
+        // 40 per warpgroup pair: a build with fewer compiled registers would block in
+        // setmaxnreg.inc for ever -- refuse it instead
+        cudaFuncAttributes fa;
+        LTB_CUDA_CHECK(cudaFuncGetAttributes(&fa, k10_walk_kernel));
+        if (fa.numRegs * K10_THREADS < 256 * (56 + 144 + 40)) {
+            set_error("group_masks_walk: kernel compiled with %d registers per thread, the "
+                      "setmaxnreg layout needs 80", fa.numRegs);
+            return LTB_ERR_UNSUPPORTED;
+        }
         LTB_CUDA_CHECK(cudaFuncSetAttribute(k10_walk_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)K10Smem::TOTAL));

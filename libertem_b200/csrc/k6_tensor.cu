@@ -288,8 +288,9 @@ struct K6Smem {
 // chains are numbered over the lifetime of the CTA, so every parity is (chain / 2) & 1.
 // DWM = 2 additionally doubles the converter warps (4..19, drain warps 20..27): the two warps
 // of a frame-row quarter split the 32 pixels of the sub-stage, which halves the instruction
-// stream in front of every A-operand hand-over (the bound at 25-32 columns once the drain is
-// gone: ncu warp-state samples sit on the conversion ALU code, not on the mbarrier waits).
+// stream in front of every A-operand hand-over.  Validated (tests/test_k6_gpu.py) but measured
+// SLOWER than DWM = 1 (0.73-0.75 vs 0.76-0.79 sustained at 25-32 columns): at the board's power
+// limit more resident warps cost SM clock; kept as LTB200_K6_DW=2 for comparison.
 constexpr int K6_DRAIN_WARPS = 8;
 __host__ __device__ constexpr int k6_threads(int base, int dwm) {
     return base + (dwm > 0 ? K6_DRAIN_WARPS * 32 : 0) + (dwm == 2 ? K6_CONV_WARPS * 32 : 0);
@@ -898,6 +899,19 @@ static int k6_launch(const CUtensorMap& tmd, const CUtensorMap& tmm, const K6Par
     LTB_CUDA_CHECK(cudaGetDevice(&dev));
     static thread_local int configured_dev = -1;
     if (configured_dev != dev) {
+        if constexpr (DWM > 0) {
+            // setmaxnreg re-deals threads x compiled registers (40 / 88 / 128 or 40 / 64 / 104
+            // per role): with fewer compiled registers setmaxnreg.inc would block for ever
+            cudaFuncAttributes fa;
+            LTB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+            const int need = DWM == 1 ? 128 * 40 + 256 * 88 + 256 * 128
+                                      : 128 * 40 + 512 * 64 + 256 * 104;
+            if (fa.numRegs * k6_threads(K6In<TIN>::THREADS, DWM) < need) {
+                set_error("masks_dense_tc: drain-warp form compiled with %d registers per "
+                          "thread; use LTB200_K6_DW=0", fa.numRegs);
+                return LTB_ERR_UNSUPPORTED;
+            }
+        }
         LTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
         configured_dev = dev;
